@@ -1,0 +1,225 @@
+/*
+ * rrtk.h -- C ABI of librrtk.so: the B200 (sm_100a) tree-expansion hot path of rrtplanner.
+ *
+ * The reference (rland93/rrtplanner) has no FFI layer: its hot path is a set of Python methods on
+ * the planner classes of rrtplanner/rrt.py.  Each entry point below names the reference interface it
+ * replaces (file:line in /root/reference).  The Python classes in rrtplanner_b200/rrt.py bind these
+ * symbols with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is caller-owned.  "d_" parameters are DEVICE pointers,
+ *     "h_" parameters are HOST pointers (pinned memory makes the copies asynchronous).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer entry
+ *     points only enqueue work on it; host-pointer entry points synchronise it before returning.
+ *   - every function returns RRTK_OK (0) or a negative rrtk_status; rrtk_last_error() gives text.
+ *   - occupancy grids are (W, H) arrays indexed og[x*H + y] exactly like the reference's og[x, y]
+ *     (rrt.py:218); any non-zero cell is an obstacle (rrt.py:191).
+ *   - coordinates are int32 in the ABI; the planner kernels require 0 <= x < W <= 16384,
+ *     0 <= y < H <= 16384 and n <= 65534.
+ *
+ * Bit grid layout ("tiled"): the grid is cut into 32x32-cell tiles, tile (tx, ty) = (x>>5, y>>5),
+ * tiles stored row-major over (tx, ty) with TY = ceil(H/32) tiles per row; one tile is 32
+ * consecutive uint32 words (128 bytes, one L2 line); word (x & 31) of a tile holds the 32 cells
+ * y = 32*ty .. 32*ty+31 of row x, bit (y & 31).  Cells outside (W, H) are set (obstacle).
+ */
+#ifndef RRTK_H
+#define RRTK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRTK_VERSION 100
+
+typedef enum {
+    RRTK_OK = 0,
+    RRTK_ERR_INVALID = -1,   /* bad argument (NULL pointer, size out of range, point outside grid) */
+    RRTK_ERR_CAPACITY = -2,  /* problem does not fit the kernel's shared-memory / index limits */
+    RRTK_ERR_CUDA = -3,      /* a CUDA runtime call failed; see rrtk_last_error() */
+    RRTK_ERR_NODEVICE = -4   /* no CUDA device visible */
+} rrtk_status;
+
+typedef enum {
+    RRTK_STANDARD = 0,       /* RRTStandard.plan      rrt.py:386-447 */
+    RRTK_STAR = 1,           /* RRTStar.plan          rrt.py:466-556 */
+    RRTK_INFORMED = 2        /* RRTStarInformed.plan  rrt.py:653-758 */
+} rrtk_kind;
+
+/* one plan = one (world, start, goal) triple; 64 bytes */
+typedef struct {
+    int32_t world;           /* index of the bit grid this plan runs on */
+    int32_t start_x, start_y;
+    int32_t goal_x, goal_y;
+    int32_t reserved[3];
+    double rot[4];           /* row-major 2x2 of rotation_to_world_frame (rrt.py:601-613); informed only */
+} rrtk_plan_desc;
+
+/* per-plan statistics, int64 slots (rrtk_plan_batch writes RRTK_STAT_COUNT of them per plan) */
+enum {
+    RRTK_STAT_J = 0,           /* filled vertices before goal connection (the reference's j) */
+    RRTK_STAT_VGOAL,           /* goal vertex id: j when connected, else 0 (rrt.py:319,330-331) */
+    RRTK_STAT_FOUND,           /* 1 when the goal row was appended */
+    RRTK_STAT_CHECKS,          /* collision checks executed on the device (parallel form) */
+    RRTK_STAT_CELLS,           /* grid cells those checks tested (first hit inclusive) */
+    RRTK_STAT_FIRST_SOL_ITER,  /* informed: iteration of the first solution vertex, else -1 */
+    RRTK_STAT_ELL_ITERS,       /* informed: iterations sampled from the ellipse */
+    RRTK_STAT_NN_PAIRS,        /* sum over iterations of filled vertices scanned */
+    RRTK_STAT_RING_MEMBERS,    /* sum over accepted iterations of |within(r_rewire)| */
+    RRTK_STAT_ACCEPTED,        /* accepted samples */
+    RRTK_STAT_RESERVED0,
+    RRTK_STAT_RESERVED1,
+    RRTK_STAT_COUNT
+};
+
+int rrtk_version(void);
+const char *rrtk_last_error(void);
+/* number of visible CUDA devices (0 if none; never fails) */
+int rrtk_device_count(void);
+int rrtk_set_device(int device);
+/* SM count and opt-in shared memory per block of the current device */
+int rrtk_device_info(int *sm_count, int *smem_optin_bytes);
+
+/* ---- occupancy grids ------------------------------------------------------------------------- */
+/* uint32 words of one tiled bit grid */
+size_t rrtk_grid_words(int W, int H);
+
+/* K0.  Replaces the `og[x, y] != 0` test of rrt.py:218 by a packed copy: d_og is nworlds
+ * consecutive (W,H) uint8 grids, d_bits receives nworlds * rrtk_grid_words(W,H) words. */
+int rrtk_pack_grid(const uint8_t *d_og, int nworlds, int W, int H, uint32_t *d_bits, void *stream);
+
+/* free-space index for RRT.sample_all_free (rrt.py:64,231-240): d_rowcum[w*(W+1) + x] = number of
+ * free cells in rows < x of world w (so entry W is nfree, the size of the reference's `free`). */
+int rrtk_free_rows(const uint32_t *d_bits, int nworlds, int W, int H, int32_t *d_rowcum, void *stream);
+
+/* Synthetic worlds (measurement fixture; oggen.py:7-45 semantics, integer value-noise fBm that is
+ * bit-identical to rrtplanner_b200/worlds.py).  World i uses seed seeds[i].  d_scratch must hold
+ * nworlds * W * H int32 + 2 * nworlds int32. */
+int rrtk_gen_worlds(const int32_t *d_seeds, int nworlds, int W, int H, int thresh_permille,
+                    int32_t *d_scratch, uint8_t *d_og, void *stream);
+
+/* ---- K1: RRT.collisionfree (rrt.py:183-229), batched ------------------------------------------- */
+/* d_segs: nseg x (ax, ay, bx, by) int32, all points inside the grid.  d_world: optional per-segment
+ * world index (NULL = world 0).  d_free[s] = 1 iff the walk a->b meets no obstacle (both ends
+ * included).  d_cells[s] (optional) = number of cells the reference's loop reads before returning
+ * (index of first obstacle + 1, or max(|dx|,|dy|) + 1). */
+int rrtk_collision_segments(const uint32_t *d_bits, int W, int H, const int32_t *d_segs,
+                            const int32_t *d_world, int64_t nseg, uint8_t *d_free, int32_t *d_cells,
+                            void *stream);
+
+/* ---- K2: RRT.near(points, x)[0] (rrt.py:131-155), batched, pinned tie rule (lowest index) ------- */
+/* d_pts: npts x (x, y) int32.  d_queries: nq x (x, y).  d_count (optional): query q only sees the
+ * first d_count[q] points (the filled prefix of the tree); NULL = all npts.  d_idx[q] = nearest
+ * vertex, d_d2[q] (optional) = its exact squared distance. */
+int rrtk_nearest_batch(const int32_t *d_pts, int npts, const int32_t *d_queries, const int32_t *d_count,
+                       int nq, int32_t *d_idx, int64_t *d_d2, void *stream);
+
+/* same for floating-point vertices / queries (numpy semantics: key = sqrt(dx*dx + dy*dy) in IEEE
+ * double, no contraction); d_dist[q] (optional) = that key */
+int rrtk_nearest_batch_f64(const double *d_pts, int npts, const double *d_queries, const int32_t *d_count,
+                           int nq, int32_t *d_idx, double *d_dist, void *stream);
+
+/* ---- K3: RRT.within(points, x, r) (rrt.py:157-181), batched --------------------------------------- */
+/* d_out[q*cap .. ] receives the ascending indices with d^2 < r*r (strict), d_len[q] their number
+ * (may exceed cap: only the first cap are stored). */
+int rrtk_within_batch(const int32_t *d_pts, int npts, const int32_t *d_queries, const int32_t *d_count,
+                      int nq, double r, int cap, int32_t *d_out, int32_t *d_len, void *stream);
+
+/* floating-point form: dx*dx + dy*dy < r*r in IEEE double -- the reference's own known-answer test
+ * calls within() with x = [0.5, 0.5] (tests/test_rrt.py:116-119) */
+int rrtk_within_batch_f64(const double *d_pts, int npts, const double *d_queries, const int32_t *d_count,
+                          int nq, double r, int cap, int32_t *d_out, int32_t *d_len, void *stream);
+
+/* distance keys for the full ordering RRT.near returns (rrt.py:150-155): d_d2[i] = |pts[i]-q|^2 */
+int rrtk_dist2(const int32_t *d_pts, int npts, int qx, int qy, int64_t *d_d2, void *stream);
+int rrtk_dist_f64(const double *d_pts, int npts, double qx, double qy, double *d_dist, void *stream);
+/* ascending stable ordering of int64 keys (ties: lowest index first) -- the pinned np.argsort */
+int rrtk_argsort_i64(const int64_t *d_keys, int n, int32_t *d_perm, void *d_scratch, size_t scratch_bytes,
+                     void *stream);
+size_t rrtk_argsort_scratch_bytes(int n);
+
+/* ---- sample streams: RRT.sample_all_free with numpy's PCG64 (rrt.py:85,231-240) ------------------- */
+/* h_state: per plan 4 x uint64 = PCG64 {state_hi, state_lo, inc_hi, inc_lo} as numpy's
+ * default_rng(seed).bit_generator.state reports them.  Writes n samples (x, y) int16 per plan:
+ * sample i = free[integers(0, nfree)] of that plan's world. */
+int rrtk_sample_streams(const uint32_t *d_bits, const int32_t *d_rowcum, int W, int H,
+                        const rrtk_plan_desc *d_plans, int nplans, const uint64_t *d_state, int n,
+                        int16_t *d_samples, void *stream);
+
+/* ---- K7: the plan() loops (rrt.py:418-437, 498-548, 690-748) + go2goal (rrt.py:284-332) ---------- */
+/*
+ * Runs nplans independent plans, one thread block each, tree and bit grid resident on chip.
+ *   d_bits     nworlds tiled bit grids (rrtk_pack_grid)
+ *   d_plans    nplans descriptors
+ *   d_samples  nplans x n x (x, y) int16: sample i of plan p is what sample_all_free returns in
+ *              iteration i (rrt.py:421,502,696)
+ *   d_balls    informed only: nplans x n x 2 doubles, the unitball() point (rrt.py:579-587) used in
+ *              iteration i if that iteration samples the ellipse; may be NULL for other kinds.
+ *              Informed with d_balls == NULL is a probe run: each plan stops at its first solution
+ *              vertex (RRTK_STAT_FIRST_SOL_ITER tells the caller where the ellipse phase starts)
+ *   outputs, (n + 1) rows per plan -- row j is the goal vertex when connected (rrt.py:319-325):
+ *   d_pts      int16 (x, y); rows the reference leaves unfilled hold (-32768, -32768)
+ *   d_cost     float64 cost-to-come (vcosts); +inf in unfilled rows
+ *   d_parent   int32 parent vertex; -1 for the root and unfilled rows
+ *   d_stats    RRTK_STAT_COUNT int64 per plan
+ *   d_ell_c    informed only (else NULL): d_ell_c[p*(n+1) + j] = cbest of the last ellipse sample
+ *              drawn while the tree had j vertices (rrt.py:698-701), NaN where none
+ * r_rewire / r_goal as in the constructors (rrt.py:454-464, 563-577).  `threads` = block size
+ * (0 = library default).
+ */
+int rrtk_plan_batch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans,
+                    int nplans, int n, double r_rewire, double r_goal, const int16_t *d_samples,
+                    const double *d_balls, int16_t *d_pts, double *d_cost, int32_t *d_parent,
+                    int64_t *d_stats, double *d_ell_c, int threads, void *stream);
+
+/* shared memory one plan block needs and how many blocks fit on one SM (for sizing / reporting) */
+int rrtk_plan_footprint(int kind, int W, int H, int n, int threads, int *smem_bytes, int *blocks_per_sm);
+
+/* root -> goal vertex paths (RRT.route2gv, rrt.py:87-107 on a tree = parent walk): d_path gets up
+ * to cap vertex ids per plan, root first; d_len the path length (0 if vgoal has no parent chain) */
+int rrtk_extract_paths(const int32_t *d_parent, const int64_t *d_stats, int nplans, int n, int cap,
+                       int32_t *d_path, int32_t *d_len, void *stream);
+
+/* ---- host-buffer entry points (the call a Python planner object makes; copies inside) ------------ */
+typedef struct rrtk_ctx rrtk_ctx;    /* owns device scratch; one per planner object / thread */
+int rrtk_create(rrtk_ctx **out);
+int rrtk_destroy(rrtk_ctx *ctx);
+
+/* upload nworlds (W,H) uint8 grids, pack them (K0) and build the free-space index; replaces the
+ * state RRT.__init__ / RRT.set_og keep (rrt.py:64-65, 261-272).  h_nfree (optional) receives the
+ * number of free cells per world. */
+int rrtk_ctx_set_grids(rrtk_ctx *ctx, const uint8_t *h_og, int nworlds, int W, int H, int32_t *h_nfree);
+
+/* full plan() from host memory: H2D of descriptors (+ samples / balls / PCG64 states), K7, D2H of
+ * the trees.  Exactly one of h_samples / h_state must be non-NULL (explicit stream vs. seed mode).
+ * Output arrays as in rrtk_plan_batch but in host memory. */
+int rrtk_ctx_plan(rrtk_ctx *ctx, int kind, const rrtk_plan_desc *h_plans, int nplans, int n,
+                  double r_rewire, double r_goal, const int16_t *h_samples, const uint64_t *h_state,
+                  const double *h_balls, int16_t *h_pts, double *h_cost, int32_t *h_parent,
+                  int64_t *h_stats, double *h_ell_c);
+
+/* the sample stream a planner seeded with h_state would draw (seed mode of rrtk_ctx_plan, exposed
+ * so RRT.sample_all_free can be served from the same generator) */
+int rrtk_ctx_samples(rrtk_ctx *ctx, const rrtk_plan_desc *h_plans, int nplans, int n, const uint64_t *h_state,
+                     int16_t *h_samples);
+
+/* host-buffer forms of K1-K3 on the context's world `world` */
+int rrtk_ctx_collision(rrtk_ctx *ctx, int world, const int32_t *h_segs, int64_t nseg, uint8_t *h_free,
+                       int32_t *h_cells);
+int rrtk_ctx_nearest(rrtk_ctx *ctx, const int32_t *h_pts, int npts, const int32_t *h_queries, int nq,
+                     int32_t *h_idx, int64_t *h_d2);
+int rrtk_ctx_within(rrtk_ctx *ctx, const int32_t *h_pts, int npts, const int32_t *h_queries, int nq,
+                    double r, int cap, int32_t *h_out, int32_t *h_len);
+int rrtk_ctx_near_order(rrtk_ctx *ctx, const int32_t *h_pts, int npts, int qx, int qy, int32_t *h_perm);
+int rrtk_ctx_nearest_f64(rrtk_ctx *ctx, const double *h_pts, int npts, const double *h_queries, int nq,
+                         int32_t *h_idx, double *h_dist);
+int rrtk_ctx_within_f64(rrtk_ctx *ctx, const double *h_pts, int npts, const double *h_queries, int nq,
+                        double r, int cap, int32_t *h_out, int32_t *h_len);
+int rrtk_ctx_near_order_f64(rrtk_ctx *ctx, const double *h_pts, int npts, double qx, double qy, int32_t *h_perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRTK_H */

@@ -1,0 +1,239 @@
+"""ctypes binding of librrtk.so (C ABI in include/rrtk.h).
+
+There is no CPU fallback: if the library has not been built, or no CUDA device is visible when a
+kernel is needed, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librrtk.so")
+
+KIND_STANDARD, KIND_STAR, KIND_INFORMED = 0, 1, 2
+STAT_NAMES = ("j", "vgoal", "found", "checks", "cells", "first_solution_iter", "ellipse_iters",
+              "nn_pairs", "ring_members", "accepted", "reserved0", "reserved1")
+STAT_COUNT = len(STAT_NAMES)
+
+# numpy mirror of rrtk_plan_desc (64 bytes)
+PLAN_DESC = np.dtype([("world", "<i4"), ("start_x", "<i4"), ("start_y", "<i4"), ("goal_x", "<i4"),
+                      ("goal_y", "<i4"), ("reserved", "<i4", (3,)), ("rot", "<f8", (4,))], align=True)
+assert PLAN_DESC.itemsize == 64
+
+
+class RRTKError(RuntimeError):
+    pass
+
+
+_vp, _i, _i64, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/rrtk.h declares is listed (tests check this)
+SIGNATURES = {
+    "rrtk_version": (_i, []),
+    "rrtk_last_error": (C.c_char_p, []),
+    "rrtk_device_count": (_i, []),
+    "rrtk_set_device": (_i, [_i]),
+    "rrtk_device_info": (_i, [_vp, _vp]),
+    "rrtk_grid_words": (_sz, [_i, _i]),
+    "rrtk_pack_grid": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rrtk_free_rows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rrtk_gen_worlds": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "rrtk_collision_segments": (_i, [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "rrtk_nearest_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rrtk_nearest_batch_f64": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rrtk_within_batch": (_i, [_vp, _i, _vp, _vp, _i, _d, _i, _vp, _vp, _vp]),
+    "rrtk_within_batch_f64": (_i, [_vp, _i, _vp, _vp, _i, _d, _i, _vp, _vp, _vp]),
+    "rrtk_dist2": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rrtk_dist_f64": (_i, [_vp, _i, _d, _d, _vp, _vp]),
+    "rrtk_argsort_i64": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
+    "rrtk_argsort_scratch_bytes": (_sz, [_i]),
+    "rrtk_sample_streams": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "rrtk_plan_batch": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rrtk_plan_footprint": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
+    "rrtk_extract_paths": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rrtk_create": (_i, [_vp]),
+    "rrtk_destroy": (_i, [_vp]),
+    "rrtk_ctx_set_grids": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rrtk_ctx_plan": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rrtk_ctx_samples": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "rrtk_ctx_collision": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
+    "rrtk_ctx_nearest": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "rrtk_ctx_nearest_f64": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
+    "rrtk_ctx_within": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp]),
+    "rrtk_ctx_within_f64": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp]),
+    "rrtk_ctx_near_order": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rrtk_ctx_near_order_f64": (_i, [_vp, _vp, _i, _d, _d, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises ImportError if it was never built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build the CUDA extension first (python -m rrtplanner_b200.build). "
+                "rrtplanner_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc == 0:
+        return
+    msg = lib().rrtk_last_error().decode("utf-8", "replace")
+    text = f"{what}: {msg}" if what else msg
+    if rc == -1:
+        raise ValueError(text)
+    if rc == -2:
+        raise MemoryError(text)
+    raise RRTKError(text)
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def pcg64_state_words(rng: np.random.Generator) -> np.ndarray:
+    """{state_hi, state_lo, inc_hi, inc_lo} of a fresh PCG64 generator, for rrtk_sample_streams."""
+    st = rng.bit_generator.state
+    if st["bit_generator"] != "PCG64" or st["has_uint32"]:
+        raise ValueError("device sampling needs a PCG64 generator with no buffered 32-bit half")
+    s, inc = st["state"]["state"], st["state"]["inc"]
+    m = (1 << 64) - 1
+    return np.array([s >> 64, s & m, inc >> 64, inc & m], dtype=np.uint64)
+
+
+class Context:
+    """Owner of one rrtk_ctx (device scratch + stream).  Created on first use; needs a GPU."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib().rrtk_create(C.byref(self._h)), "rrtk_create")
+        self.shape = None
+        self.nworlds = 0
+
+    def close(self):
+        if self._h:
+            lib().rrtk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- grids ---------------------------------------------------------------------------------
+    def set_grids(self, og_u8: np.ndarray) -> np.ndarray:
+        """og_u8: (nworlds, W, H) uint8, non-zero = obstacle.  Returns nfree per world."""
+        og_u8 = np.ascontiguousarray(og_u8, dtype=np.uint8)
+        nw, W, H = og_u8.shape
+        nfree = np.empty(nw, dtype=np.int32)
+        check(lib().rrtk_ctx_set_grids(self._h, ptr(og_u8), nw, W, H, ptr(nfree)), "rrtk_ctx_set_grids")
+        self.shape, self.nworlds = (W, H), nw
+        return nfree
+
+    # -- plans ---------------------------------------------------------------------------------
+    def plan(self, kind, desc, n, r_rewire=0.0, r_goal=0.0, samples=None, states=None, balls=None):
+        nplans = desc.shape[0]
+        desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
+        rows = nplans * (n + 1)
+        pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
+        cost = np.empty((nplans, n + 1), dtype=np.float64)
+        parent = np.empty((nplans, n + 1), dtype=np.int32)
+        stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
+        ell = np.empty((nplans, n + 1), dtype=np.float64) if kind == KIND_INFORMED else None
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, dtype=np.int16)
+            assert samples.shape == (nplans, n, 2), samples.shape
+        if states is not None:
+            states = np.ascontiguousarray(states, dtype=np.uint64)
+            assert states.shape == (nplans, 4)
+        if balls is not None:
+            balls = np.ascontiguousarray(balls, dtype=np.float64)
+            assert balls.shape == (nplans, n, 2)
+        check(lib().rrtk_ctx_plan(self._h, kind, ptr(desc), nplans, n, float(r_rewire), float(r_goal), ptr(samples),
+                                  ptr(states), ptr(balls), ptr(pts), ptr(cost), ptr(parent), ptr(stats), ptr(ell)),
+              "rrtk_ctx_plan")
+        del rows
+        return pts, cost, parent, stats, ell
+
+    def samples(self, desc, n, states):
+        nplans = desc.shape[0]
+        desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
+        states = np.ascontiguousarray(states, dtype=np.uint64)
+        out = np.empty((nplans, n, 2), dtype=np.int16)
+        check(lib().rrtk_ctx_samples(self._h, ptr(desc), nplans, n, ptr(states), ptr(out)), "rrtk_ctx_samples")
+        return out
+
+    # -- queries -------------------------------------------------------------------------------
+    def collision(self, segs, world=0, cells=False):
+        segs = np.ascontiguousarray(segs, dtype=np.int32).reshape(-1, 4)
+        free = np.empty(segs.shape[0], dtype=np.uint8)
+        ncell = np.empty(segs.shape[0], dtype=np.int32) if cells else None
+        check(lib().rrtk_ctx_collision(self._h, world, ptr(segs), segs.shape[0], ptr(free), ptr(ncell)), "rrtk_ctx_collision")
+        return (free.astype(bool), ncell) if cells else free.astype(bool)
+
+    def nearest(self, pts, queries):
+        if np.issubdtype(pts.dtype, np.integer) and np.issubdtype(queries.dtype, np.integer):
+            p = np.ascontiguousarray(pts, dtype=np.int32)
+            q = np.ascontiguousarray(queries, dtype=np.int32).reshape(-1, 2)
+            idx = np.empty(q.shape[0], dtype=np.int32)
+            key = np.empty(q.shape[0], dtype=np.int64)
+            check(lib().rrtk_ctx_nearest(self._h, ptr(p), p.shape[0], ptr(q), q.shape[0], ptr(idx), ptr(key)), "rrtk_ctx_nearest")
+        else:
+            p = np.ascontiguousarray(pts, dtype=np.float64)
+            q = np.ascontiguousarray(queries, dtype=np.float64).reshape(-1, 2)
+            idx = np.empty(q.shape[0], dtype=np.int32)
+            key = np.empty(q.shape[0], dtype=np.float64)
+            check(lib().rrtk_ctx_nearest_f64(self._h, ptr(p), p.shape[0], ptr(q), q.shape[0], ptr(idx), ptr(key)),
+                  "rrtk_ctx_nearest_f64")
+        return idx, key
+
+    def within(self, pts, queries, r, cap=None):
+        integer = np.issubdtype(pts.dtype, np.integer) and np.issubdtype(np.asarray(queries).dtype, np.integer)
+        p = np.ascontiguousarray(pts, dtype=np.int32 if integer else np.float64)
+        q = np.ascontiguousarray(queries, dtype=p.dtype).reshape(-1, 2)
+        cap = p.shape[0] if cap is None else cap
+        out = np.empty((q.shape[0], cap), dtype=np.int32)
+        ln = np.empty(q.shape[0], dtype=np.int32)
+        fn = lib().rrtk_ctx_within if integer else lib().rrtk_ctx_within_f64
+        check(fn(self._h, ptr(p), p.shape[0], ptr(q), q.shape[0], float(r), cap, ptr(out), ptr(ln)), "rrtk_ctx_within")
+        return out, ln
+
+    def near_order(self, pts, x):
+        integer = np.issubdtype(pts.dtype, np.integer) and np.issubdtype(np.asarray(x).dtype, np.integer)
+        p = np.ascontiguousarray(pts, dtype=np.int32 if integer else np.float64)
+        perm = np.empty(p.shape[0], dtype=np.int32)
+        if integer:
+            check(lib().rrtk_ctx_near_order(self._h, ptr(p), p.shape[0], int(x[0]), int(x[1]), ptr(perm)), "rrtk_ctx_near_order")
+        else:
+            check(lib().rrtk_ctx_near_order_f64(self._h, ptr(p), p.shape[0], float(x[0]), float(x[1]), ptr(perm)),
+                  "rrtk_ctx_near_order_f64")
+        return perm
+
+
+_shared_ctx = None
+
+
+def shared_context() -> Context:
+    """Process-wide context used by the static-method wrappers (near / within / collisionfree)."""
+    global _shared_ctx
+    if _shared_ctx is None:
+        _shared_ctx = Context()
+    return _shared_ctx

@@ -1,0 +1,240 @@
+"""Batched planning: thousands of independent plans (worlds x start/goal pairs) per launch.
+
+Not in the reference (its ``plan()`` handles one query); this is the batched driver the north star
+asks for.  Every plan is what ``RRTStandard / RRTStar / RRTStarInformed(og, n, ...).plan(xstart, xgoal)``
+(rrt.py:386-447, 466-556, 653-758) would compute for its world and sample stream; plans never
+interact, so a batch shards across GPUs by plan index with no collective (``shard`` below).
+
+Two layers:
+
+* ``DeviceBatch`` -- buffers resident in HBM (torch owns the memory and the stream), kernels
+  enqueued through the device-pointer entry points of the C ABI.  Used by ``bench.py`` for the
+  kernel-side throughput and by the multi-GPU driver.
+* ``plan_batch`` -- host arrays in, host arrays out, through the host-buffer C-ABI call
+  ``rrtk_ctx_plan`` (the end-to-end path).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+KINDS = {"standard": _lib.KIND_STANDARD, "star": _lib.KIND_STAR, "informed": _lib.KIND_INFORMED,
+         "RRTStandard": _lib.KIND_STANDARD, "RRTStar": _lib.KIND_STAR, "RRTStarInformed": _lib.KIND_INFORMED}
+
+
+def make_desc(world_ids, starts, goals, rots=None) -> np.ndarray:
+    """Array of rrtk_plan_desc from per-plan world index, start (P,2), goal (P,2), rotation (P,2,2)."""
+    starts = np.asarray(starts).reshape(-1, 2)
+    goals = np.asarray(goals).reshape(-1, 2)
+    d = np.zeros(starts.shape[0], dtype=_lib.PLAN_DESC)
+    d["world"] = np.asarray(world_ids, dtype=np.int32)
+    d["start_x"], d["start_y"] = starts[:, 0], starts[:, 1]
+    d["goal_x"], d["goal_y"] = goals[:, 0], goals[:, 1]
+    if rots is not None:
+        d["rot"] = np.asarray(rots, dtype=np.float64).reshape(-1, 4)
+    return d
+
+
+def seed_states(seeds: Sequence[int]) -> np.ndarray:
+    """PCG64 start states of ``np.random.default_rng(seed)`` (rrt.py:85) for a list of seeds."""
+    return np.stack([_lib.pcg64_state_words(np.random.default_rng(int(s))) for s in seeds])
+
+
+def shard(nplans: int, rank: int, world_size: int) -> range:
+    """Contiguous plan-index range of ``rank`` (plans are independent: no data-path collective)."""
+    per = (nplans + world_size - 1) // world_size
+    return range(min(rank * per, nplans), min((rank + 1) * per, nplans))
+
+
+@dataclass
+class BatchResult:
+    """Host copies of the trees: rows 0..n per plan, laid out as rrtk_plan_batch documents."""
+    pts: np.ndarray        # (P, n+1, 2) int16, (-32768, -32768) in unfilled rows
+    cost: np.ndarray       # (P, n+1) float64, inf in unfilled rows
+    parent: np.ndarray     # (P, n+1) int32, -1 for root / unfilled
+    stats: np.ndarray      # (P, STAT_COUNT) int64
+    ell_c: Optional[np.ndarray] = None
+
+    def stat(self, name: str) -> np.ndarray:
+        return self.stats[:, _lib.STAT_NAMES.index(name)]
+
+    def path(self, p: int):
+        """Vertex ids root -> goal vertex of plan p."""
+        v = int(self.stats[p, 1])
+        out = [v]
+        while v > 0:
+            v = int(self.parent[p, v])
+            out.append(v)
+        return out[::-1]
+
+    def path_cost(self, p: int) -> float:
+        return float(self.cost[p, int(self.stats[p, 1])])
+
+
+def plan_batch(kind, ogs, n, starts, goals, world_ids=None, r_rewire=0.0, r_goal=0.0, samples=None, seeds=None,
+               balls=None, rots=None, ctx: Optional[_lib.Context] = None) -> BatchResult:
+    """End-to-end batched plan() from host arrays through ``rrtk_ctx_plan``.
+
+    ogs: (nworlds, W, H) array, non-zero = obstacle.  Either ``samples`` (P, n, 2) -- the explicit
+    sample streams -- or ``seeds`` (P,) -- plan p draws what a planner built with seed=seeds[p] would.
+    """
+    k = KINDS[kind] if isinstance(kind, str) else int(kind)
+    ogs = np.asarray(ogs)
+    if ogs.ndim == 2:
+        ogs = ogs[None]
+    starts = np.asarray(starts).reshape(-1, 2)
+    nplans = starts.shape[0]
+    if world_ids is None:
+        world_ids = np.arange(nplans) % ogs.shape[0]
+    own = ctx is None
+    ctx = ctx or _lib.Context()
+    try:
+        ctx.set_grids((ogs != 0).astype(np.uint8))
+        desc = make_desc(world_ids, starts, goals, rots)
+        states = None if seeds is None else seed_states(seeds)
+        pts, cost, parent, stats, ell = ctx.plan(k, desc, n, r_rewire, r_goal, samples=samples, states=states, balls=balls)
+    finally:
+        if own:
+            ctx.close()
+    return BatchResult(pts, cost, parent, stats, ell)
+
+
+class DeviceBatch:
+    """HBM-resident batch on one GPU.  torch is plumbing only: allocation, stream, copies."""
+
+    def __init__(self, kind, W: int, H: int, n: int, r_rewire=0.0, r_goal=0.0, device=None, threads: int = 0):
+        import torch
+
+        self.torch = torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceBatch needs a CUDA device (no CPU fallback)")
+        self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.kind = KINDS[kind] if isinstance(kind, str) else int(kind)
+        self.W, self.H, self.n = W, H, n
+        self.r_rewire, self.r_goal, self.threads = float(r_rewire), float(r_goal), threads
+        self.L = _lib.lib()
+        self.words = int(self.L.rrtk_grid_words(W, H))
+        self.og = self.bits = self.rowcum = None
+        self.desc = self.samples = self.balls = None
+        self.nplans = 0
+        self.out = None
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _empty(self, shape, dtype):
+        return self.torch.empty(shape, dtype=dtype, device=self.dev)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    # -- worlds --------------------------------------------------------------------------------
+    def set_worlds_u8(self, og_u8):
+        """og_u8: torch uint8 tensor (nworlds, W, H) already on the device."""
+        t = self.torch
+        assert og_u8.dtype == t.uint8 and og_u8.is_cuda and tuple(og_u8.shape[1:]) == (self.W, self.H)
+        self.og = og_u8.contiguous()
+        nw = self.og.shape[0]
+        self.bits = self._empty((nw, self.words), t.int32)
+        self.rowcum = self._empty((nw, self.W + 1), t.int32)
+        with t.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_pack_grid(self._p(self.og), nw, self.W, self.H, self._p(self.bits), self._stream()), "pack")
+            _lib.check(self.L.rrtk_free_rows(self._p(self.bits), nw, self.W, self.H, self._p(self.rowcum), self._stream()), "free_rows")
+        return self
+
+    def set_worlds_host(self, ogs: np.ndarray):
+        t = self.torch
+        h = t.from_numpy(np.ascontiguousarray((np.asarray(ogs) != 0).astype(np.uint8)))
+        return self.set_worlds_u8(h.to(self.dev))
+
+    def gen_worlds(self, seeds: Sequence[int], thresh: float = 0.33, chunk: int = 256):
+        """Synthetic worlds on the device (bit-identical to worlds.perlin_occupancygrid)."""
+        t = self.torch
+        seeds = np.asarray(seeds, dtype=np.int32)
+        nw = seeds.shape[0]
+        og = self._empty((nw, self.W, self.H), t.uint8)
+        scratch = self._empty((chunk * self.W * self.H + 2 * chunk,), t.int32)
+        d_seeds = t.from_numpy(seeds).to(self.dev)
+        with t.cuda.device(self.dev):
+            for lo in range(0, nw, chunk):
+                m = min(chunk, nw - lo)
+                _lib.check(self.L.rrtk_gen_worlds(self._p(d_seeds[lo:]), m, self.W, self.H, int(round(thresh * 1000)),
+                                                  self._p(scratch), self._p(og[lo:]), self._stream()), "gen_worlds")
+        return self.set_worlds_u8(og)
+
+    def nfree(self) -> np.ndarray:
+        return self.rowcum[:, self.W].cpu().numpy()
+
+    # -- plans ---------------------------------------------------------------------------------
+    def set_plans(self, desc: np.ndarray):
+        t = self.torch
+        desc = np.ascontiguousarray(desc, dtype=_lib.PLAN_DESC)
+        self.nplans = desc.shape[0]
+        self.desc = t.from_numpy(desc.view(np.uint8).reshape(self.nplans, 64)).to(self.dev)
+        P, n = self.nplans, self.n
+        self.out = dict(pts=self._empty((P, n + 1, 2), t.int16), cost=self._empty((P, n + 1), t.float64),
+                        parent=self._empty((P, n + 1), t.int32), stats=self._empty((P, _lib.STAT_COUNT), t.int64),
+                        ell=self._empty((P, n + 1), t.float64) if self.kind == _lib.KIND_INFORMED else None)
+        return self
+
+    def set_samples_host(self, samples: np.ndarray):
+        s = np.ascontiguousarray(samples, dtype=np.int16)
+        assert s.shape == (self.nplans, self.n, 2)
+        self.samples = self.torch.from_numpy(s).to(self.dev)
+        return self
+
+    def set_balls_host(self, balls: np.ndarray):
+        b = np.ascontiguousarray(balls, dtype=np.float64)
+        assert b.shape == (self.nplans, self.n, 2)
+        self.balls = self.torch.from_numpy(b).to(self.dev)
+        return self
+
+    def seed_samples(self, seeds: Sequence[int]):
+        """Sample streams on the device from numpy-compatible PCG64 (rrt.py:85,231-240)."""
+        t = self.torch
+        st = t.from_numpy(seed_states(seeds).view(np.int64)).to(self.dev)
+        self.samples = self._empty((self.nplans, self.n, 2), t.int16)
+        with t.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_sample_streams(self._p(self.bits), self._p(self.rowcum), self.W, self.H, self._p(self.desc),
+                                                  self.nplans, self._p(st), self.n, self._p(self.samples), self._stream()),
+                       "sample_streams")
+        return self
+
+    def run(self):
+        """Enqueue the plan kernel on torch's current stream (asynchronous)."""
+        o = self.out
+        with self.torch.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_plan_batch(self.kind, self._p(self.bits), self.W, self.H, self._p(self.desc), self.nplans, self.n,
+                                              self.r_rewire, self.r_goal, self._p(self.samples), self._p(self.balls),
+                                              self._p(o["pts"]), self._p(o["cost"]), self._p(o["parent"]), self._p(o["stats"]),
+                                              self._p(o["ell"]), self.threads, self._stream()), "plan_batch")
+        return self
+
+    def paths(self, cap: int):
+        t = self.torch
+        path = self._empty((self.nplans, cap), t.int32)
+        ln = self._empty((self.nplans,), t.int32)
+        with t.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_extract_paths(self._p(self.out["parent"]), self._p(self.out["stats"]), self.nplans, self.n, cap,
+                                                 self._p(path), self._p(ln), self._stream()), "extract_paths")
+        return path, ln
+
+    def footprint(self):
+        import ctypes as C
+        smem, blocks = C.c_int(0), C.c_int(0)
+        with self.torch.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_plan_footprint(self.kind, self.W, self.H, self.n, self.threads, C.byref(smem), C.byref(blocks)),
+                       "plan_footprint")
+        return smem.value, blocks.value
+
+    def download(self) -> BatchResult:
+        o = self.out
+        self.torch.cuda.synchronize(self.dev)
+        return BatchResult(o["pts"].cpu().numpy(), o["cost"].cpu().numpy(), o["parent"].cpu().numpy(), o["stats"].cpu().numpy(),
+                           None if o["ell"] is None else o["ell"].cpu().numpy())

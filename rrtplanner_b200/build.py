@@ -1,0 +1,61 @@
+"""Build rrtplanner_b200/librrtk.so (hand-written sm_100a CUDA behind the C ABI of include/rrtk.h).
+
+    python -m rrtplanner_b200.build [--force]
+
+nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the
+repository snapshot; nothing is JIT-compiled at run time.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "librrtk.so")
+SOURCES = ["api.cu", "grid.cu", "collision.cu", "queries.cu", "rng.cu", "plan.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    "--fmad=false",            # cost arithmetic must be mul / add / sqrt in IEEE double, never fused
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "rrtk.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append(f"== {src}\n{out}")
+        if p.returncode:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
+    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

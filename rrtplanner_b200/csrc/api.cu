@@ -1,0 +1,525 @@
+// extern "C" surface of librrtk.so (declared in include/rrtk.h): argument checks, device info,
+// the host-buffer context, and thin forwards to the kernel launchers.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rrtk {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? RRTK_ERR_NODEVICE : RRTK_ERR_CUDA;
+}
+
+// launchers implemented in the other translation units
+int pack_launch(const uint8_t *, int, int, int, uint32_t *, cudaStream_t);
+int free_rows_launch(const uint32_t *, int, int, int, int32_t *, cudaStream_t);
+int worlds_launch(const int32_t *, int, int, int, int, int32_t *, uint8_t *, cudaStream_t);
+int collision_launch(const uint32_t *, int, int, const int32_t *, const int32_t *, int64_t, uint8_t *, int32_t *, int, int,
+                     cudaStream_t);
+int nearest_launch(const int32_t *, int, const int32_t *, const int32_t *, int, int32_t *, int64_t *, cudaStream_t);
+int nearest_launch_f64(const double *, int, const double *, const int32_t *, int, int32_t *, double *, cudaStream_t);
+int within_launch(const int32_t *, int, const int32_t *, const int32_t *, int, double, int, int32_t *, int32_t *, cudaStream_t);
+int within_launch_f64(const double *, int, const double *, const int32_t *, int, double, int, int32_t *, int32_t *, cudaStream_t);
+int dist2_launch(const int32_t *, int, int, int, int64_t *, cudaStream_t);
+int dist_launch_f64(const double *, int, double, double, double *, cudaStream_t);
+int argsort_launch(const int64_t *, int, int32_t *, void *, size_t, cudaStream_t);
+size_t argsort_scratch(int);
+int sample_streams_launch(const uint32_t *, const int32_t *, int, int, const rrtk_plan_desc *, int, const uint64_t *, int,
+                          int16_t *, int, cudaStream_t);
+int plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
+                const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, cudaStream_t);
+int plan_footprint(int, int, int, int, int, int, int, int *, int *);
+int paths_launch(const int32_t *, const int64_t *, int, int, int, int32_t *, int32_t *, cudaStream_t);
+
+struct DevInfo { int dev = -1, sms = 0, optin = 0, sm_smem = 0; };
+static thread_local DevInfo g_dev;
+
+static int dev_info(DevInfo **out)
+{
+    int dev = 0;
+    RRTK_CUDA(cudaGetDevice(&dev));
+    if (g_dev.dev != dev) {
+        RRTK_CUDA(cudaDeviceGetAttribute(&g_dev.sms, cudaDevAttrMultiProcessorCount, dev));
+        RRTK_CUDA(cudaDeviceGetAttribute(&g_dev.optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        RRTK_CUDA(cudaDeviceGetAttribute(&g_dev.sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+        g_dev.dev = dev;
+    }
+    *out = &g_dev;
+    return RRTK_OK;
+}
+
+static int check_grid_dims(int W, int H, int limit)
+{
+    if (W < 1 || H < 1 || W > limit || H > limit) {
+        set_error("grid size (%d, %d) out of range [1, %d]", W, H, limit);
+        return RRTK_ERR_INVALID;
+    }
+    return RRTK_OK;
+}
+#define RRTK_REQUIRE(cond, msg)                 \
+    do {                                        \
+        if (!(cond)) {                          \
+            rrtk::set_error("%s", msg);         \
+            return RRTK_ERR_INVALID;            \
+        }                                       \
+    } while (0)
+#define RRTK_TRY(call)                  \
+    do {                                \
+        int rc_ = (call);               \
+        if (rc_ != RRTK_OK) return rc_; \
+    } while (0)
+
+}  // namespace rrtk
+
+using namespace rrtk;
+
+// ---- device-side growable buffer used by the host-buffer context ---------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return RRTK_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        RRTK_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return RRTK_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct rrtk_ctx {
+    cudaStream_t stream = nullptr;
+    int W = 0, H = 0, nworlds = 0;
+    DevBuf og, bits, rowcum;                    // worlds
+    DevBuf plans, samples, state, balls;        // plan inputs
+    DevBuf pts, cost, parent, stats, ell;       // plan outputs
+    DevBuf a, b, c, d, e;                       // query scratch
+};
+
+extern "C" {
+
+int rrtk_version(void) { return RRTK_VERSION; }
+const char *rrtk_last_error(void) { return g_err; }
+
+int rrtk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int rrtk_set_device(int device)
+{
+    RRTK_CUDA(cudaSetDevice(device));
+    return RRTK_OK;
+}
+int rrtk_device_info(int *sm_count, int *smem_optin_bytes)
+{
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    if (sm_count) *sm_count = d->sms;
+    if (smem_optin_bytes) *smem_optin_bytes = d->optin;
+    return RRTK_OK;
+}
+
+size_t rrtk_grid_words(int W, int H) { return (W < 1 || H < 1) ? 0 : grid_words(W, H); }
+
+int rrtk_pack_grid(const uint8_t *d_og, int nworlds, int W, int H, uint32_t *d_bits, void *stream)
+{
+    RRTK_REQUIRE(d_og && d_bits && nworlds >= 0, "rrtk_pack_grid: null pointer or negative count");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    if (nworlds == 0) return RRTK_OK;
+    return pack_launch(d_og, nworlds, W, H, d_bits, (cudaStream_t)stream);
+}
+
+int rrtk_free_rows(const uint32_t *d_bits, int nworlds, int W, int H, int32_t *d_rowcum, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_rowcum && nworlds >= 0, "rrtk_free_rows: null pointer or negative count");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    if (nworlds == 0) return RRTK_OK;
+    return free_rows_launch(d_bits, nworlds, W, H, d_rowcum, (cudaStream_t)stream);
+}
+
+int rrtk_gen_worlds(const int32_t *d_seeds, int nworlds, int W, int H, int thresh_permille, int32_t *d_scratch,
+                    uint8_t *d_og, void *stream)
+{
+    RRTK_REQUIRE(d_seeds && d_scratch && d_og, "rrtk_gen_worlds: null pointer");
+    RRTK_REQUIRE(nworlds >= 0 && nworlds <= 65535, "rrtk_gen_worlds: nworlds must be in [0, 65535] per call");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    if (nworlds == 0) return RRTK_OK;
+    return worlds_launch(d_seeds, nworlds, W, H, thresh_permille, d_scratch, d_og, (cudaStream_t)stream);
+}
+
+int rrtk_collision_segments(const uint32_t *d_bits, int W, int H, const int32_t *d_segs, const int32_t *d_world,
+                            int64_t nseg, uint8_t *d_free, int32_t *d_cells, void *stream)
+{
+    RRTK_REQUIRE(d_bits && (nseg == 0 || (d_segs && d_free)) && nseg >= 0, "rrtk_collision_segments: null pointer");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return collision_launch(d_bits, W, H, d_segs, d_world, nseg, d_free, d_cells, d->sms, d->optin, (cudaStream_t)stream);
+}
+
+int rrtk_nearest_batch(const int32_t *d_pts, int npts, const int32_t *d_queries, const int32_t *d_count, int nq,
+                       int32_t *d_idx, int64_t *d_d2, void *stream)
+{
+    RRTK_REQUIRE(npts >= 0 && nq >= 0 && (nq == 0 || (d_queries && d_idx)) && (npts == 0 || d_pts), "rrtk_nearest_batch: bad argument");
+    return nearest_launch(d_pts, npts, d_queries, d_count, nq, d_idx, d_d2, (cudaStream_t)stream);
+}
+int rrtk_nearest_batch_f64(const double *d_pts, int npts, const double *d_queries, const int32_t *d_count, int nq,
+                           int32_t *d_idx, double *d_dist, void *stream)
+{
+    RRTK_REQUIRE(npts >= 0 && nq >= 0 && (nq == 0 || (d_queries && d_idx)) && (npts == 0 || d_pts), "rrtk_nearest_batch_f64: bad argument");
+    return nearest_launch_f64(d_pts, npts, d_queries, d_count, nq, d_idx, d_dist, (cudaStream_t)stream);
+}
+
+int rrtk_within_batch(const int32_t *d_pts, int npts, const int32_t *d_queries, const int32_t *d_count, int nq, double r,
+                      int cap, int32_t *d_out, int32_t *d_len, void *stream)
+{
+    RRTK_REQUIRE(npts >= 0 && nq >= 0 && cap >= 0 && (nq == 0 || (d_queries && d_len && (cap == 0 || d_out))) && (npts == 0 || d_pts),
+                 "rrtk_within_batch: bad argument");
+    return within_launch(d_pts, npts, d_queries, d_count, nq, r, cap, d_out, d_len, (cudaStream_t)stream);
+}
+int rrtk_within_batch_f64(const double *d_pts, int npts, const double *d_queries, const int32_t *d_count, int nq, double r,
+                          int cap, int32_t *d_out, int32_t *d_len, void *stream)
+{
+    RRTK_REQUIRE(npts >= 0 && nq >= 0 && cap >= 0 && (nq == 0 || (d_queries && d_len && (cap == 0 || d_out))) && (npts == 0 || d_pts),
+                 "rrtk_within_batch_f64: bad argument");
+    return within_launch_f64(d_pts, npts, d_queries, d_count, nq, r, cap, d_out, d_len, (cudaStream_t)stream);
+}
+
+int rrtk_dist2(const int32_t *d_pts, int npts, int qx, int qy, int64_t *d_d2, void *stream)
+{
+    RRTK_REQUIRE(npts >= 0 && (npts == 0 || (d_pts && d_d2)), "rrtk_dist2: bad argument");
+    return dist2_launch(d_pts, npts, qx, qy, d_d2, (cudaStream_t)stream);
+}
+int rrtk_dist_f64(const double *d_pts, int npts, double qx, double qy, double *d_dist, void *stream)
+{
+    RRTK_REQUIRE(npts >= 0 && (npts == 0 || (d_pts && d_dist)), "rrtk_dist_f64: bad argument");
+    return dist_launch_f64(d_pts, npts, qx, qy, d_dist, (cudaStream_t)stream);
+}
+size_t rrtk_argsort_scratch_bytes(int n) { return argsort_scratch(n); }
+int rrtk_argsort_i64(const int64_t *d_keys, int n, int32_t *d_perm, void *d_scratch, size_t scratch_bytes, void *stream)
+{
+    RRTK_REQUIRE(n >= 0 && (n == 0 || (d_keys && d_perm && d_scratch)), "rrtk_argsort_i64: bad argument");
+    return argsort_launch(d_keys, n, d_perm, d_scratch, scratch_bytes, (cudaStream_t)stream);
+}
+
+int rrtk_sample_streams(const uint32_t *d_bits, const int32_t *d_rowcum, int W, int H, const rrtk_plan_desc *d_plans,
+                        int nplans, const uint64_t *d_state, int n, int16_t *d_samples, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_rowcum && d_plans && d_state && d_samples && nplans >= 0 && n >= 0, "rrtk_sample_streams: bad argument");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return sample_streams_launch(d_bits, d_rowcum, W, H, d_plans, nplans, d_state, n, d_samples, d->optin, (cudaStream_t)stream);
+}
+
+int rrtk_plan_batch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans, int nplans, int n,
+                    double r_rewire, double r_goal, const int16_t *d_samples, const double *d_balls, int16_t *d_pts,
+                    double *d_cost, int32_t *d_parent, int64_t *d_stats, double *d_ell_c, int threads, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_plans && d_samples && d_pts && d_cost && d_parent && d_stats, "rrtk_plan_batch: null pointer");
+    RRTK_REQUIRE(kind != RRTK_INFORMED || d_ell_c, "rrtk_plan_batch: informed plans need d_ell_c");
+    RRTK_REQUIRE(nplans >= 0 && n >= 1 && n <= 65534, "rrtk_plan_batch: need nplans >= 0 and 1 <= n <= 65534");
+    RRTK_REQUIRE(r_rewire == r_rewire && r_goal == r_goal, "rrtk_plan_batch: NaN radius");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    if (nplans == 0) return RRTK_OK;
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return plan_launch(kind, d_bits, W, H, d_plans, nplans, n, r_rewire, r_goal, d_samples, d_balls, d_pts, d_cost, d_parent,
+                       d_stats, d_ell_c, threads, d->optin, (cudaStream_t)stream);
+}
+
+int rrtk_plan_footprint(int kind, int W, int H, int n, int threads, int *smem_bytes, int *blocks_per_sm)
+{
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    int rc = plan_footprint(kind, W, H, n, threads, d->optin, d->sm_smem, smem_bytes, blocks_per_sm);
+    if (rc) set_error("plan with n=%d does not fit shared memory", n);
+    return rc;
+}
+
+int rrtk_extract_paths(const int32_t *d_parent, const int64_t *d_stats, int nplans, int n, int cap, int32_t *d_path,
+                       int32_t *d_len, void *stream)
+{
+    RRTK_REQUIRE(d_parent && d_stats && d_path && d_len && nplans >= 0 && n >= 1 && cap >= 1, "rrtk_extract_paths: bad argument");
+    if (nplans == 0) return RRTK_OK;
+    return paths_launch(d_parent, d_stats, nplans, n, cap, d_path, d_len, (cudaStream_t)stream);
+}
+
+// ---- host-buffer context ---------------------------------------------------------------------------
+int rrtk_create(rrtk_ctx **out)
+{
+    RRTK_REQUIRE(out, "rrtk_create: null pointer");
+    *out = nullptr;
+    if (rrtk_device_count() < 1) {
+        set_error("no CUDA device visible: librrtk has no CPU fallback");
+        return RRTK_ERR_NODEVICE;
+    }
+    rrtk_ctx *c = new rrtk_ctx();
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+    *out = c;
+    return RRTK_OK;
+}
+
+int rrtk_destroy(rrtk_ctx *c)
+{
+    if (!c) return RRTK_OK;
+    DevBuf *all[] = {&c->og, &c->bits, &c->rowcum, &c->plans, &c->samples, &c->state, &c->balls, &c->pts,
+                     &c->cost, &c->parent, &c->stats, &c->ell, &c->a, &c->b, &c->c, &c->d, &c->e};
+    for (DevBuf *b : all) b->release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return RRTK_OK;
+}
+
+int rrtk_ctx_set_grids(rrtk_ctx *c, const uint8_t *h_og, int nworlds, int W, int H, int32_t *h_nfree)
+{
+    RRTK_REQUIRE(c && h_og && nworlds >= 1, "rrtk_ctx_set_grids: bad argument");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    const size_t cells = (size_t)W * H;
+    RRTK_TRY(c->og.reserve(cells * nworlds));
+    RRTK_TRY(c->bits.reserve(grid_words(W, H) * 4 * nworlds));
+    RRTK_TRY(c->rowcum.reserve((size_t)(W + 1) * 4 * nworlds));
+    RRTK_CUDA(cudaMemcpyAsync(c->og.p, h_og, cells * nworlds, cudaMemcpyHostToDevice, c->stream));
+    RRTK_TRY(pack_launch(c->og.as<uint8_t>(), nworlds, W, H, c->bits.as<uint32_t>(), c->stream));
+    RRTK_TRY(free_rows_launch(c->bits.as<uint32_t>(), nworlds, W, H, c->rowcum.as<int32_t>(), c->stream));
+    if (h_nfree)
+        RRTK_CUDA(cudaMemcpy2DAsync(h_nfree, 4, c->rowcum.as<int32_t>() + W, (size_t)(W + 1) * 4, 4, nworlds,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    RRTK_CUDA(cudaStreamSynchronize(c->stream));
+    c->W = W; c->H = H; c->nworlds = nworlds;
+    return RRTK_OK;
+}
+
+int rrtk_ctx_plan(rrtk_ctx *c, int kind, const rrtk_plan_desc *h_plans, int nplans, int n, double r_rewire, double r_goal,
+                  const int16_t *h_samples, const uint64_t *h_state, const double *h_balls, int16_t *h_pts, double *h_cost,
+                  int32_t *h_parent, int64_t *h_stats, double *h_ell_c)
+{
+    RRTK_REQUIRE(c && h_plans && h_pts && h_cost && h_parent && h_stats, "rrtk_ctx_plan: null pointer");
+    RRTK_REQUIRE(c->nworlds > 0, "rrtk_ctx_plan: call rrtk_ctx_set_grids first");
+    RRTK_REQUIRE((h_samples != nullptr) != (h_state != nullptr), "rrtk_ctx_plan: pass exactly one of h_samples / h_state");
+    RRTK_REQUIRE(kind != RRTK_INFORMED || h_ell_c, "rrtk_ctx_plan: informed plans need h_ell_c");
+    RRTK_REQUIRE(nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan: need nplans >= 0 and 1 <= n <= 65534");
+    if (nplans == 0) return RRTK_OK;
+    for (int p = 0; p < nplans; ++p) {
+        const rrtk_plan_desc &d = h_plans[p];
+        if (d.world < 0 || d.world >= c->nworlds || d.start_x < 0 || d.start_x >= c->W || d.goal_x < 0 || d.goal_x >= c->W ||
+            d.start_y < 0 || d.start_y >= c->H || d.goal_y < 0 || d.goal_y >= c->H) {
+            set_error("plan %d: world index or start/goal outside the grid", p);
+            return RRTK_ERR_INVALID;
+        }
+    }
+    if (h_samples) {
+        const size_t total = (size_t)nplans * n;
+        for (size_t i = 0; i < total; ++i) {
+            const int x = h_samples[2 * i], y = h_samples[2 * i + 1];
+            if (x < 0 || x >= c->W || y < 0 || y >= c->H) {
+                set_error("sample %zu of plan %zu lies outside the grid", i % n, i / n);
+                return RRTK_ERR_INVALID;
+            }
+        }
+    }
+    const size_t rows = (size_t)nplans * (n + 1);
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->plans.reserve(sizeof(rrtk_plan_desc) * nplans));
+    RRTK_TRY(c->samples.reserve((size_t)nplans * n * 4));
+    RRTK_TRY(c->pts.reserve(rows * 4));
+    RRTK_TRY(c->cost.reserve(rows * 8));
+    RRTK_TRY(c->parent.reserve(rows * 4));
+    RRTK_TRY(c->stats.reserve((size_t)nplans * RRTK_STAT_COUNT * 8));
+    RRTK_CUDA(cudaMemcpyAsync(c->plans.p, h_plans, sizeof(rrtk_plan_desc) * nplans, cudaMemcpyHostToDevice, st));
+    if (h_samples) {
+        RRTK_CUDA(cudaMemcpyAsync(c->samples.p, h_samples, (size_t)nplans * n * 4, cudaMemcpyHostToDevice, st));
+    } else {
+        DevInfo *d;
+        RRTK_TRY(dev_info(&d));
+        RRTK_TRY(c->state.reserve((size_t)nplans * 32));
+        RRTK_CUDA(cudaMemcpyAsync(c->state.p, h_state, (size_t)nplans * 32, cudaMemcpyHostToDevice, st));
+        RRTK_TRY(sample_streams_launch(c->bits.as<uint32_t>(), c->rowcum.as<int32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(),
+                                       nplans, c->state.as<uint64_t>(), n, c->samples.as<int16_t>(), d->optin, st));
+    }
+    if (kind == RRTK_INFORMED) {
+        RRTK_TRY(c->ell.reserve(rows * 8));
+        if (h_balls) {
+            RRTK_TRY(c->balls.reserve((size_t)nplans * n * 16));
+            RRTK_CUDA(cudaMemcpyAsync(c->balls.p, h_balls, (size_t)nplans * n * 16, cudaMemcpyHostToDevice, st));
+        }
+    }
+    RRTK_TRY(rrtk_plan_batch(kind, c->bits.as<uint32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(), nplans, n, r_rewire, r_goal,
+                             c->samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? c->balls.as<double>() : nullptr,
+                             c->pts.as<int16_t>(), c->cost.as<double>(),
+                             c->parent.as<int32_t>(), c->stats.as<int64_t>(), c->ell.as<double>(), 0, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_pts, c->pts.p, rows * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_cost, c->cost.p, rows * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_parent, c->parent.p, rows * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_stats, c->stats.p, (size_t)nplans * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    if (kind == RRTK_INFORMED) RRTK_CUDA(cudaMemcpyAsync(h_ell_c, c->ell.p, rows * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+
+int rrtk_ctx_samples(rrtk_ctx *c, const rrtk_plan_desc *h_plans, int nplans, int n, const uint64_t *h_state, int16_t *h_samples)
+{
+    RRTK_REQUIRE(c && h_plans && h_state && h_samples && nplans >= 1 && n >= 1, "rrtk_ctx_samples: bad argument");
+    RRTK_REQUIRE(c->nworlds > 0, "rrtk_ctx_samples: call rrtk_ctx_set_grids first");
+    for (int p = 0; p < nplans; ++p) RRTK_REQUIRE(h_plans[p].world >= 0 && h_plans[p].world < c->nworlds, "rrtk_ctx_samples: bad world index");
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->plans.reserve(sizeof(rrtk_plan_desc) * nplans));
+    RRTK_TRY(c->samples.reserve((size_t)nplans * n * 4));
+    RRTK_TRY(c->state.reserve((size_t)nplans * 32));
+    RRTK_CUDA(cudaMemcpyAsync(c->plans.p, h_plans, sizeof(rrtk_plan_desc) * nplans, cudaMemcpyHostToDevice, st));
+    RRTK_CUDA(cudaMemcpyAsync(c->state.p, h_state, (size_t)nplans * 32, cudaMemcpyHostToDevice, st));
+    RRTK_TRY(sample_streams_launch(c->bits.as<uint32_t>(), c->rowcum.as<int32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(), nplans,
+                                   c->state.as<uint64_t>(), n, c->samples.as<int16_t>(), d->optin, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_samples, c->samples.p, (size_t)nplans * n * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+
+int rrtk_ctx_collision(rrtk_ctx *c, int world, const int32_t *h_segs, int64_t nseg, uint8_t *h_free, int32_t *h_cells)
+{
+    RRTK_REQUIRE(c && nseg >= 0 && (nseg == 0 || (h_segs && h_free)), "rrtk_ctx_collision: bad argument");
+    RRTK_REQUIRE(c->nworlds > 0 && world >= 0 && world < c->nworlds, "rrtk_ctx_collision: no such world (call rrtk_ctx_set_grids)");
+    if (nseg == 0) return RRTK_OK;
+    for (int64_t s = 0; s < nseg; ++s) {
+        const int32_t *e = h_segs + 4 * s;
+        if (e[0] < 0 || e[0] >= c->W || e[2] < 0 || e[2] >= c->W || e[1] < 0 || e[1] >= c->H || e[3] < 0 || e[3] >= c->H) {
+            set_error("segment %lld has an endpoint outside the (%d, %d) grid", (long long)s, c->W, c->H);
+            return RRTK_ERR_INVALID;
+        }
+    }
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->a.reserve((size_t)nseg * 16));
+    RRTK_TRY(c->b.reserve((size_t)nseg));
+    RRTK_TRY(c->c.reserve((size_t)nseg * 4));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_segs, (size_t)nseg * 16, cudaMemcpyHostToDevice, st));
+    const uint32_t *bits = c->bits.as<uint32_t>() + (size_t)world * grid_words(c->W, c->H);
+    RRTK_TRY(rrtk_collision_segments(bits, c->W, c->H, c->a.as<int32_t>(), nullptr, nseg, c->b.as<uint8_t>(), c->c.as<int32_t>(), st));
+    RRTK_CUDA(cudaMemcpyAsync(h_free, c->b.p, (size_t)nseg, cudaMemcpyDeviceToHost, st));
+    if (h_cells) RRTK_CUDA(cudaMemcpyAsync(h_cells, c->c.p, (size_t)nseg * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+
+int rrtk_ctx_nearest(rrtk_ctx *c, const int32_t *h_pts, int npts, const int32_t *h_queries, int nq, int32_t *h_idx, int64_t *h_d2)
+{
+    RRTK_REQUIRE(c && npts >= 1 && nq >= 1 && h_pts && h_queries && h_idx, "rrtk_ctx_nearest: bad argument");
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->a.reserve((size_t)npts * 8));
+    RRTK_TRY(c->b.reserve((size_t)nq * 8));
+    RRTK_TRY(c->c.reserve((size_t)nq * 4));
+    RRTK_TRY(c->d.reserve((size_t)nq * 8));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_pts, (size_t)npts * 8, cudaMemcpyHostToDevice, st));
+    RRTK_CUDA(cudaMemcpyAsync(c->b.p, h_queries, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    RRTK_TRY(nearest_launch(c->a.as<int32_t>(), npts, c->b.as<int32_t>(), nullptr, nq, c->c.as<int32_t>(), c->d.as<int64_t>(), st));
+    RRTK_CUDA(cudaMemcpyAsync(h_idx, c->c.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (h_d2) RRTK_CUDA(cudaMemcpyAsync(h_d2, c->d.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+int rrtk_ctx_nearest_f64(rrtk_ctx *c, const double *h_pts, int npts, const double *h_queries, int nq, int32_t *h_idx, double *h_dist)
+{
+    RRTK_REQUIRE(c && npts >= 1 && nq >= 1 && h_pts && h_queries && h_idx, "rrtk_ctx_nearest_f64: bad argument");
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->a.reserve((size_t)npts * 16));
+    RRTK_TRY(c->b.reserve((size_t)nq * 16));
+    RRTK_TRY(c->c.reserve((size_t)nq * 4));
+    RRTK_TRY(c->d.reserve((size_t)nq * 8));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_pts, (size_t)npts * 16, cudaMemcpyHostToDevice, st));
+    RRTK_CUDA(cudaMemcpyAsync(c->b.p, h_queries, (size_t)nq * 16, cudaMemcpyHostToDevice, st));
+    RRTK_TRY(nearest_launch_f64(c->a.as<double>(), npts, c->b.as<double>(), nullptr, nq, c->c.as<int32_t>(), c->d.as<double>(), st));
+    RRTK_CUDA(cudaMemcpyAsync(h_idx, c->c.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    if (h_dist) RRTK_CUDA(cudaMemcpyAsync(h_dist, c->d.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+
+int rrtk_ctx_within(rrtk_ctx *c, const int32_t *h_pts, int npts, const int32_t *h_queries, int nq, double r, int cap,
+                    int32_t *h_out, int32_t *h_len)
+{
+    RRTK_REQUIRE(c && npts >= 1 && nq >= 1 && cap >= 1 && h_pts && h_queries && h_out && h_len, "rrtk_ctx_within: bad argument");
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->a.reserve((size_t)npts * 8));
+    RRTK_TRY(c->b.reserve((size_t)nq * 8));
+    RRTK_TRY(c->c.reserve((size_t)nq * cap * 4));
+    RRTK_TRY(c->d.reserve((size_t)nq * 4));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_pts, (size_t)npts * 8, cudaMemcpyHostToDevice, st));
+    RRTK_CUDA(cudaMemcpyAsync(c->b.p, h_queries, (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+    RRTK_TRY(within_launch(c->a.as<int32_t>(), npts, c->b.as<int32_t>(), nullptr, nq, r, cap, c->c.as<int32_t>(), c->d.as<int32_t>(), st));
+    RRTK_CUDA(cudaMemcpyAsync(h_out, c->c.p, (size_t)nq * cap * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_len, c->d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+int rrtk_ctx_within_f64(rrtk_ctx *c, const double *h_pts, int npts, const double *h_queries, int nq, double r, int cap,
+                        int32_t *h_out, int32_t *h_len)
+{
+    RRTK_REQUIRE(c && npts >= 1 && nq >= 1 && cap >= 1 && h_pts && h_queries && h_out && h_len, "rrtk_ctx_within_f64: bad argument");
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->a.reserve((size_t)npts * 16));
+    RRTK_TRY(c->b.reserve((size_t)nq * 16));
+    RRTK_TRY(c->c.reserve((size_t)nq * cap * 4));
+    RRTK_TRY(c->d.reserve((size_t)nq * 4));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_pts, (size_t)npts * 16, cudaMemcpyHostToDevice, st));
+    RRTK_CUDA(cudaMemcpyAsync(c->b.p, h_queries, (size_t)nq * 16, cudaMemcpyHostToDevice, st));
+    RRTK_TRY(within_launch_f64(c->a.as<double>(), npts, c->b.as<double>(), nullptr, nq, r, cap, c->c.as<int32_t>(), c->d.as<int32_t>(), st));
+    RRTK_CUDA(cudaMemcpyAsync(h_out, c->c.p, (size_t)nq * cap * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_len, c->d.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+
+// full ordering RRT.near returns (rrt.py:150-155), pinned stable
+static int near_order_common(rrtk_ctx *c, int npts, int32_t *h_perm)
+{
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->c.reserve((size_t)npts * 4));
+    RRTK_TRY(c->d.reserve(argsort_scratch(npts)));
+    RRTK_TRY(argsort_launch(c->b.as<int64_t>(), npts, c->c.as<int32_t>(), c->d.p, c->d.cap, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_perm, c->c.p, (size_t)npts * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    return RRTK_OK;
+}
+int rrtk_ctx_near_order(rrtk_ctx *c, const int32_t *h_pts, int npts, int qx, int qy, int32_t *h_perm)
+{
+    RRTK_REQUIRE(c && npts >= 1 && h_pts && h_perm, "rrtk_ctx_near_order: bad argument");
+    RRTK_TRY(c->a.reserve((size_t)npts * 8));
+    RRTK_TRY(c->b.reserve((size_t)npts * 8));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_pts, (size_t)npts * 8, cudaMemcpyHostToDevice, c->stream));
+    RRTK_TRY(dist2_launch(c->a.as<int32_t>(), npts, qx, qy, c->b.as<int64_t>(), c->stream));
+    return near_order_common(c, npts, h_perm);
+}
+int rrtk_ctx_near_order_f64(rrtk_ctx *c, const double *h_pts, int npts, double qx, double qy, int32_t *h_perm)
+{
+    RRTK_REQUIRE(c && npts >= 1 && h_pts && h_perm, "rrtk_ctx_near_order_f64: bad argument");
+    RRTK_TRY(c->a.reserve((size_t)npts * 16));
+    RRTK_TRY(c->b.reserve((size_t)npts * 8));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_pts, (size_t)npts * 16, cudaMemcpyHostToDevice, c->stream));
+    // non-negative doubles order like their bit patterns, so the int64 sorter applies
+    RRTK_TRY(dist_launch_f64(c->a.as<double>(), npts, qx, qy, c->b.as<double>(), c->stream));
+    return near_order_common(c, npts, h_perm);
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Shared device helpers: tiled bit-grid addressing and the warp-cooperative line walk.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rrtk.h"
+
+#define RRTK_FULL 0xffffffffu
+
+namespace rrtk {
+
+// ---- error plumbing (api.cu owns the buffer) ------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+#define RRTK_CUDA(call)                                              \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return rrtk::cuda_fail(e_, #call);    \
+    } while (0)
+
+// ---- tiled bit grid (layout documented in include/rrtk.h) ------------------------------------
+__host__ __device__ __forceinline__ int tiles_y(int H) { return (H + 31) >> 5; }
+__host__ __device__ __forceinline__ int tiles_x(int W) { return (W + 31) >> 5; }
+__host__ __device__ __forceinline__ size_t grid_words(int W, int H)
+{
+    return (size_t)tiles_x(W) * tiles_y(H) * 32;
+}
+__device__ __forceinline__ uint32_t word_index(int x, int y, int TY)
+{
+    return (uint32_t)((((x >> 5) * TY + (y >> 5)) << 5) | (x & 31));
+}
+
+// Grid accessors: the walk is templated on where the words live.
+struct SharedGrid {
+    const uint32_t *w;
+    __device__ __forceinline__ uint32_t load(uint32_t i) const { return w[i]; }
+};
+struct GlobalGrid {
+    const uint32_t *w;
+    __device__ __forceinline__ uint32_t load(uint32_t i) const { return __ldg(w + i); }
+};
+
+// floor(num / den) for 0 <= num < 2^24, 0 < den < 2^24 via one fp32 reciprocal and a fix-up.
+__device__ __forceinline__ int small_div(int num, int den, int &rem)
+{
+    int q = __float2int_rz(__int2float_rn(num) * __frcp_rn(__int2float_rn(den)));
+    int r = num - q * den;
+    if (r < 0) { r += den; --q; }
+    if (r >= den) { r -= den; ++q; }
+    rem = r;
+    return q;
+}
+
+// Warp-cooperative form of RRT.collisionfree (rrt.py:183-229).  The reference walks
+// L + 1 = max(|dx|,|dy|) + 1 cells with an integer error accumulator; cell k of that walk has the
+// closed form
+//     major axis:  k steps          minor axis:  floor((2*k*minor + major) / (2*major)) steps
+// (checked exhaustively in tests/test_oracle.py::test_closed_form_cell_sequence), so lane l of the
+// warp tests cell 32*c + l of chunk c, and a ballot finds the first occupied one.  All 32 lanes
+// must call this with the same segment.  Returns k >= 0 = index of the first occupied cell, or
+// -(L + 1) when the walk is free -- i.e. |ret| or ret + 1 is the number of cells the reference reads.
+template <class Grid>
+__device__ __forceinline__ int warp_first_hit(const Grid &g, int TY, int ax, int ay, int bx, int by, int lane)
+{
+    const int dx = bx - ax, dy = by - ay;
+    const int adx = abs(dx), ady = abs(dy);
+    const int sx = dx > 0 ? 1 : -1, sy = dy > 0 ? 1 : -1;
+    const bool xmajor = adx >= ady;
+    const int major = xmajor ? adx : ady;
+    const int minor = xmajor ? ady : adx;
+    const int den = 2 * major;
+
+    int k = lane;
+    int q = 0, r = 0;
+    if (major > 0) q = small_div(2 * lane * minor + major, den, r);   // num < 63 * 16384 + ... < 2^24
+    int dq = 0, dr = 0;
+    if (major >= 32) dq = small_div(64 * minor, den, dr);             // per-chunk increment of (q, r)
+
+    for (int base = 0; base <= major; base += 32) {
+        const int cx = xmajor ? ax + sx * k : ax + sx * q;
+        const int cy = xmajor ? ay + sy * q : ay + sy * k;
+        bool hit = false;
+        if (k <= major) hit = (g.load(word_index(cx, cy, TY)) >> (cy & 31)) & 1u;
+        const unsigned m = __ballot_sync(RRTK_FULL, hit);
+        if (m) return base + __ffs(m) - 1;
+        k += 32;
+        q += dq;
+        r += dr;
+        if (r >= den) { r -= den; ++q; }
+    }
+    return -(major + 1);
+}
+
+__device__ __forceinline__ int cells_tested(int first_hit_ret) { return first_hit_ret < 0 ? -first_hit_ret : first_hit_ret + 1; }
+
+// packed tree vertex: x | y << 16 (coordinates < 16384)
+__device__ __forceinline__ uint32_t pack_xy(int x, int y) { return (uint32_t)x | ((uint32_t)y << 16); }
+__device__ __forceinline__ int px(uint32_t p) { return (int)(p & 0xffffu); }
+__device__ __forceinline__ int py(uint32_t p) { return (int)(p >> 16); }
+// vertex slot that is never nearest and never inside a radius (x = 49151): for any real point
+// (coordinates < 16384) its squared distance is >= 2^30 > 2 * 16383^2 and < 2^32.
+#define RRTK_FAR_VERTEX 0x0000BFFFu
+
+__device__ __forceinline__ uint32_t dist2(uint32_t p, int qx, int qy)
+{
+    const int dx = px(p) - qx, dy = py(p) - qy;
+    return (uint32_t)(dx * dx) + (uint32_t)(dy * dy);
+}
+
+// cost-to-come of v plus straight-line length: rrt.py:70-78 with r2norm of rrt.py:10-24 --
+// exact integer d^2, correctly rounded f64 sqrt, one IEEE add (no contraction possible).
+__device__ __forceinline__ double reach_cost(double cv, uint32_t d2) { return __dadd_rn(cv, __dsqrt_rn((double)d2)); }
+
+}  // namespace rrtk

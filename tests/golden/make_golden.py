@@ -275,6 +275,34 @@ def gen_plans(refp, ref_plain):
         save_plan(f"wall40x30_{kind}_n{n}", kind, og, n, xs, xg, smp[:n], rec, balls, r, rg)
 
 
+def gen_seeded(refp):
+    """The reference driven ONLY through its public constructor/plan API with a seed (no stream
+    injection): what the drop-in classes must reproduce.  Two successive plan() calls on one object
+    check that the generator state carries over (rrt.py:85)."""
+    og = worlds.perlin_occupancygrid(160, 120, seed=worlds.world_seed(7))
+    xs, xg = worlds.start_goal(og, 7)
+    xs2, xg2 = worlds.start_goal(og, 8)
+    out = {"og": np.packbits(og != 0, axis=1), "og_shape": np.array(og.shape), "xs": xs, "xg": xg, "xs2": xs2, "xg2": xg2}
+    cases = {
+        "standard": lambda: refp.RRTStandard(og, 300, pbar=False, seed=42),
+        "star": lambda: refp.RRTStar(og, 300, 30, pbar=False, seed=43),
+        "informed": lambda: refp.RRTStarInformed(og, 500, 30, 10, pbar=False, seed=44),
+    }
+    for name, mk in cases.items():
+        p = mk()
+        for rep, (a, b) in enumerate(((xs, xg), (xs2, xg2))):
+            T, gv = p.plan(a.copy(), b.copy())
+            for k, v in graph_arrays(T, gv).items():
+                out[f"{name}{rep}_{k}"] = v
+            if name == "informed":
+                keys = np.array(sorted(p.ellipses), dtype=np.int64)
+                out[f"{name}{rep}_ell_keys"] = keys
+                out[f"{name}{rep}_ell_vals"] = np.array([[p.ellipses[k][0][0], p.ellipses[k][0][1], p.ellipses[k][1],
+                                                         p.ellipses[k][2], p.ellipses[k][3]] for k in keys]).reshape(-1, 5)
+            print("seeded", name, rep, "gv", int(gv), "nodes", T.number_of_nodes(), "edges", T.number_of_edges())
+    np.savez_compressed(os.path.join(HERE, "seeded_api.npz"), **out)
+
+
 def unit_balls(n, seed):
     """n unit-ball points produced exactly as RRTStarInformed.unitball does (rrt.py:579-587)."""
     rng = np.random.default_rng(seed)
@@ -308,3 +336,4 @@ if __name__ == "__main__":
     gen_queries(ref_plain)
     gen_misc(ref_plain)
     gen_plans(ref_pinned, ref_plain)
+    gen_seeded(ref_pinned)

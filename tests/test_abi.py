@@ -1,0 +1,83 @@
+"""CPU-side checks of the boundary: the C-ABI library builds/loads, exports every symbol the header
+declares, and fails loudly (never falls back) when no GPU is present.  No compute calls."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from rrtplanner_b200 import _lib, build as build_mod
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_mod.build()
+    return _lib.lib()
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "rrtk.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rrtk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    names = header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/rrtk.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_version_and_layout(lib):
+    assert lib.rrtk_version() == 100
+    assert _lib.PLAN_DESC.itemsize == 64
+    assert lib.rrtk_grid_words(512, 512) == 512 * 512 // 32
+    assert lib.rrtk_grid_words(43, 100) == 2 * 4 * 32      # padded to whole 32x32 tiles
+    assert lib.rrtk_grid_words(0, 5) == 0
+
+
+def test_invalid_arguments_are_rejected_without_a_gpu(lib):
+    assert lib.rrtk_pack_grid(None, 1, 8, 8, None, None) == -1
+    assert b"null" in lib.rrtk_last_error()
+    assert lib.rrtk_plan_batch(1, None, 8, 8, None, 1, 10, 1.0, 1.0, None, None, None, None, None, None, None, 0, None) == -1
+    with pytest.raises(ValueError):
+        _lib.check(-1, "x")
+    with pytest.raises(MemoryError):
+        _lib.check(-2, "x")
+
+
+def test_no_silent_cpu_fallback(lib):
+    """Without a CUDA device the product path must raise, not compute on the host."""
+    import rrtplanner_b200 as R
+    if lib.rrtk_device_count() > 0:
+        pytest.skip("GPU present")
+    og = np.zeros((16, 16))
+    p = R.RRTStar(og, 10, 5, pbar=False)
+    with pytest.raises(RuntimeError):
+        p.plan(np.array([1, 1]), np.array([9, 9]))
+    with pytest.raises(RuntimeError):
+        R.RRT.collisionfree(og, np.array([1, 1]), np.array([2, 2]))
+    with pytest.raises(NotImplementedError):
+        R.RRT(og, 10).plan(np.array([1, 1]), np.array([2, 2]))
+    with pytest.raises(NotImplementedError):
+        R.RRTStar(og, 10, 5, costfn=lambda *a: 0.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "rrtplanner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, f
+
+
+def test_pcg_state_words():
+    w = _lib.pcg64_state_words(np.random.default_rng(0))
+    st = np.random.default_rng(0).bit_generator.state["state"]
+    assert (int(w[0]) << 64) | int(w[1]) == st["state"] and (int(w[2]) << 64) | int(w[3]) == st["inc"]

@@ -1,0 +1,128 @@
+"""GPU tests of the drop-in classes: same constructor / plan() calls as the reference's users make
+(docs/getting-started.rst:50-72, tests/test_rrt.py:122-136), results compared with what the pinned
+reference returned for the same seeds (tests/golden/seeded_api.npz)."""
+import os
+
+import networkx as nx
+import numpy as np
+import pytest
+
+import rrtplanner_b200 as R
+from oracle import rrt_oracle as O
+from tests.conftest import GOLDEN, load_plan, golden_plans
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def seeded():
+    z = np.load(os.path.join(GOLDEN, "seeded_api.npz"))
+    d = {k: z[k] for k in z.files}
+    w, h = (int(v) for v in d["og_shape"])
+    d["og"] = np.unpackbits(d["og"], axis=1)[:, :h].astype(np.int64)
+    return d
+
+
+def graph_matches(T, gv, z, prefix):
+    assert int(gv) == int(z[f"{prefix}_gv"])
+    assert [int(v) for v in T.nodes] == [int(v) for v in z[f"{prefix}_g_nodes"]]
+    pts = np.stack([np.asarray(T.nodes[v]["pt"]) for v in T.nodes])
+    assert pts.dtype == np.int64 and np.array_equal(pts, z[f"{prefix}_g_pts"])
+    e = list(T.edges(data=True))
+    assert [int(a) for a, _, _ in e] == [int(v) for v in z[f"{prefix}_g_eu"]]
+    assert [int(b) for _, b, _ in e] == [int(v) for v in z[f"{prefix}_g_ev"]]
+    assert np.array_equal(np.array([d["dist"] for _, _, d in e]), z[f"{prefix}_g_dist"])
+    assert np.array_equal(np.array([float(d["cost"]) for _, _, d in e]), z[f"{prefix}_g_cost"])
+
+
+@pytest.mark.parametrize("name", ["standard", "star", "informed"])
+def test_seeded_public_api_matches_reference(seeded, name):
+    og = seeded["og"]
+    mk = {"standard": lambda: R.RRTStandard(og, 300, pbar=False, seed=42),
+          "star": lambda: R.RRTStar(og, 300, 30, pbar=False, seed=43),
+          "informed": lambda: R.RRTStarInformed(og, 500, 30, 10, pbar=False, seed=44)}[name]
+    p = mk()
+    for rep, (a, b) in enumerate(((seeded["xs"], seeded["xg"]), (seeded["xs2"], seeded["xg2"]))):
+        T, gv = p.plan(a.copy(), b.copy())          # second call continues the generator (rrt.py:85)
+        graph_matches(T, gv, seeded, f"{name}{rep}")
+        path = p.route2gv(T, gv)
+        assert path[0] == 0 and path[-1] == gv
+        lines = p.vertices_as_ndarray(T, path)
+        assert lines.shape == (len(path) - 1, 2, 2)
+        if name == "informed":
+            keys = sorted(p.ellipses)
+            assert keys == [int(k) for k in seeded[f"{name}{rep}_ell_keys"]]
+            vals = np.array([[p.ellipses[k][0][0], p.ellipses[k][0][1], p.ellipses[k][1], p.ellipses[k][2], p.ellipses[k][3]]
+                             for k in keys]).reshape(-1, 5)
+            assert np.allclose(vals, seeded[f"{name}{rep}_ell_vals"], rtol=1e-12, atol=1e-12)
+
+
+def test_golden_streams_through_classes():
+    """cfg1 (256^2, n=1000, r=50, seed 0): the class API reproduces the golden graphs."""
+    for path in golden_plans():
+        g = load_plan(path)
+        if int(g["seed"]) < 0 or g["kind"] == "informed":
+            continue
+        og = g["og"]
+        p = R.RRTStandard(og, g["n"], pbar=False, seed=int(g["seed"])) if g["kind"] == "standard" else \
+            R.RRTStar(og, g["n"], float(g["r_rewire"]), pbar=False, seed=int(g["seed"]))
+        T, gv = p.plan(g["xstart"], g["xgoal"])
+        z = {f"x_{k}": v for k, v in g.items()}
+        graph_matches(T, gv, z, "x")
+
+
+def test_reference_test_suite_shapes():
+    """The reference's own smoke tests (tests/test_rrt.py:97-136) through the drop-in."""
+    rng = np.random.default_rng(0)
+    for dtype in (int, float, np.uint32, np.float32):
+        for topo in ("empty", "square"):
+            og = np.zeros((43, 100), dtype=dtype)
+            if topo == "square":
+                og[43 // 4: 3 * 43 // 4, 100 // 4: 3 * 100 // 4] = 1
+            base = R.RRT(og, 25)
+            p1 = np.array([rng.integers(0, 43), rng.integers(0, 100)])
+            p2 = np.array([rng.integers(0, 43), rng.integers(0, 100)])
+            assert base.collisionfree(base.og, p1, p2) == O.collisionfree(og, p1, p2)
+            pts = np.stack([rng.integers(0, 43, 10), rng.integers(0, 43, 10)], -1)
+            assert np.array_equal(base.near(pts, p1), O.near_sorted(pts, p1))
+            assert np.array_equal(base.within(pts, p1, 10), O.within(pts, p1, 10))
+            for planner in (R.RRTStandard(og, 100, pbar=False), R.RRTStar(og, 100, r_rewire=50, pbar=False),
+                            R.RRTStarInformed(og, 100, r_rewire=50, r_goal=5, pbar=False)):
+                xs, xg = planner.sample_all_free(), planner.sample_all_free()
+                T, gv = planner.plan(xs, xg)
+                assert isinstance(T, nx.DiGraph) and T.number_of_nodes() in (100, 101)
+
+
+def test_set_og_and_set_n_replan():
+    og = R.perlin_occupancygrid(96, 96, seed=3)
+    p = R.RRTStar(og, 200, 20, pbar=False, seed=1)
+    xs, xg = R.worlds.start_goal(og, 1)
+    T1, g1 = p.plan(xs, xg)
+    og2 = np.zeros_like(og)
+    p.set_og(og2)
+    p.set_n(150)
+    T2, g2 = p.plan(xs, xg)
+    assert T2.number_of_nodes() == 151 and p.free.shape[0] == 96 * 96
+    # equals a fresh reference-style run on the new grid with the generator where it now stands
+    q = R.RRTStar(og2, 150, 20, pbar=False, seed=1)
+    q.rand_gen.integers(0, np.argwhere(og == 0).shape[0], size=200)      # the draws plan #1 consumed
+    T3, g3 = q.plan(xs, xg)
+    assert g2 == g3 and list(T2.edges) == list(T3.edges)
+
+
+def test_go2goal_standalone():
+    og = R.perlin_occupancygrid(96, 96, seed=3)
+    xs, xg = R.worlds.start_goal(og, 1)
+    smp = O.sample_stream(og, 120, 5)
+    t = O.plan_star(og, 120, 20, xs, xg, smp)
+    from collections import defaultdict
+    p = R.RRTStar(og, 120, 20, pbar=False)
+    j = t.j
+    pts = np.full((120, 2), np.iinfo(np.int64).min, dtype=np.int64)
+    pts[:j] = t.points[:j]
+    vc = np.full(120, np.inf)
+    vc[:j] = t.vcosts[:j]
+    vgoal, ch, par, P2, C2 = p.go2goal(vc, pts, xg, j, defaultdict(list), {})
+    assert int(vgoal) == int(t.vgoal)
+    if t.found:
+        assert par[vgoal] == int(t.parents[t.vgoal]) and C2[vgoal] == t.vcosts[t.vgoal]
