@@ -1,0 +1,389 @@
+"""Benchmark of the north-star metric: batched RRT* plans/s (512x512 worlds, n=5000, r_rewire=50).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--plans P] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: P independent RRT* plans per GPU (world w
+seeded 1000+w, one start/goal pair per world, sample stream of plan p = default_rng(p)), i.e. the
+sampler kernel + the persistent plan kernel.  N > 1 is launched by torchrun, one rank per GPU;
+plans are independent so every rank runs its own P plans (weak scaling, no data-path collective);
+only per-plan statistics are gathered at the end of each step.
+
+The JSON line carries, besides the contract keys: `roofline` (plan kernel: algorithmic bytes /
+CUDA-event time against the shared-memory bandwidth of SURVEY.md section 8(d), plus an HBM view), `e2e`
+(same metric through the host-buffer C-ABI call rrtk_ctx_plan: H2D of grids/descriptors/seeds and
+D2H of all trees inside the timed region), `cpu_baseline` (the oracle's Python/Numba port of the
+reference, one core, a bounded sample of the same plans) and `clocks`.
+
+`--impl reference` times the reference's CPU algorithm (oracle/rrt_oracle.py: the numpy/Numba port
+with the reference's cost profile -- the Python reference itself cannot travel to the GPU box) on
+all host cores, one plan per process, on the same worlds / pairs / streams.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W = H = 512
+N_ITER = 5000
+R_REWIRE = 50.0
+METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
+WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# workload definition shared by both arms
+# ------------------------------------------------------------------------------------------------
+def plan_ids(rank: int, plans_per_gpu: int) -> np.ndarray:
+    return np.arange(rank * plans_per_gpu, (rank + 1) * plans_per_gpu)
+
+
+def host_world_and_pair(pid: int):
+    """CPU construction of plan pid's inputs (identical to what the GPU arm builds on the device)."""
+    from rrtplanner_b200 import worlds
+    og = worlds.perlin_occupancygrid(W, H, seed=worlds.world_seed(pid)).astype(np.uint8)
+    xs, xg = worlds.start_goal(og, pid)
+    return og, xs, xg
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm
+# ------------------------------------------------------------------------------------------------
+def _cpu_one(pid: int):
+    from oracle import rrt_oracle as O
+    og, xs, xg = host_world_and_pair(pid)
+    smp = O.sample_stream(og, N_ITER, pid)
+    t = time.perf_counter()
+    tree = O.plan_star(og, N_ITER, R_REWIRE, xs, xg, smp)
+    return time.perf_counter() - t, tree.j, tree.checks, float(tree.vcosts[tree.vgoal])
+
+
+def _cpu_warm():
+    """JIT-compile the two Numba functions before forking / timing (rrt.py:10,183-184 are JIT'd too)."""
+    from oracle import rrt_oracle as O
+    og = np.zeros((32, 32), dtype=np.uint8)
+    O.plan_star(og, 20, 5.0, [1, 1], [20, 20], O.sample_stream(og, 20, 0))
+
+
+def cpu_baseline_single(nplans: int = 3):
+    _cpu_warm()
+    t0 = time.perf_counter()
+    recs = [_cpu_one(p) for p in range(nplans)]
+    dt = time.perf_counter() - t0
+    return {"value": nplans / dt, "unit": "plans/s", "cores": 1, "kind": "port",
+            "sample": f"plans 0..{nplans - 1} of the workload run sequentially with oracle/rrt_oracle.py:plan_star "
+                      f"(numpy + Numba port with the reference's per-iteration cost profile), {dt:.1f} s",
+            "checks_per_s": sum(r[2] for r in recs) / dt}
+
+
+def reference_arm(args):
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    _cpu_warm()                                  # compile before fork so workers inherit the JIT code
+    ctx = mp.get_context("fork")
+    per_step = cores
+    times = []
+    with ctx.Pool(cores) as pool:
+        for s in range(args.warmup + args.steps):
+            ids = [(s * per_step + k) % 4096 for k in range(per_step)]
+            t0 = time.perf_counter()
+            recs = pool.map(_cpu_one, ids, chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+                checks = sum(r[2] for r in recs)
+    total = sum(times)
+    value = per_step * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "plans/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "plans_per_step": per_step,
+                   "note": "CPU arm: each step is a bounded sample of the workload, one plan per host core"},
+        "cpu_baseline": {"value": value, "unit": "plans/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} plans per step, one per process on {cores} cores, oracle/rrt_oracle.py:plan_star"},
+        "e2e": {"value": value, "unit": "plans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "collision_checks_per_s": checks / times[-1], "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from rrtplanner_b200 import _lib, batch, worlds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if _lib.lib().rrtk_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    P = args.plans
+    ids = plan_ids(rank, P)
+
+    # ---- setup (untimed): worlds, pairs, descriptors resident in HBM -------------------------
+    db = batch.DeviceBatch("star", W, H, N_ITER, R_REWIRE, device=local, threads=args.threads)
+    db.gen_worlds([worlds.world_seed(int(p)) for p in ids])
+    # start/goal of plan p = first two distinct draws of free[default_rng(2000+p).integers(nfree)]
+    # (worlds.start_goal), produced with the device sampler so no grid has to visit the host
+    pair_db = batch.DeviceBatch("star", W, H, 8, device=local)
+    pair_db.bits, pair_db.rowcum = db.bits, db.rowcum
+    pair_db.set_plans(batch.make_desc(np.arange(P), np.zeros((P, 2)), np.zeros((P, 2))))
+    pair_db.seed_samples(2000 + ids)
+    draws = pair_db.samples.cpu().numpy().astype(np.int64)
+    starts = draws[:, 0]
+    differs = (draws[:, 1:] != starts[:, None]).any(axis=2)
+    goals = draws[np.arange(P), 1 + differs.argmax(axis=1)]
+    desc = batch.make_desc(np.arange(P), starts, goals)
+    db.set_plans(desc)
+    states = torch.from_numpy(batch.seed_states(ids).view(np.int64)).to(dev)
+    db.samples = torch.empty((P, N_ITER, 2), dtype=torch.int16, device=dev)
+    L = db.L
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        _lib.check(L.rrtk_sample_streams(db.bits.data_ptr(), db.rowcum.data_ptr(), W, H, db.desc.data_ptr(), P, states.data_ptr(),
+                                         N_ITER, db.samples.data_ptr(), stream.cuda_stream), "sample_streams")
+        db.run()
+
+    gathered = [torch.empty_like(db.out["stats"]) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def gather_stats():
+        if world > 1:
+            dist.gather(db.out["stats"], gathered, dst=0)
+
+    for _ in range(args.warmup):
+        step()
+        gather_stats()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream -----------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_begin.record(stream)
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        _lib.check(L.rrtk_sample_streams(db.bits.data_ptr(), db.rowcum.data_ptr(), W, H, db.desc.data_ptr(), P, states.data_ptr(),
+                                         N_ITER, db.samples.data_ptr(), stream.cuda_stream), "sample_streams")
+        ev[k][1].record(stream)
+        db.run()
+        ev[k][2].record(stream)
+        gather_stats()
+    e_end.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    ms_total = e_begin.elapsed_time(e_end)
+    ms_sampler = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(args.steps)]))
+    ms_plan = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(args.steps)]))
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    stats = db.out["stats"].cpu().numpy()
+    S = {n: stats[:, i] for i, n in enumerate(_lib.STAT_NAMES)}
+    if world > 1 and rank == 0:
+        all_stats = torch.stack(gathered).cpu().numpy().reshape(-1, _lib.STAT_COUNT)
+    else:
+        all_stats = stats
+
+    # ---- end-to-end through the host-buffer C ABI (what a Python caller of plan_batch gets) ----
+    e2e = None
+    if not args.no_e2e:
+        Pe = min(P, args.e2e_plans)
+        og_pinned = torch.empty((Pe, W, H), dtype=torch.uint8, pin_memory=True)
+        og_pinned.copy_(db.og[:Pe])
+        torch.cuda.synchronize(dev)
+        og_host = og_pinned.numpy()
+        out = (torch.empty((Pe, N_ITER + 1, 2), dtype=torch.int16, pin_memory=True).numpy(),
+               torch.empty((Pe, N_ITER + 1), dtype=torch.float64, pin_memory=True).numpy(),
+               torch.empty((Pe, N_ITER + 1), dtype=torch.int32, pin_memory=True).numpy(),
+               torch.empty((Pe, _lib.STAT_COUNT), dtype=torch.int64, pin_memory=True).numpy(), None)
+        ctx = _lib.Context()
+        desc_e = desc[:Pe]
+
+        def e2e_step():
+            ctx.set_grids(og_host)                                   # H2D of the grids + K0 + free index
+            st = batch.seed_states(ids[:Pe])                         # seeds -> PCG64 states (host)
+            ctx.plan(_lib.KIND_STAR, desc_e, N_ITER, R_REWIRE, states=st, out=out)     # H2D, sampler, K7, D2H
+
+        for _ in range(max(1, args.warmup - 1)):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        same = np.array_equal(out[3][:, :3], stats[:Pe, :3]) and np.array_equal(out[1], db.out["cost"][:Pe].cpu().numpy())
+        e2e = {"value": Pe * world * args.steps / dt, "unit": "plans/s",
+               "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
+               "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8 + 4)),
+               "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt / args.steps,
+               "api": "rrtk_ctx_set_grids + rrtk_ctx_plan (seed mode) via rrtplanner_b200._lib.Context, pinned host buffers",
+               "matches_device_arm": bool(same)}
+        ctx.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- derived numbers ------------------------------------------------------------------------
+    plans_total = P * world
+    value = plans_total * args.steps / (ms_total / 1000.0)
+    nn_pairs, ring, cells, checks = (float(S[k].sum()) for k in ("nn_pairs", "ring_members", "cells", "checks"))
+    alg_bytes = 8.0 * nn_pairs + 8.0 * ring + 4.0 * cells          # SURVEY.md section 8(d) per-unit figures, one launch
+    achieved = alg_bytes / (ms_plan / 1000.0) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_mhz = clocks.get("sm_mhz") or peaks.get("clocks_under_load", {}).get("sm_mhz_median") or 1965.0
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    smem_peak = 128.0 * sms * sm_mhz * 1e6 / 1e9                      # 128 B/clk/SM x SMs x measured SM clock
+    hbm_bytes = P * (db.words * 4 + N_ITER * 4 + (N_ITER + 1) * 16 + 64 + _lib.STAT_COUNT * 8)
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    smem_b, blocks_per_sm = db.footprint()
+    roofline = {
+        "kernel": "rrtk::plan_kernel<RRTK_STAR, grid in smem>", "bound": "smem", "achieved": achieved, "peak": smem_peak,
+        "unit": "GB/s", "frac": achieved / smem_peak, "traffic": None,
+        "peak_source": f"128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz SM clock sampled during the timed region (SURVEY.md 8(d)); "
+                       "MEASURED_PEAKS.json has no shared-memory figure",
+        "algorithmic_bytes_per_launch": alg_bytes,
+        "bytes_model": "8 B x (iteration, filled vertex) pairs + 8 B x radius-set members + 4 B x grid cells tested",
+        "kernel_ms": ms_plan, "smem_bytes_actually_read_per_launch": 4.0 * nn_pairs + 4.0 * ring + 4.0 * cells,
+        "hbm_view": {"bytes_per_launch": hbm_bytes, "achieved": hbm_bytes / (ms_plan / 1000.0) / 1e9, "peak": hbm_peak,
+                     "frac": hbm_bytes / (ms_plan / 1000.0) / 1e9 / hbm_peak,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650"},
+        "iterations_per_s_per_sm": P * N_ITER / (ms_plan / 1000.0) / sms,
+        "blocks_per_sm": blocks_per_sm, "smem_bytes_per_block": smem_b,
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": "plans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "plans_per_gpu": P, "plans_total": plans_total, "threads_per_plan": args.threads or "default",
+                   "l2": "inputs+outputs per step (%.0f MB) exceed the 126 MB L2; no explicit flush" % (hbm_bytes / 1e6),
+                   "obstacle_fraction": float(db.og[: min(P, 256)].float().mean().item()),
+                   "mean_vertices": float(all_stats[:, 0].mean()), "goal_found_frac": float(all_stats[:, 2].mean())},
+        "clocks": clocks,
+        "roofline": roofline,
+        "collision_checks_per_s": checks * world / (ms_plan / 1000.0),
+        "collision_cells_per_s": cells * world / (ms_plan / 1000.0),
+        "kernel_ms": {"sample_streams": ms_sampler, "plan": ms_plan},
+        "gpu_launches": 2 * args.steps,
+        "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_single(args.cpu_plans)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--plans", type=int, default=4096, help="plans per GPU per step")
+    ap.add_argument("--threads", type=int, default=0, help="threads per plan block (0 = library default)")
+    ap.add_argument("--e2e-plans", type=int, default=4096)
+    ap.add_argument("--cpu-plans", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,15 +149,20 @@ class Context:
         return nfree
 
     # -- plans ---------------------------------------------------------------------------------
-    def plan(self, kind, desc, n, r_rewire=0.0, r_goal=0.0, samples=None, states=None, balls=None):
+    def plan(self, kind, desc, n, r_rewire=0.0, r_goal=0.0, samples=None, states=None, balls=None, out=None):
+        """``out``: optional preallocated (pts, cost, parent, stats, ell) host arrays (e.g. pinned)."""
         nplans = desc.shape[0]
         desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
-        rows = nplans * (n + 1)
-        pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
-        cost = np.empty((nplans, n + 1), dtype=np.float64)
-        parent = np.empty((nplans, n + 1), dtype=np.int32)
-        stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
-        ell = np.empty((nplans, n + 1), dtype=np.float64) if kind == KIND_INFORMED else None
+        if out is not None:
+            pts, cost, parent, stats, ell = out
+            assert pts.shape == (nplans, n + 1, 2) and pts.dtype == np.int16 and cost.shape == (nplans, n + 1)
+            assert parent.dtype == np.int32 and stats.shape == (nplans, STAT_COUNT)
+        else:
+            pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
+            cost = np.empty((nplans, n + 1), dtype=np.float64)
+            parent = np.empty((nplans, n + 1), dtype=np.int32)
+            stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
+            ell = np.empty((nplans, n + 1), dtype=np.float64) if kind == KIND_INFORMED else None
         if samples is not None:
             samples = np.ascontiguousarray(samples, dtype=np.int16)
             assert samples.shape == (nplans, n, 2), samples.shape
@@ -170,7 +175,6 @@ class Context:
         check(lib().rrtk_ctx_plan(self._h, kind, ptr(desc), nplans, n, float(r_rewire), float(r_goal), ptr(samples),
                                   ptr(states), ptr(balls), ptr(pts), ptr(cost), ptr(parent), ptr(stats), ptr(ell)),
               "rrtk_ctx_plan")
-        del rows
         return pts, cost, parent, stats, ell
 
     def samples(self, desc, n, states):

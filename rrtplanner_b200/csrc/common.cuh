@@ -40,10 +40,13 @@ struct GlobalGrid {
     __device__ __forceinline__ uint32_t load(uint32_t i) const { return __ldg(w + i); }
 };
 
-// floor(num / den) for 0 <= num < 2^24, 0 < den < 2^24 via one fp32 reciprocal and a fix-up.
+// floor(num / den) for 0 <= num < 2^24, 0 < den < 2^24 and a quotient <= 64, via one approximate
+// fp32 reciprocal and a +-1 fix-up (the estimate is within 1e-5 of the true quotient).
 __device__ __forceinline__ int small_div(int num, int den, int &rem)
 {
-    int q = __float2int_rz(__int2float_rn(num) * __frcp_rn(__int2float_rn(den)));
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__int2float_rn(den)));      // one MUFU; the fix-up absorbs its error
+    int q = __float2int_rz(__int2float_rn(num) * inv);
     int r = num - q * den;
     if (r < 0) { r += den; --q; }
     if (r >= den) { r -= den; ++q; }

@@ -8,30 +8,33 @@
 // reference run on the same sample stream with its two unstable argsorts pinned to "lowest index
 // first" (SURVEY.md section 8(c)); tests/test_plan_gpu.py checks that bit for bit.
 //
-// Per iteration (block-wide, 1 barrier if the sample is rejected, 2 if accepted):
+// Per iteration (block-wide, 1 barrier if the sample is a duplicate / the tree is full, else 2):
 //   scan      every thread visits 4 vertices per 128-bit shared load: exact integer d^2, running
-//             (min d^2, lowest index), and -- RRT*/informed -- radius-set members appended to a
-//             shared list.  Unfilled slots hold a far-away sentinel, so the loop has no tail
-//             predicates.  Vertex 0 (the start) is kept in registers and merged after the scan so
-//             that "d^2 == 0 among vertices >= 1" is exactly the reference's `sampled` set test.
-//   barrier 1 per-warp minima are combined by every warp redundantly (no second barrier).
-//   gate      every warp redundantly walks nearest -> sample (rrt.py:424/506/706).
-//   choose    radius-set members are dealt to warps; lanes evaluate cost in FP64 (exact d^2,
-//             __dsqrt_rn, __dadd_rn), candidates that beat the nearest vertex's cost are walked
-//             warp-cooperatively, each warp keeps its (cost, index) minimum.
-//   barrier 2 minima combined; thread 0 stores cost/parent of the new vertex.
+//             (min d^2, lowest index), and -- RRT*/informed -- one radius-set membership bit per
+//             visited vertex in a word private to the thread (no atomics, no shared list).
+//             Unfilled slots hold a far-away sentinel, so the loop has no tail predicates.
+//             Vertex 0 (the start) is kept in registers and merged after the scan so that
+//             "d^2 == 0 among vertices >= 1" is exactly the reference's `sampled` set test.
+//   barrier 1 per-warp minima are combined by every warp redundantly (REDUX, no extra barrier).
+//   gate      warp 0 walks nearest -> sample (rrt.py:424/506/706) and publishes the verdict ...
+//   choose    ... while every warp already evaluates its own radius-set members: cost in FP64
+//             (exact d^2, __dsqrt_rn, __dadd_rn); members that beat the nearest vertex's cost and
+//             the warp's best so far are walked warp-cooperatively.
+//   barrier 2 verdict read; per-warp (cost, index) minima combined with three REDUX; thread 0
+//             stores cost/parent of the new vertex.
 //
 // The reference's "rewire" block (rrt.py:532-546, 732-742) tests vcosts[vn] + d < vcosts[vn] and
 // can never fire with the default cost function (oracle/rrt_oracle.py counts it: always 0), so
 // it has no device counterpart.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rrtk {
 
 constexpr int kMaxWarps = 16;
-constexpr int kGranule = 4;   // radius-set entries are dealt to warps in runs of 4 lanes
 
 struct PlanParams {
     const uint32_t *bits;
@@ -80,10 +83,10 @@ __global__ void plan_kernel(PlanParams P)
     __shared__ uint2 s_near[2][kMaxWarps];            // per-warp (min d2, index), double-buffered
     __shared__ double s_bestc[kMaxWarps];
     __shared__ int s_bestv[kMaxWarps];
-    __shared__ int s_ringcnt[2];
+    __shared__ int s_gate;
     __shared__ unsigned long long s_goalc;
     __shared__ int s_goalv;
-    __shared__ unsigned long long s_checks, s_cells;
+    __shared__ unsigned long long s_checks, s_cells, s_ring_total;
 
     const int tid = threadIdx.x, T = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nw = T >> 5;
@@ -91,10 +94,11 @@ __global__ void plan_kernel(PlanParams P)
     const int n = P.n;
     const int npad = (n + 1 + 3) & ~3;
 
+    const int log2T = 31 - __clz(T);                                  // T is a power of two (checked by the launcher)
+    const int hit_words_max = ((((npad >> 2) + T - 1) >> log2T) + 7) >> 3;
     uint32_t *s_pts = smem;                                           // npad words
-    uint16_t *s_ring = reinterpret_cast<uint16_t *>(smem + npad);     // n + 1 entries
-    uint32_t *s_grid = smem + npad + ((n + 1 + 1) >> 1);              // grid words (GRID_SMEM)
-    s_grid = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(s_grid) + 15) & ~uintptr_t(15));
+    uint32_t *s_hit = smem + npad;                                    // hit_words_max * T words, thread-private
+    uint32_t *s_grid = s_hit + ((hit_words_max * T + 3) & ~3);        // grid words (GRID_SMEM)
 
     const rrtk_plan_desc d = P.plans[plan];
     const uint32_t *gbits = P.bits + (size_t)d.world * P.words_per_grid;
@@ -108,8 +112,8 @@ __global__ void plan_kernel(PlanParams P)
         for (size_t i = tid; i < P.words_per_grid / 4; i += T) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        s_ringcnt[0] = s_ringcnt[1] = 0;
-        s_checks = s_cells = 0ull;
+        s_gate = 0;
+        s_checks = s_cells = s_ring_total = 0ull;
     }
     __syncthreads();
 
@@ -136,7 +140,8 @@ __global__ void plan_kernel(PlanParams P)
     bool have_sol = false;              // INFORMED: running least_cost over vsoln (rrt.py:627-633)
     int vsol = 0;
     double csol = 0.0;
-    long long first_sol = -1, ell_iters = 0, nn_pairs = 0, ring_members = 0, accepted = 0;
+    long long first_sol = -1, ell_iters = 0, nn_pairs = 0, accepted = 0;
+    unsigned ring_count = 0;                // radius-set members seen by this thread
     unsigned my_checks = 0, my_cells = 0;   // per-warp counters (lane 0 meaningful)
 
     short2 snext = samples[0];
@@ -154,39 +159,43 @@ __global__ void plan_kernel(PlanParams P)
             ++ell_iters;
         }
         const int par = it & 1;
-        if (KIND != RRTK_STANDARD && tid == 0) s_ringcnt[par ^ 1] = 0;
 
         // ---- scan: nearest + radius set over vertices 1 .. j-1 ------------------------------
+        // Radius-set membership is recorded as one bit per visited vertex in a word private to
+        // the visiting thread (4 bits per step, 8 steps per word): no atomics, no shared list.
         uint32_t bd = 0xffffffffu, bi = 0;
+        const int nquads = (j + 3) >> 2;
+        const int hit_words = (((nquads + T - 1) >> log2T) + 7) >> 3;     // block-uniform
         {
             const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts);
-            const int nquads = (j + 3) >> 2;
             const uint32_t r2x = P.r2_excl;
-#define VISIT(word_, v_)                                                     \
+            uint32_t hits = 0;
+            int step = 0;
+#define VISIT(word_, v_, bit_)                                               \
     {                                                                        \
         const uint32_t dd = dist2(word_, x, y);                              \
         if (dd < bd) { bd = dd; bi = (v_); }                                 \
-        if (KIND != RRTK_STANDARD && dd < r2x) {                             \
-            const int pos = atomicAdd(&s_ringcnt[par], 1);                   \
-            s_ring[pos] = (uint16_t)(v_);                                    \
-        }                                                                    \
+        if (KIND != RRTK_STANDARD && dd < r2x) nib |= (bit_);                \
     }
 #pragma unroll 2
-            for (int q = tid; q < nquads; q += T) {
+            for (int q = tid; q < nquads; q += T, ++step) {
                 const uint4 w = q4[q];
                 const int v = q << 2;
-                VISIT(w.x, v)
-                VISIT(w.y, v + 1)
-                VISIT(w.z, v + 2)
-                VISIT(w.w, v + 3)
+                uint32_t nib = 0;
+                VISIT(w.x, v, 1u)
+                VISIT(w.y, v + 1, 2u)
+                VISIT(w.z, v + 2, 4u)
+                VISIT(w.w, v + 3, 8u)
+                if (KIND != RRTK_STANDARD) {
+                    hits |= nib << ((step & 7) << 2);
+                    if ((step & 7) == 7) { s_hit[(step >> 3) * T + tid] = hits; hits = 0; }
+                }
             }
 #undef VISIT
+            if (KIND != RRTK_STANDARD)
+                for (int wd = step >> 3; wd < hit_words; ++wd) { s_hit[wd * T + tid] = hits; hits = 0; }
         }
         const uint32_t d2s = dist2(startp, x, y);
-        if (KIND != RRTK_STANDARD && tid == 0 && d2s < P.r2_excl) {
-            const int pos = atomicAdd(&s_ringcnt[par], 1);
-            s_ring[pos] = 0;
-        }
         {   // warp minimum, lowest index among equals
             const uint32_t wd = warp_min_u32(bd);
             const uint32_t wi = warp_min_u32(bd == wd ? bi : 0xffffffffu);
@@ -208,11 +217,9 @@ __global__ void plan_kernel(PlanParams P)
         if (d2s <= bd) { bd = d2s; bi = 0; }        // vertex 0 wins ties (lowest index)
         const int vnear = (int)bi;
         const uint32_t pnear = vnear == 0 ? startp : (KIND == RRTK_STANDARD && vnear == lastv ? lastp : s_pts[vnear]);
-
-        // ---- gate: rrt.py:424-425 / 506-507 / 706-707 ---------------------------------------
-        const int hit = WALK(px(pnear), py(pnear), x, y);
-        if (warp == 0) { my_checks += 1; my_cells += cells_tested(hit); }
-        if (hit >= 0 || dup || j == n) continue;
+        // the reference walks nearest -> sample before looking at the other two gate terms
+        // (rrt.py:424-425 / 506-507 / 706-707); they do not depend on the walk, so test them first
+        if (dup || j == n) continue;
 
         const double cnear = vnear == 0 ? 0.0 : (KIND == RRTK_STANDARD && vnear == lastv ? lastc : cost[vnear]);
         const double c0 = reach_cost(cnear, bd);
@@ -221,46 +228,75 @@ __global__ void plan_kernel(PlanParams P)
         const uint32_t pnew = pack_xy(x, y);
 
         if (KIND == RRTK_STANDARD) {
+            const int hit = WALK(px(pnear), py(pnear), x, y);              // every warp, redundantly: no 2nd barrier
+            if (warp == 0) { my_checks += 1; my_cells += cells_tested(hit); }
+            if (hit >= 0) continue;
             if (tid == 0) { s_pts[j] = pnew; cost[j] = c0; parent[j] = vnear; }
             lastp = pnew; lastv = j; lastc = c0;
         } else {
-            if (tid == 0) s_pts[j] = pnew;          // nobody reads slot j before barrier 2
-            // ---- choose parent: rrt.py:510-521 ----------------------------------------------
-            const int cnt = s_ringcnt[par];
-            ring_members += cnt;
+            // ---- gate (warp 0 only) overlapped with choose-parent (all warps): rrt.py:506-521 ----
             double wc = CUDART_INF;                 // this warp's best (cost, vertex)
             int wv = 0x7fffffff;
-            for (int base = 0; base < cnt; base += 32 * nw) {
-                const int e = base + (lane / kGranule) * (kGranule * nw) + warp * kGranule + (lane % kGranule);
-                const bool valid = e < cnt;
-                const int v = valid ? (int)s_ring[e] : 0;
-                const uint32_t p = v == 0 ? startp : s_pts[v];
-                double cn = CUDART_INF;
-                if (valid) cn = reach_cost(v == 0 ? 0.0 : cost[v], dist2(p, x, y));
-                unsigned m = __ballot_sync(RRTK_FULL, valid && cn < c0);
-                while (m) {
-                    const int l = __ffs(m) - 1;
-                    m &= m - 1;
-                    const double cv = __shfl_sync(RRTK_FULL, cn, l);
-                    const int vv = __shfl_sync(RRTK_FULL, v, l);
-                    const uint32_t pp = __shfl_sync(RRTK_FULL, p, l);
-                    if (cv < wc || (cv == wc && vv < wv)) {
-                        const int h = WALK(px(pp), py(pp), x, y);
-                        my_checks += 1; my_cells += cells_tested(h);
-                        if (h < 0) { wc = cv; wv = vv; }
+            bool warp_active = true;
+            if (warp == 0) {
+                const int hit = WALK(px(pnear), py(pnear), x, y);
+                my_checks += 1; my_cells += cells_tested(hit);
+                if (lane == 0) {
+                    s_gate = hit < 0;
+                    if (hit < 0) s_pts[j] = pnew;   // nobody reads slot j before barrier 2
+                }
+                warp_active = hit < 0;
+            }
+            unsigned ring_it = 0;
+            if (warp_active && warp == nw - 1 && d2s < P.r2_excl) {            // vertex 0 lives in registers
+                const double cn = reach_cost(0.0, d2s);
+                if (cn < c0) {
+                    const int h = WALK(sx, sy, x, y);
+                    my_checks += 1; my_cells += cells_tested(h);
+                    if (h < 0) { wc = cn; wv = 0; }
+                }
+                if (lane == 0) ring_it = 1;
+            }
+            for (int wd = 0; warp_active && wd < hit_words; ++wd) {
+                uint32_t bits = s_hit[wd * T + tid];             // written by this very thread
+                ring_it += __popc(bits);
+                while (__any_sync(RRTK_FULL, bits != 0)) {
+                    const bool has = bits != 0;
+                    const int b = has ? __ffs(bits) - 1 : 0;
+                    bits &= bits - 1;
+                    const int v = ((tid + (wd * 8 + (b >> 2)) * T) << 2) + (b & 3);
+                    const uint32_t p = has ? s_pts[v] : 0u;
+                    double cn = CUDART_INF;
+                    if (has) cn = reach_cost(cost[v], dist2(p, x, y));
+                    unsigned m = __ballot_sync(RRTK_FULL, cn < c0);
+                    while (m) {
+                        const int l = __ffs(m) - 1;
+                        m &= m - 1;
+                        const double cv = __shfl_sync(RRTK_FULL, cn, l);
+                        const int vv = __shfl_sync(RRTK_FULL, v, l);
+                        if (cv < wc || (cv == wc && vv < wv)) {
+                            const uint32_t pp = __shfl_sync(RRTK_FULL, p, l);
+                            const int h = WALK(px(pp), py(pp), x, y);
+                            my_checks += 1; my_cells += cells_tested(h);
+                            if (h < 0) { wc = cv; wv = vv; }
+                        }
                     }
                 }
             }
             if (lane == 0) { s_bestc[warp] = wc; s_bestv[warp] = wv; }
             __syncthreads();                                               // ---- barrier 2
-            double bc = CUDART_INF;
-            int bv = 0x7fffffff;
-            for (int w = 0; w < nw; ++w) {
-                const double c = s_bestc[w];
-                const int v = s_bestv[w];
-                if (c < bc || (c == bc && v < bv)) { bc = c; bv = v; }
+            if (!s_gate) continue;
+            ring_count += ring_it;
+            {   // minimum (cost, vertex) over the warps: costs are positive doubles, so their bit
+                // patterns order like unsigned integers
+                const double c = lane < nw ? s_bestc[lane] : CUDART_INF;
+                const uint32_t v = lane < nw ? (uint32_t)s_bestv[lane] : 0x7fffffffu;
+                const uint32_t hi = (uint32_t)__double2hiint(c), lo = (uint32_t)__double2loint(c);
+                const uint32_t mhi = warp_min_u32(hi);
+                const uint32_t mlo = warp_min_u32(hi == mhi ? lo : 0xffffffffu);
+                const uint32_t mv = warp_min_u32(hi == mhi && lo == mlo ? v : 0xffffffffu);
+                if (mv != 0x7fffffffu) { vbest = (int)mv; cbest = __hiloint2double((int)mhi, (int)mlo); }
             }
-            if (bv != 0x7fffffff) { vbest = bv; cbest = bc; }
             if (tid == 0) { cost[j] = cbest; parent[j] = vbest; }          // rrt.py:524-529
         }
         if (KIND == RRTK_INFORMED) {
@@ -318,9 +354,11 @@ __global__ void plan_kernel(PlanParams P)
             }
         }
     }
+    ring_count = __reduce_add_sync(RRTK_FULL, ring_count);
     if (lane == 0) {
         atomicAdd(&s_checks, (unsigned long long)my_checks);
         atomicAdd(&s_cells, (unsigned long long)my_cells);
+        atomicAdd(&s_ring_total, (unsigned long long)ring_count);
     }
     __syncthreads();
 
@@ -353,7 +391,7 @@ __global__ void plan_kernel(PlanParams P)
         st[RRTK_STAT_FIRST_SOL_ITER] = first_sol;
         st[RRTK_STAT_ELL_ITERS] = ell_iters;
         st[RRTK_STAT_NN_PAIRS] = nn_pairs;
-        st[RRTK_STAT_RING_MEMBERS] = ring_members;
+        st[RRTK_STAT_RING_MEMBERS] = (long long)s_ring_total;
         st[RRTK_STAT_ACCEPTED] = accepted;
         st[RRTK_STAT_RESERVED0] = 0;
         st[RRTK_STAT_RESERVED1] = 0;
@@ -361,64 +399,81 @@ __global__ void plan_kernel(PlanParams P)
 #undef WALK
 }
 
-static size_t plan_smem_bytes(int W, int H, int n, bool grid_smem)
+static size_t plan_smem_bytes(int W, int H, int n, int threads, bool grid_smem)
 {
     const size_t npad = (size_t)((n + 1 + 3) & ~3);
-    size_t words = npad + (size_t)((n + 2) >> 1) + 4;    // +4: alignment slack for the grid
+    const size_t hit_words = ((((npad >> 2) + threads - 1) / threads) + 7) >> 3;
+    size_t words = npad + ((hit_words * threads + 3) & ~(size_t)3);
     if (grid_smem) words += grid_words(W, H);
     return words * 4;
 }
 
-template <int KIND>
-static int launch_kind(const PlanParams &P, int nplans, int W, int H, int n, int threads, int optin, cudaStream_t st)
+// Where does the bit grid live?  Shared memory gives the shortest walk latency, but the tree
+// (4 B / vertex) is what must stay on chip; when staging the grid as well would lower the number
+// of resident plan blocks per SM, the grid is left in global memory (read-only path, L1/L2
+// resident: one tile = one 128-byte line).  RRTK_GRID_SMEM=0/1 overrides for experiments.
+static int blocks_by_smem(size_t bytes, int threads, int sm_smem)
 {
-    const size_t with_grid = plan_smem_bytes(W, H, n, true);
-    const size_t without = plan_smem_bytes(W, H, n, false);
-    // static shared (slots, counters) is < 1 KB; keep 2 KB headroom
+    int by_smem = (int)((size_t)sm_smem / (bytes + 1024 + 1024));   // + static + per-block reservation
+    int by_threads = 2048 / threads;
+    int r = by_smem < by_threads ? by_smem : by_threads;
+    return r < 1 ? 1 : (r > 32 ? 32 : r);
+}
+static bool choose_grid_smem(int W, int H, int n, int threads, int optin, int sm_smem, size_t *bytes)
+{
     const size_t budget = (size_t)optin - 2048;
-    if (without > budget) {
-        set_error("plan does not fit shared memory: n=%d needs %zu bytes, device allows %zu", n, without, budget);
+    const size_t with_grid = plan_smem_bytes(W, H, n, threads, true);
+    const size_t without = plan_smem_bytes(W, H, n, threads, false);
+    bool in_smem = with_grid <= budget && blocks_by_smem(with_grid, threads, sm_smem) >= blocks_by_smem(without, threads, sm_smem);
+    const char *force = getenv("RRTK_GRID_SMEM");
+    if (force && force[0] == '0') in_smem = false;
+    if (force && force[0] == '1' && with_grid <= budget) in_smem = true;
+    *bytes = in_smem ? with_grid : without;
+    return in_smem;
+}
+
+template <int KIND>
+static int launch_kind(const PlanParams &P, int nplans, int W, int H, int n, int threads, int optin, int sm_smem, cudaStream_t st)
+{
+    size_t bytes = 0;
+    const bool in_smem = choose_grid_smem(W, H, n, threads, optin, sm_smem, &bytes);
+    if (bytes > (size_t)optin - 2048) {   // static shared (slots, counters) is < 1 KB; keep 2 KB headroom
+        set_error("plan does not fit shared memory: n=%d needs %zu bytes, device allows %zu", n, bytes, (size_t)optin - 2048);
         return RRTK_ERR_CAPACITY;
     }
-    if (with_grid <= budget) {
-        RRTK_CUDA(cudaFuncSetAttribute(plan_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)with_grid));
-        plan_kernel<KIND, true><<<nplans, threads, with_grid, st>>>(P);
+    if (in_smem) {
+        RRTK_CUDA(cudaFuncSetAttribute(plan_kernel<KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        plan_kernel<KIND, true><<<nplans, threads, bytes, st>>>(P);
     } else {
-        RRTK_CUDA(cudaFuncSetAttribute(plan_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)without));
-        plan_kernel<KIND, false><<<nplans, threads, without, st>>>(P);
+        RRTK_CUDA(cudaFuncSetAttribute(plan_kernel<KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        plan_kernel<KIND, false><<<nplans, threads, bytes, st>>>(P);
     }
     RRTK_CUDA(cudaGetLastError());
     return RRTK_OK;
 }
 
-int plan_default_threads(int n) { return n >= 2048 ? 256 : 128; }
+int plan_default_threads(int n) { return n >= 1024 ? 128 : 64; }
 
 int plan_footprint(int kind, int W, int H, int n, int threads, int optin, int sm_smem, int *smem_bytes, int *blocks_per_sm)
 {
     (void)kind;
     if (threads <= 0) threads = plan_default_threads(n);
-    const size_t budget = (size_t)optin - 2048;
-    size_t b = plan_smem_bytes(W, H, n, true);
-    if (b > budget) b = plan_smem_bytes(W, H, n, false);
-    if (b > budget) return RRTK_ERR_CAPACITY;
+    size_t b = 0;
+    choose_grid_smem(W, H, n, threads, optin, sm_smem, &b);
+    if (b > (size_t)optin - 2048) return RRTK_ERR_CAPACITY;
     if (smem_bytes) *smem_bytes = (int)b;
-    if (blocks_per_sm) {
-        int by_smem = (int)((size_t)sm_smem / (b + 1024 + 1024));   // + static + per-block reservation
-        int by_threads = 2048 / threads;
-        int r = by_smem < by_threads ? by_smem : by_threads;
-        *blocks_per_sm = r < 1 ? 1 : (r > 32 ? 32 : r);
-    }
+    if (blocks_per_sm) *blocks_per_sm = blocks_by_smem(b, threads, sm_smem);
     return RRTK_OK;
 }
 
 int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans, int nplans, int n,
                 double r_rewire, double r_goal, const int16_t *d_samples, const double *d_balls, int16_t *d_pts,
                 double *d_cost, int32_t *d_parent, int64_t *d_stats, double *d_ell_c, int threads, int optin,
-                cudaStream_t st)
+                int sm_smem, cudaStream_t st)
 {
     if (threads <= 0) threads = plan_default_threads(n);
-    if (threads % 32 || threads < 32 || threads > 32 * kMaxWarps) {
-        set_error("threads must be a multiple of 32 in [32, %d]", 32 * kMaxWarps);
+    if (threads < 32 || threads > 32 * kMaxWarps || (threads & (threads - 1))) {
+        set_error("threads must be a power of two in [32, %d]", 32 * kMaxWarps);
         return RRTK_ERR_INVALID;
     }
     PlanParams P;
@@ -439,9 +494,9 @@ int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_
     P.stats = reinterpret_cast<long long *>(d_stats);
     P.ell_c = d_ell_c;
     switch (kind) {
-        case RRTK_STANDARD: return launch_kind<RRTK_STANDARD>(P, nplans, W, H, n, threads, optin, st);
-        case RRTK_STAR: return launch_kind<RRTK_STAR>(P, nplans, W, H, n, threads, optin, st);
-        case RRTK_INFORMED: return launch_kind<RRTK_INFORMED>(P, nplans, W, H, n, threads, optin, st);
+        case RRTK_STANDARD: return launch_kind<RRTK_STANDARD>(P, nplans, W, H, n, threads, optin, sm_smem, st);
+        case RRTK_STAR: return launch_kind<RRTK_STAR>(P, nplans, W, H, n, threads, optin, sm_smem, st);
+        case RRTK_INFORMED: return launch_kind<RRTK_INFORMED>(P, nplans, W, H, n, threads, optin, sm_smem, st);
     }
     set_error("unknown planner kind %d", kind);
     return RRTK_ERR_INVALID;

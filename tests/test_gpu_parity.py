@@ -277,6 +277,8 @@ def assert_same_as_oracle(res, p, want):
     assert np.array_equal(res.cost[p, :top].view(np.int64), wc[:top].view(np.int64))
     assert int(res.stats[p, _lib.STAT_NAMES.index("nn_pairs")]) <= wst["nn_pairs"]
     assert int(res.stats[p, _lib.STAT_NAMES.index("accepted")]) == wst["accepted"]
+    if "ring_members" in wst:   # sum over accepted iterations of |within(points, xnew, r_rewire)| (filled rows)
+        assert int(res.stats[p, _lib.STAT_NAMES.index("ring_members")]) == wst["ring_members"]
     if found:   # north star: path cost within 1e-5 relative (it is bit-equal, checked above)
         assert abs(res.path_cost(p) - wc[j]) <= 1e-5 * wc[j]
 
@@ -337,8 +339,12 @@ def test_batch_properties_full_size():
     db.seed_samples(np.arange(nplans) % 50)          # plans p and p+50k on the same world share a stream only if wid matches
     a = db.run().download()
     b = db.run().download()                           # idempotent: same inputs, same bits
-    for f in ("pts", "cost", "parent", "stats"):
+    for f in ("pts", "cost", "parent"):
         assert np.array_equal(getattr(a, f), getattr(b, f))
+    # statistics too, except the two work counters: how many goal-connection candidates get pruned
+    # depends on which warp publishes its result first (results never do)
+    keep = [i for i, nm in enumerate(_lib.STAT_NAMES) if nm not in ("checks", "cells")]
+    assert np.array_equal(a.stats[:, keep], b.stats[:, keep])
     j = a.stat("j")
     assert (j >= 2).all() and (j <= n).all()
     for p in range(0, nplans, 7):
@@ -359,7 +365,7 @@ def test_batch_properties_full_size():
     c = db2.run().download()
     for k, p in enumerate(sub):
         assert np.array_equal(c.pts[k], a.pts[p]) and np.array_equal(c.cost[k].view(np.int64), a.cost[p].view(np.int64))
-        assert np.array_equal(c.parent[k], a.parent[p]) and np.array_equal(c.stats[k], a.stats[p])
+        assert np.array_equal(c.parent[k], a.parent[p]) and np.array_equal(c.stats[k][keep], a.stats[p][keep])
 
 
 # ---- edge cases ----------------------------------------------------------------------------------------
