@@ -280,9 +280,9 @@ def gpu_arm(args):
         desc_e = desc[:Pe]
 
         def e2e_step():
-            ctx.set_grids(og_host)                                   # H2D of the grids + K0 + free index
             st = batch.seed_states(ids[:Pe])                         # seeds -> PCG64 states (host)
-            ctx.plan(_lib.KIND_STAR, desc_e, N_ITER, R_REWIRE, states=st, out=out)     # H2D, sampler, K7, D2H
+            # chunked pipeline: H2D grids, K0 + free index, sampler, K7, D2H of every tree
+            ctx.plan_worlds(_lib.KIND_STAR, og_host, desc_e, N_ITER, R_REWIRE, states=st, out=out, chunk=args.e2e_chunk)
 
         for _ in range(max(1, args.warmup - 1)):
             e2e_step()
@@ -301,7 +301,8 @@ def gpu_arm(args):
                "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
                "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8 + 4)),
                "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt / args.steps,
-               "api": "rrtk_ctx_set_grids + rrtk_ctx_plan (seed mode) via rrtplanner_b200._lib.Context, pinned host buffers",
+               "api": "rrtk_ctx_plan_worlds (seed mode, chunks of %d plans on 3 streams) via rrtplanner_b200._lib.Context, "
+                      "pinned host buffers" % (args.e2e_chunk or 512),
                "matches_device_arm": bool(same)}
         ctx.close()
 
@@ -328,7 +329,7 @@ def gpu_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     smem_b, blocks_per_sm = db.footprint()
     roofline = {
-        "kernel": "rrtk::plan_kernel<RRTK_STAR, grid in smem>", "bound": "smem", "achieved": achieved, "peak": smem_peak,
+        "kernel": "rrtk::plan_kernel<RRTK_STAR, K=%d samples per round>" % ((args.threads or 128) // 32), "bound": "smem", "achieved": achieved, "peak": smem_peak,
         "unit": "GB/s", "frac": achieved / smem_peak, "traffic": None,
         "peak_source": f"128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz SM clock sampled during the timed region (SURVEY.md 8(d)); "
                        "MEASURED_PEAKS.json has no shared-memory figure",
@@ -373,6 +374,7 @@ def main():
     ap.add_argument("--plans", type=int, default=4096, help="plans per GPU per step")
     ap.add_argument("--threads", type=int, default=0, help="threads per plan block (0 = library default)")
     ap.add_argument("--e2e-plans", type=int, default=4096)
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="plans per pipeline chunk of the end-to-end call (0 = library default)")
     ap.add_argument("--cpu-plans", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -200,6 +200,16 @@ int rrtk_ctx_plan(rrtk_ctx *ctx, int kind, const rrtk_plan_desc *h_plans, int np
                   const double *h_balls, int16_t *h_pts, double *h_cost, int32_t *h_parent,
                   int64_t *h_stats, double *h_ell_c);
 
+/* rrtk_ctx_set_grids + rrtk_ctx_plan in one call, pipelined: plans (ordered by world index) are
+ * processed in chunks of chunk_plans (0 = 512) on rotating streams, so the upload of one chunk's
+ * grids and the download of another's trees overlap the kernels; give pinned host buffers for the
+ * copies to be asynchronous.  The worlds are not kept in the context afterwards. */
+int rrtk_ctx_plan_worlds(rrtk_ctx *ctx, int kind, const uint8_t *h_og, int nworlds, int W, int H,
+                         const rrtk_plan_desc *h_plans, int nplans, int n, double r_rewire, double r_goal,
+                         const int16_t *h_samples, const uint64_t *h_state, const double *h_balls,
+                         int16_t *h_pts, double *h_cost, int32_t *h_parent, int64_t *h_stats, double *h_ell_c,
+                         int chunk_plans);
+
 /* the sample stream a planner seeded with h_state would draw (seed mode of rrtk_ctx_plan, exposed
  * so RRT.sample_all_free can be served from the same generator) */
 int rrtk_ctx_samples(rrtk_ctx *ctx, const rrtk_plan_desc *h_plans, int nplans, int n, const uint64_t *h_state,

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librrtk.so")
+LIB_PATH = os.environ.get("RRTK_LIB") or os.path.join(_HERE, "librrtk.so")   # RRTK_LIB: experiment builds
 
 KIND_STANDARD, KIND_STAR, KIND_INFORMED = 0, 1, 2
 STAT_NAMES = ("j", "vgoal", "found", "checks", "cells", "first_solution_iter", "ellipse_iters",
@@ -58,6 +58,7 @@ SIGNATURES = {
     "rrtk_destroy": (_i, [_vp]),
     "rrtk_ctx_set_grids": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rrtk_ctx_plan": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rrtk_ctx_plan_worlds": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rrtk_ctx_samples": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "rrtk_ctx_collision": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
     "rrtk_ctx_nearest": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
@@ -175,6 +176,29 @@ class Context:
         check(lib().rrtk_ctx_plan(self._h, kind, ptr(desc), nplans, n, float(r_rewire), float(r_goal), ptr(samples),
                                   ptr(states), ptr(balls), ptr(pts), ptr(cost), ptr(parent), ptr(stats), ptr(ell)),
               "rrtk_ctx_plan")
+        return pts, cost, parent, stats, ell
+
+    def plan_worlds(self, kind, og_u8, desc, n, r_rewire=0.0, r_goal=0.0, samples=None, states=None, balls=None, out=None,
+                    chunk=0):
+        """Upload + plan + download, pipelined over chunks of plans (plans ordered by world index)."""
+        og_u8 = np.ascontiguousarray(og_u8, dtype=np.uint8)
+        nw, W, H = og_u8.shape
+        nplans = desc.shape[0]
+        desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
+        if out is not None:
+            pts, cost, parent, stats, ell = out
+        else:
+            pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
+            cost = np.empty((nplans, n + 1), dtype=np.float64)
+            parent = np.empty((nplans, n + 1), dtype=np.int32)
+            stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
+            ell = np.empty((nplans, n + 1), dtype=np.float64) if kind == KIND_INFORMED else None
+        samples = None if samples is None else np.ascontiguousarray(samples, dtype=np.int16)
+        states = None if states is None else np.ascontiguousarray(states, dtype=np.uint64)
+        balls = None if balls is None else np.ascontiguousarray(balls, dtype=np.float64)
+        check(lib().rrtk_ctx_plan_worlds(self._h, kind, ptr(og_u8), nw, W, H, ptr(desc), nplans, n, float(r_rewire), float(r_goal),
+                                         ptr(samples), ptr(states), ptr(balls), ptr(pts), ptr(cost), ptr(parent), ptr(stats),
+                                         ptr(ell), int(chunk)), "rrtk_ctx_plan_worlds")
         return pts, cost, parent, stats, ell
 
     def samples(self, desc, n, states):

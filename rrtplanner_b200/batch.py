@@ -11,7 +11,7 @@ Two layers:
   enqueued through the device-pointer entry points of the C ABI.  Used by ``bench.py`` for the
   kernel-side throughput and by the multi-GPU driver.
 * ``plan_batch`` -- host arrays in, host arrays out, through the host-buffer C-ABI call
-  ``rrtk_ctx_plan`` (the end-to-end path).
+  ``rrtk_ctx_plan_worlds`` (the end-to-end path: chunked, copies overlapped with kernels).
 """
 from __future__ import annotations
 
@@ -39,9 +39,77 @@ def make_desc(world_ids, starts, goals, rots=None) -> np.ndarray:
     return d
 
 
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def _mul64_wide(a, b):
+    """(hi, lo) of the 128-bit product of two uint64 arrays."""
+    a0, a1, b0, b1 = a & _M32, a >> np.uint64(32), b & _M32, b >> np.uint64(32)
+    p00, p01, p10, p11 = a0 * b0, a0 * b1, a1 * b0, a1 * b1
+    mid = (p00 >> np.uint64(32)) + (p01 & _M32) + (p10 & _M32)
+    lo = (p00 & _M32) | (mid << np.uint64(32))
+    hi = p11 + (p01 >> np.uint64(32)) + (p10 >> np.uint64(32)) + (mid >> np.uint64(32))
+    return hi, lo
+
+
 def seed_states(seeds: Sequence[int]) -> np.ndarray:
-    """PCG64 start states of ``np.random.default_rng(seed)`` (rrt.py:85) for a list of seeds."""
-    return np.stack([_lib.pcg64_state_words(np.random.default_rng(int(s))) for s in seeds])
+    """PCG64 start states {state_hi, state_lo, inc_hi, inc_lo} of ``np.random.default_rng(seed)``
+    (rrt.py:85) for an array of non-negative integer seeds < 2**64, vectorised.
+
+    Restates numpy's published seeding path (numpy/random/bit_generator.pyx ``SeedSequence``:
+    hashmix / mix over a 4-word pool, ``generate_state(4, uint64)``; numpy/random/_pcg64.pyx +
+    pcg64.h ``pcg_setseq_128_srandom_r``).  tests/test_host_logic.py checks it against numpy."""
+    seeds = np.asarray(seeds)
+    if seeds.ndim != 1 or (seeds.size and (seeds.min() < 0)):
+        raise ValueError("seeds must be a 1-D array of non-negative integers")
+    seeds = seeds.astype(np.uint64)
+    u32 = np.uint32
+    sh = u32(16)
+    with np.errstate(over="ignore"):
+        ent = [(seeds & _M32).astype(u32), (seeds >> np.uint64(32)).astype(u32)]
+        hc = np.full(seeds.shape, 0x43B0D7E5, dtype=u32)
+
+        def hashmix(v):
+            nonlocal hc
+            v = v ^ hc
+            hc = hc * u32(0x931E8875)
+            v = v * hc
+            return v ^ (v >> sh)
+
+        def mix(x, y):
+            r = u32(0xCA01F9DD) * x - u32(0x4973F715) * y
+            return r ^ (r >> sh)
+
+        pool = [hashmix(ent[i] if i < 2 else np.zeros_like(ent[0])) for i in range(4)]
+        for src in range(4):
+            for dst in range(4):
+                if src != dst:
+                    pool[dst] = mix(pool[dst], hashmix(pool[src]))
+        hb = np.full(seeds.shape, 0x8B51F9DD, dtype=u32)
+        words = []
+        for i in range(8):
+            v = pool[i % 4] ^ hb
+            hb = hb * u32(0x58F38DED)
+            v = v * hb
+            words.append((v ^ (v >> sh)).astype(np.uint64))
+        w = [words[2 * i] | (words[2 * i + 1] << np.uint64(32)) for i in range(4)]
+        # pcg_setseq_128_srandom_r: state = 0; inc = (initseq << 1) | 1; step; state += initstate; step
+        init_hi, init_lo, seq_hi, seq_lo = w
+        inc_hi = (seq_hi << np.uint64(1)) | (seq_lo >> np.uint64(63))
+        inc_lo = (seq_lo << np.uint64(1)) | np.uint64(1)
+        mh, ml = np.uint64(0x2360ED051FC65DA4), np.uint64(0x4385DF649FCCF645)
+
+        def step(hi, lo):
+            phi, plo = _mul64_wide(lo, np.full_like(lo, ml))
+            phi = phi + hi * ml + lo * mh
+            nlo = plo + inc_lo
+            return phi + inc_hi + (nlo < plo).astype(np.uint64), nlo
+
+        hi, lo = step(np.zeros_like(init_hi), np.zeros_like(init_lo))
+        nlo = lo + init_lo
+        hi = hi + init_hi + (nlo < lo).astype(np.uint64)
+        hi, lo = step(hi, nlo)
+    return np.stack([hi, lo, inc_hi, inc_lo], axis=1)
 
 
 def shard(nplans: int, rank: int, world_size: int) -> range:
@@ -77,7 +145,7 @@ class BatchResult:
 
 def plan_batch(kind, ogs, n, starts, goals, world_ids=None, r_rewire=0.0, r_goal=0.0, samples=None, seeds=None,
                balls=None, rots=None, ctx: Optional[_lib.Context] = None) -> BatchResult:
-    """End-to-end batched plan() from host arrays through ``rrtk_ctx_plan``.
+    """End-to-end batched plan() from host arrays through ``rrtk_ctx_plan_worlds``.
 
     ogs: (nworlds, W, H) array, non-zero = obstacle.  Either ``samples`` (P, n, 2) -- the explicit
     sample streams -- or ``seeds`` (P,) -- plan p draws what a planner built with seed=seeds[p] would.
@@ -93,10 +161,20 @@ def plan_batch(kind, ogs, n, starts, goals, world_ids=None, r_rewire=0.0, r_goal
     own = ctx is None
     ctx = ctx or _lib.Context()
     try:
-        ctx.set_grids((ogs != 0).astype(np.uint8))
+        og_u8 = ogs if ogs.dtype == np.uint8 else (ogs != 0).astype(np.uint8)
         desc = make_desc(world_ids, starts, goals, rots)
         states = None if seeds is None else seed_states(seeds)
-        pts, cost, parent, stats, ell = ctx.plan(k, desc, n, r_rewire, r_goal, samples=samples, states=states, balls=balls)
+        order = np.argsort(desc["world"], kind="stable")          # the pipelined call wants plans grouped by world
+        if (np.diff(desc["world"]) >= 0).all():
+            pts, cost, parent, stats, ell = ctx.plan_worlds(k, og_u8, desc, n, r_rewire, r_goal, samples=samples,
+                                                            states=states, balls=balls)
+        else:
+            inv = np.empty_like(order)
+            inv[order] = np.arange(order.size)
+            take = lambda a: None if a is None else np.asarray(a)[order]          # noqa: E731
+            res = ctx.plan_worlds(k, og_u8, desc[order], n, r_rewire, r_goal, samples=take(samples), states=take(states),
+                                  balls=take(balls))
+            pts, cost, parent, stats, ell = (None if a is None else a[inv] for a in res)
     finally:
         if own:
             ctx.close()

@@ -30,31 +30,34 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = None, extra=()) -> str:
+    """``out`` / ``extra``: experiment builds (other output path, extra nvcc flags such as -D...)."""
+    if out is None and not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
+    tag = "" if out is None else "." + os.path.basename(out)
+    out = out or OUT
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(HERE, "build", src.replace(".cu", tag + ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:
-        out, _ = p.communicate()
-        log.append(f"== {src}\n{out}")
+        text, _ = p.communicate()
+        log.append(f"== {src}\n{text}")
         if p.returncode:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs])
-    with open(os.path.join(HERE, "build", "ptxas.log"), "w") as f:
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs])
+    with open(os.path.join(HERE, "build", "ptxas%s.log" % tag), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -104,6 +104,14 @@ struct DevBuf {
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// one stage of the chunked upload / plan / download pipeline of rrtk_ctx_plan_worlds
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    DevBuf og, bits, rowcum, plans, samples, state, balls, pts, cost, parent, stats, ell;
+    std::vector<rrtk_plan_desc> desc;
+};
+constexpr int kPipeSlots = 3;
+
 struct rrtk_ctx {
     cudaStream_t stream = nullptr;
     int W = 0, H = 0, nworlds = 0;
@@ -111,6 +119,7 @@ struct rrtk_ctx {
     DevBuf plans, samples, state, balls;        // plan inputs
     DevBuf pts, cost, parent, stats, ell;       // plan outputs
     DevBuf a, b, c, d, e;                       // query scratch
+    PipeSlot pipe[kPipeSlots];
 };
 
 extern "C" {
@@ -287,6 +296,11 @@ int rrtk_destroy(rrtk_ctx *c)
     DevBuf *all[] = {&c->og, &c->bits, &c->rowcum, &c->plans, &c->samples, &c->state, &c->balls, &c->pts,
                      &c->cost, &c->parent, &c->stats, &c->ell, &c->a, &c->b, &c->c, &c->d, &c->e};
     for (DevBuf *b : all) b->release();
+    for (PipeSlot &p : c->pipe) {
+        DevBuf *pb[] = {&p.og, &p.bits, &p.rowcum, &p.plans, &p.samples, &p.state, &p.balls, &p.pts, &p.cost, &p.parent, &p.stats, &p.ell};
+        for (DevBuf *b : pb) b->release();
+        if (p.stream) cudaStreamDestroy(p.stream);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RRTK_OK;
@@ -376,6 +390,105 @@ int rrtk_ctx_plan(rrtk_ctx *c, int kind, const rrtk_plan_desc *h_plans, int npla
     if (kind == RRTK_INFORMED) RRTK_CUDA(cudaMemcpyAsync(h_ell_c, c->ell.p, rows * 8, cudaMemcpyDeviceToHost, st));
     RRTK_CUDA(cudaStreamSynchronize(st));
     return RRTK_OK;
+}
+
+// Upload, plan and download in chunks of plans on rotating streams, so that host<->device copies of
+// one chunk overlap the kernels of its neighbours.  Plans must be ordered by world index.
+int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds, int W, int H, const rrtk_plan_desc *h_plans,
+                         int nplans, int n, double r_rewire, double r_goal, const int16_t *h_samples, const uint64_t *h_state,
+                         const double *h_balls, int16_t *h_pts, double *h_cost, int32_t *h_parent, int64_t *h_stats,
+                         double *h_ell_c, int chunk_plans)
+{
+    RRTK_REQUIRE(c && h_og && h_plans && h_pts && h_cost && h_parent && h_stats, "rrtk_ctx_plan_worlds: null pointer");
+    RRTK_REQUIRE((h_samples != nullptr) != (h_state != nullptr), "rrtk_ctx_plan_worlds: pass exactly one of h_samples / h_state");
+    RRTK_REQUIRE(kind != RRTK_INFORMED || h_ell_c, "rrtk_ctx_plan_worlds: informed plans need h_ell_c");
+    RRTK_REQUIRE(nworlds >= 1 && nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan_worlds: need nworlds >= 1, nplans >= 0, 1 <= n <= 65534");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    if (nplans == 0) return RRTK_OK;
+    if (chunk_plans <= 0) chunk_plans = 512;
+    for (int p = 0; p < nplans; ++p) {
+        const rrtk_plan_desc &d = h_plans[p];
+        if (d.world < 0 || d.world >= nworlds || d.start_x < 0 || d.start_x >= W || d.goal_x < 0 || d.goal_x >= W ||
+            d.start_y < 0 || d.start_y >= H || d.goal_y < 0 || d.goal_y >= H) {
+            set_error("plan %d: world index or start/goal outside the grid", p);
+            return RRTK_ERR_INVALID;
+        }
+        if (p && d.world < h_plans[p - 1].world) {
+            set_error("rrtk_ctx_plan_worlds: plans must be ordered by world index (plan %d)", p);
+            return RRTK_ERR_INVALID;
+        }
+    }
+    if (h_samples) {
+        const size_t total = (size_t)nplans * n;
+        for (size_t i = 0; i < total; ++i) {
+            const int x = h_samples[2 * i], y = h_samples[2 * i + 1];
+            if (x < 0 || x >= W || y < 0 || y >= H) {
+                set_error("sample %zu of plan %zu lies outside the grid", i % n, i / n);
+                return RRTK_ERR_INVALID;
+            }
+        }
+    }
+    DevInfo *di;
+    RRTK_TRY(dev_info(&di));
+    const size_t cells = (size_t)W * H, words = grid_words(W, H), rows1 = (size_t)n + 1;
+    int status = RRTK_OK;
+    for (int p0 = 0, ci = 0; p0 < nplans && status == RRTK_OK; p0 += chunk_plans, ++ci) {
+        const int m = (nplans - p0 < chunk_plans) ? nplans - p0 : chunk_plans;
+        PipeSlot &s = c->pipe[ci % kPipeSlots];
+        if (!s.stream) RRTK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        cudaStream_t st = s.stream;
+        const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
+        // buffers of this slot may still be in use by the chunk that last ran on it: stream order covers
+        // the device side; growing a buffer frees it, so drain the stream first in that (first-call) case
+        const bool grow = s.og.cap < cells * nw || s.pts.cap < rows1 * m * 4 || s.samples.cap < (size_t)m * n * 4;
+        if (grow) RRTK_CUDA(cudaStreamSynchronize(st));
+        RRTK_TRY(s.og.reserve(cells * nw));
+        RRTK_TRY(s.bits.reserve(words * 4 * nw));
+        RRTK_TRY(s.rowcum.reserve((size_t)(W + 1) * 4 * nw));
+        RRTK_TRY(s.plans.reserve(sizeof(rrtk_plan_desc) * m));
+        RRTK_TRY(s.samples.reserve((size_t)m * n * 4));
+        RRTK_TRY(s.pts.reserve(rows1 * m * 4));
+        RRTK_TRY(s.cost.reserve(rows1 * m * 8));
+        RRTK_TRY(s.parent.reserve(rows1 * m * 4));
+        RRTK_TRY(s.stats.reserve((size_t)m * RRTK_STAT_COUNT * 8));
+        RRTK_CUDA(cudaMemcpyAsync(s.og.p, h_og + cells * w0, cells * nw, cudaMemcpyHostToDevice, st));
+        RRTK_TRY(pack_launch(s.og.as<uint8_t>(), nw, W, H, s.bits.as<uint32_t>(), st));
+        RRTK_TRY(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st));
+        s.desc.assign(h_plans + p0, h_plans + p0 + m);
+        for (rrtk_plan_desc &d : s.desc) d.world -= w0;
+        RRTK_CUDA(cudaMemcpyAsync(s.plans.p, s.desc.data(), sizeof(rrtk_plan_desc) * m, cudaMemcpyHostToDevice, st));
+        if (h_samples) {
+            RRTK_CUDA(cudaMemcpyAsync(s.samples.p, h_samples + (size_t)p0 * n * 2, (size_t)m * n * 4, cudaMemcpyHostToDevice, st));
+        } else {
+            RRTK_TRY(s.state.reserve((size_t)m * 32));
+            RRTK_CUDA(cudaMemcpyAsync(s.state.p, h_state + (size_t)p0 * 4, (size_t)m * 32, cudaMemcpyHostToDevice, st));
+            RRTK_TRY(sample_streams_launch(s.bits.as<uint32_t>(), s.rowcum.as<int32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m,
+                                           s.state.as<uint64_t>(), n, s.samples.as<int16_t>(), di->optin, st));
+        }
+        if (kind == RRTK_INFORMED) {
+            RRTK_TRY(s.ell.reserve(rows1 * m * 8));
+            if (h_balls) {
+                RRTK_TRY(s.balls.reserve((size_t)m * n * 16));
+                RRTK_CUDA(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st));
+            }
+        }
+        RRTK_TRY(rrtk_plan_batch(kind, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, r_rewire, r_goal,
+                                 s.samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? s.balls.as<double>() : nullptr,
+                                 s.pts.as<int16_t>(), s.cost.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(),
+                                 s.ell.as<double>(), 0, st));
+        RRTK_CUDA(cudaMemcpyAsync(h_pts + (size_t)p0 * rows1 * 2, s.pts.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st));
+        RRTK_CUDA(cudaMemcpyAsync(h_cost + (size_t)p0 * rows1, s.cost.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st));
+        RRTK_CUDA(cudaMemcpyAsync(h_parent + (size_t)p0 * rows1, s.parent.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st));
+        RRTK_CUDA(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st));
+        if (kind == RRTK_INFORMED)
+            RRTK_CUDA(cudaMemcpyAsync(h_ell_c + (size_t)p0 * rows1, s.ell.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (PipeSlot &s : c->pipe)
+        if (s.stream) {
+            cudaError_t e = cudaStreamSynchronize(s.stream);
+            if (e != cudaSuccess && status == RRTK_OK) status = cuda_fail(e, "cudaStreamSynchronize");
+        }
+    return status;
 }
 
 int rrtk_ctx_samples(rrtk_ctx *c, const rrtk_plan_desc *h_plans, int nplans, int n, const uint64_t *h_state, int16_t *h_samples)

@@ -245,7 +245,7 @@ def test_plan_golden(ctx, golden_plan):
     assert (pts[0][top:] == -32768).all() and np.isinf(cost[0][top:]).all() and (parent[0][top:] == -1).all()
 
 
-@pytest.mark.parametrize("threads", [32, 64, 128, 256, 512])
+@pytest.mark.parametrize("threads", [64, 128, 256])
 def test_plan_result_independent_of_block_size(golden_plan, threads):
     g = golden_plan
     if g["n"] > 400:
@@ -366,6 +366,39 @@ def test_batch_properties_full_size():
     for k, p in enumerate(sub):
         assert np.array_equal(c.pts[k], a.pts[p]) and np.array_equal(c.cost[k].view(np.int64), a.cost[p].view(np.int64))
         assert np.array_equal(c.parent[k], a.parent[p]) and np.array_equal(c.stats[k][keep], a.stats[p][keep])
+
+
+def test_pipelined_host_call_equals_device_batch():
+    """rrtk_ctx_plan_worlds (chunked upload/plan/download on rotating streams) == one-shot DeviceBatch,
+    including plans given in arbitrary world order and several plans per world."""
+    W, H, n, nworlds, nplans = 160, 128, 600, 9, 41
+    ogs = np.stack([worlds.perlin_occupancygrid(W, H, seed=30 + w) for w in range(nworlds)]).astype(np.uint8)
+    rng = np.random.default_rng(2)
+    wid = rng.integers(0, nworlds, nplans)
+    pairs = [worlds.start_goal(ogs[wid[p]], p) for p in range(nplans)]
+    starts, goals = [a for a, _ in pairs], [b for _, b in pairs]
+    seeds = np.arange(100, 100 + nplans)
+    db = batch.DeviceBatch("star", W, H, n, 30.0).set_worlds_host(ogs)
+    db.set_plans(batch.make_desc(wid, starts, goals))
+    db.seed_samples(seeds)
+    want = db.run().download()
+    keep = [i for i, nm in enumerate(_lib.STAT_NAMES) if nm not in ("checks", "cells")]
+    for chunk in (0, 7, 64):
+        c = _lib.Context()
+        got = batch.plan_batch("star", ogs, n, starts, goals, wid, 30.0, seeds=seeds, ctx=c) if chunk == 0 else None
+        if got is None:
+            order = np.argsort(wid, kind="stable")
+            res = c.plan_worlds(1, ogs, batch.make_desc(wid, starts, goals)[order], n, 30.0, states=batch.seed_states(seeds)[order], chunk=chunk)
+            inv = np.empty_like(order)
+            inv[order] = np.arange(nplans)
+            got = batch.BatchResult(*[a[inv] if a is not None else None for a in res])
+        c.close()
+        assert np.array_equal(got.pts, want.pts) and np.array_equal(got.parent, want.parent)
+        assert np.array_equal(got.cost.view(np.int64), want.cost.view(np.int64))
+        assert np.array_equal(got.stats[:, keep], want.stats[:, keep])
+    with pytest.raises(ValueError):      # unordered plans are rejected by the C entry point itself
+        c = _lib.Context()
+        c.plan_worlds(1, ogs, batch.make_desc([1, 0], starts[:2], goals[:2]), n, 30.0, states=batch.seed_states(seeds[:2]))
 
 
 # ---- edge cases ----------------------------------------------------------------------------------------
