@@ -13,6 +13,7 @@ import os
 
 sass_csv, so, cubin_name, func_pat = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+MAIN = sys.argv[6] if len(sys.argv) > 6 else "plan_scan.cuh"
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, stdout=subprocess.DEVNULL)
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin_name)], capture_output=True, text=True).stdout
@@ -47,7 +48,7 @@ for r in rows[2:]:
         continue
     key = line_of.get(off)
     # attribute inlined helpers to the plan.cu line that called them
-    if key and key[2] and key[0] != "plan.cu":
+    if key and key[2] and key[0] != MAIN:
         key = (key[2][0], key[2][1], None, "via " + key[0])
     agg.setdefault(key[:2] if key else None, [0, 0])
     agg[key[:2] if key else None][0] += n

@@ -1,0 +1,531 @@
+// K7 (default form): one thread block per plan, K samples per round, packed-key scan.
+//
+// Replaces the three plan() loops of the reference (rrt.py:418-437, 498-548, 690-748), go2goal
+// (rrt.py:284-332) and the primitives they call (near :131-155, within :157-181, collisionfree
+// :183-229, default costfn :70-78, informed sampler :579-633).  Results are identical to the
+// reference run on the same sample stream with its two unstable argsorts pinned to "lowest index
+// first" (SURVEY.md section 8(c)); tests/test_gpu_parity.py checks that bit for bit.
+//
+// The reference's loop is sequential (iteration i sees the tree iteration i-1 left).  A round takes
+// the next K samples and keeps that semantics exactly:
+//
+//   scan     all threads, brute force over the whole tree (north star: no spatial index).  The tree
+//            lives in shared memory as packed vertices x | y << 16, laid out so that thread t owns
+//            the vertices v = row * T + t ("column t"): one LDS.128 = rows 4s .. 4s+3 of the
+//            column, conflict free, and the filled part of the tree is always spread evenly over
+//            the threads.  For vertex v and sample q the scan needs d2 = |v - q|^2 only up to a
+//            per-sample constant, so it evaluates
+//                key = S * (|v|^2 - 2 v.q) + row - S * (r^2 - |q|^2)          S = 2^sbits > row
+//            with two IMADs (S |v|^2 + row is per vertex, shared by the K samples; -2 S q per
+//            sample), then  key < 0  <=>  d2 < r^2  (one funnel shift appends the sign bit to the
+//            thread's membership word) and  min key  <=>  (min d2, lowest row)  (half a 3-input
+//            minimum per pair).  Everything is exact integer arithmetic: |key| < 2^31 is checked
+//            on the host (grids up to 4096 / 2896 / 2048 cells a side for 1 / 2 / 4 membership
+//            words); larger grids use the 32-bit-distance kernel of plan_wide.cu.
+//   barrier
+//   owner    warp (k mod warps) owns sample k and evaluates it against the round-start tree:
+//            combine the per-warp minima, duplicate test, walk nearest -> sample
+//            (rrt.py:424/506/706), FP64 cost via the nearest vertex, compaction of the membership
+//            words into a dense list, choose-parent (rrt.py:510-521) best first: the cheapest
+//            candidate that beats the incumbent is walked, the first free one wins.
+//   barrier
+//   commit   warp 0 replays the K results in sample order against the vertices accepted earlier in
+//            the same round (one per lane): equal cell -> duplicate; inside the radius -> extra
+//            candidate (cost, walk); strictly nearer than the recorded nearest vertex, or a change
+//            of the informed sampler's state -> the round is cut there and the remaining samples
+//            are redone next round (rare).  Accepted vertices are appended in order, and the next
+//            round's samples (free-space stream or informed ellipse) are staged.
+//   barrier
+//
+// so every decision is the one the sequential loop would take.  The reference's "rewire" block
+// (rrt.py:532-546, 732-742) tests vcosts[vn] + d < vcosts[vn] and can never fire with the default
+// cost function (oracle/rrt_oracle.py counts it: always 0), so it has no device counterpart.
+#pragma once
+#include <type_traits>
+
+#include "plan_common.cuh"
+
+namespace rrtk {
+
+constexpr int kKeyDead = 0x20000400;        // key of a masked-out slot: above every real key and every threshold
+constexpr int kKeyNever = -0x20000400;      // threshold of an inactive sample: below every real key
+
+// position of vertex v in the on-chip tree: quad (step, column) holds rows 4*step .. 4*step+3
+template <int T>
+__device__ __forceinline__ int tree_slot(int v)
+{
+    const int row = v / T, col = v - row * T;
+    return ((((row >> 2) * T) + col) << 2) | (row & 3);
+}
+
+template <int KIND, int K, int T>
+struct ScanCfg {
+    // resident blocks per SM the register allocation aims for
+    static constexpr int kMinBlocks = (T <= 64) ? 12 : (T <= 128) ? 6 : (T <= 160) ? 5 : (T <= 256) ? 3 : 1;
+};
+
+template <int KIND, int K, int T>
+__global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_kernel(PlanParams P)
+{
+    constexpr int NW = T / 32;
+    static_assert(T % 32 == 0 && K <= 16 && K >= 1, "block shape");
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ int2 s_near[K][NW];                    // [sample][warp] (min key >> sbits, vertex)
+    __shared__ SampleRec s_rec[K];
+    __shared__ RoundSummary s_sum;
+    __shared__ short2 s_q[K];                         // samples of the round
+    __shared__ double s_qc[K];                        // informed: cbest each ellipse sample was drawn with
+    __shared__ unsigned long long s_goalc;
+    __shared__ int s_goalv;
+    __shared__ unsigned long long s_checks, s_cells;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int plan = blockIdx.x;
+    const int n = P.n;
+    const int sbits = P.sbits;
+    const int S = 1 << sbits;
+    const int cap = P.list_cap;
+    const int HW = P.hit_words;
+
+    const int npts = 4 * T * P.steps_max;
+    uint32_t *s_pts = smem;                                               // npts words
+    uint32_t *s_hits = smem + npts;                                       // [HW][K][T] thread-private membership words
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_hits + (KIND == RRTK_STANDARD ? 0 : HW * K * T));   // [K][cap]
+
+    const rrtk_plan_desc *dsc = P.plans + plan;
+    const uint32_t *gbits = P.bits + (size_t)dsc->world * P.words_per_grid;
+    const int sx = dsc->start_x, sy = dsc->start_y, gx = dsc->goal_x, gy = dsc->goal_y;
+    const uint32_t startp = pack_xy(sx, sy);
+
+    double *cost = P.cost + (size_t)plan * (n + 1);
+    int *parent = P.parent + (size_t)plan * (n + 1);
+    const short2 *samples = P.samples + (size_t)plan * n;
+    const double2 *balls = (KIND == RRTK_INFORMED && P.balls) ? P.balls + (size_t)plan * n : nullptr;
+    double *ell_c = (KIND == RRTK_INFORMED) ? P.ell_c + (size_t)plan * (n + 1) : nullptr;
+    const uint32_t r2x = P.r2_excl;
+
+    for (int i = tid; i < npts; i += T) s_pts[i] = startp;                // slot 0 = the root; the rest is never read unmasked
+    if (tid < K) s_q[tid] = samples[min(tid, n - 1)];
+    if (tid == 0) { s_checks = s_cells = 0ull; cost[0] = 0.0; parent[0] = -1; }
+    if (KIND == RRTK_INFORMED)
+        for (int i = tid; i <= n; i += T) ell_c[i] = CUDART_NAN;
+    __syncthreads();
+
+    GlobalGrid gg{gbits};
+    const int TY = P.TY;
+#define WALK(ax_, ay_, bx_, by_) warp_first_hit(gg, TY, ax_, ay_, bx_, by_, lane)
+
+    // block-uniform state, replicated in every thread (refreshed from s_sum after each round)
+    int j = 1, it0 = 0;
+    bool have_sol = false;              // INFORMED: running least_cost over vsoln (rrt.py:627-633)
+    int vsol = 0;
+    double csol = 0.0;
+    long long first_sol = -1;
+    // counters kept by warp 0 (commit phase) / per warp (walks)
+    long long ell_iters = 0, nn_pairs = 0, ring_members = 0, accepted = 0;
+    unsigned my_checks = 0, my_cells = 0;
+
+    while (it0 < n) {
+        if (KIND != RRTK_INFORMED && j == n) break;                       // tree full: every later sample is rejected
+        if (KIND == RRTK_INFORMED && have_sol && balls == nullptr) break; // probe run: stop at first solution
+        const bool ellipse_mode = (KIND == RRTK_INFORMED) && have_sol;
+        // samples of this round: fewer while the tree is tiny (a new vertex would often be the nearest one)
+        const int kact = min(min(K, n - it0), 1 + (j >> 3));
+
+        // ---- scan: nearest + radius-set bits for K samples over vertices 0 .. j-1 ---------------
+        const int rows = (j + T - 1) / T;
+        const int steps = (rows + 3) >> 2;
+        const int nwords = (steps + 7) >> 3;
+        {
+            int ax[K], ay[K], thr[K], best[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const short2 s = s_q[k];
+                const int qq = s.x * s.x + s.y * s.y;
+                const bool act = k < kact;
+                ax[k] = act ? -2 * S * s.x : 0;
+                ay[k] = act ? -2 * S * s.y : 0;
+                long long t = (long long)S * ((long long)r2x - qq);           // key < t  <=>  d2 < r2x
+                t = t > (long long)kKeyDead ? (long long)kKeyDead : t;
+                thr[k] = (act && KIND != RRTK_STANDARD) ? (int)t : kKeyNever;
+                if (KIND == RRTK_STANDARD && act) thr[k] = 0;                 // any constant: bits unused
+                best[k] = 0x7fffffff;
+#ifdef RRTK_UNIFORM_TRICK
+                // warp-uniform by construction; a warp reduction tells the compiler, which can then keep them in uniform registers
+                ax[k] = __reduce_min_sync(RRTK_FULL, ax[k]);
+                ay[k] = __reduce_min_sync(RRTK_FULL, ay[k]);
+                thr[k] = __reduce_min_sync(RRTK_FULL, thr[k]);
+#endif
+            }
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts) + tid;
+            for (int w = 0; w < nwords; ++w) {
+                uint32_t h[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) h[k] = 0;
+                const int s_end = min(steps, 8 * w + 8);
+                auto step = [&](int s, auto masked_c) {
+                    constexpr bool masked = decltype(masked_c)::value;
+                    const uint4 q = q4[s * T];
+                    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e += 2) {
+                        int vx[2], vy[2], nvs[2];
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            vx[u] = px(wv[e + u]); vy[u] = py(wv[e + u]);
+                            const int row = 4 * s + e + u;
+                            nvs[u] = (vx[u] * vx[u] + vy[u] * vy[u]) * S + row;
+                            if (masked && row * T + tid >= j) { vx[u] = 0; vy[u] = 0; nvs[u] = kKeyDead; }
+                        }
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const int d0 = vx[0] * ax[k] + (vy[0] * ay[k] + nvs[0]) - thr[k];
+                            const int d1 = vx[1] * ax[k] + (vy[1] * ay[k] + nvs[1]) - thr[k];
+                            if (KIND != RRTK_STANDARD) {
+                                h[k] = __funnelshift_l((uint32_t)d0, h[k], 1);
+                                h[k] = __funnelshift_l((uint32_t)d1, h[k], 1);
+                            }
+                            best[k] = min(best[k], min(d0, d1));
+                        }
+                    }
+                };
+                int s = 8 * w;
+                const int s_full = min(s_end, steps - 1);
+                for (; s < s_full; ++s) step(s, std::false_type{});
+                if (s < s_end) { step(s, std::true_type{}); ++s; }
+                if (KIND != RRTK_STANDARD) {
+                    const int fill = 32 - 4 * (s - 8 * w);                    // processed slot p  <->  bit 31 - p
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + tid] = fill < 32 ? h[k] << fill : 0u;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {   // warp minimum, lowest index among equals
+                const bool any = best[k] != 0x7fffffff;
+                const int key = best[k] + thr[k];
+                const int dp = any ? (key >> sbits) : 0x7fffffff;
+                const int v = (key & (S - 1)) * T + tid;
+                const int wd = __reduce_min_sync(RRTK_FULL, dp);
+                const unsigned wi = __reduce_min_sync(RRTK_FULL, (any && dp == wd) ? (unsigned)v : 0xffffffffu);
+                if (lane == 0) s_near[k][warp] = make_int2(wd, (int)wi);
+            }
+        }
+        __syncthreads();                                                   // ---- barrier: scan results visible
+
+        // ---- owner phase: warp (k mod NW) evaluates sample k against the round-start tree ---------
+        for (int k = warp; k < K; k += NW) {
+            if (k >= kact) {
+                if (lane == 0) s_rec[k].flags = 0;
+                continue;
+            }
+            const short2 smp = s_q[k];
+            const int x = smp.x, y = smp.y;
+            uint32_t bd;
+            int vnear;
+            {
+                const int2 e = lane < NW ? s_near[k][lane] : make_int2(0x7fffffff, 0x7fffffff);
+                const int md = __reduce_min_sync(RRTK_FULL, e.x);
+                vnear = (int)__reduce_min_sync(RRTK_FULL, e.x == md ? (unsigned)e.y : 0xffffffffu);
+                bd = (uint32_t)(md + x * x + y * y);
+            }
+            // `sampled` holds accepted samples only, not xstart (rrt.py:410,426): a sample on the root's cell is a
+            // duplicate only if some vertex >= 1 sits there too (the scan reports the lowest index)
+            bool dup = bd == 0 && vnear >= 1;
+            if (bd == 0 && vnear == 0) {
+                bool f = false;
+                for (int v = 1 + lane; v < j; v += 32) f |= s_pts[tree_slot<T>(v)] == startp;
+                dup = __any_sync(RRTK_FULL, f);
+            }
+            const uint32_t pnear = s_pts[tree_slot<T>(vnear)];
+            int flags = 1 | (dup ? 2 : 0);
+            double c0 = 0.0, wc = CUDART_INF;
+            int wv = 0x7fffffff, ring = 0;
+            // the reference walks nearest -> sample before looking at the duplicate test
+            // (rrt.py:424-425 / 506-507 / 706-707); the verdicts are independent, so skip the walk
+            if (!dup) {
+                const double cnear = cost[vnear];
+                const int hit = WALK(px(pnear), py(pnear), x, y);
+                my_checks += 1; my_cells += cells_tested(hit);
+                if (hit < 0) {
+                    flags |= 4;
+                    c0 = reach_cost(cnear, bd);
+                    if (KIND != RRTK_STANDARD) {
+                        // candidates held one per lane: while one beats the incumbent, walk the cheapest
+                        auto consider = [&](bool has, int v, uint32_t p, double cn) {
+                            bool live = has && cn < c0;
+                            for (;;) {
+                                const bool cand = live && (cn < wc || (cn == wc && v < wv));
+                                if (!__any_sync(RRTK_FULL, cand)) break;
+                                // positive doubles order like their bit patterns
+                                const uint32_t hi = cand ? (uint32_t)__double2hiint(cn) : 0xffffffffu;
+                                const uint32_t mhi = warp_min_u32(hi);
+                                const uint32_t lo = (cand && hi == mhi) ? (uint32_t)__double2loint(cn) : 0xffffffffu;
+                                const uint32_t mlo = warp_min_u32(lo);
+                                const uint32_t vv = (cand && hi == mhi && lo == mlo) ? (uint32_t)v : 0xffffffffu;
+                                const uint32_t mv = warp_min_u32(vv);
+                                const int src = __ffs(__ballot_sync(RRTK_FULL, vv == mv && mv != 0xffffffffu)) - 1;
+                                const uint32_t pp = __shfl_sync(RRTK_FULL, p, src);
+                                const int h = WALK(px(pp), py(pp), x, y);
+                                my_checks += 1; my_cells += cells_tested(h);
+                                if (h < 0) { wc = __hiloint2double((int)mhi, (int)mlo); wv = (int)mv; }
+                                else if (lane == src) live = false;
+                            }
+                        };
+                        // membership words of this sample: nwords rows of T thread-private words
+                        int mine = 0;
+                        for (int w = 0; w < nwords; ++w)
+                            for (int c = lane; c < T; c += 32) mine += __popc(s_hits[(w * K + k) * T + c]);
+                        const int total = __reduce_add_sync(RRTK_FULL, mine);
+                        ring = total;
+                        if (total <= cap) {
+                            // compaction: exclusive prefix of the per-lane counts, then every lane lists its members
+                            int incl = mine;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int t = __shfl_up_sync(RRTK_FULL, incl, o);
+                                if (lane >= o) incl += t;
+                            }
+                            uint16_t *list = s_list + k * cap;
+                            int pos = incl - mine;
+                            for (int w = 0; w < nwords; ++w)
+                                for (int c = lane; c < T; c += 32) {
+                                    uint32_t bits = s_hits[(w * K + k) * T + c];
+                                    const int vbase = 32 * w * T + c;
+                                    while (bits) {
+                                        const int p = __clz(bits);
+                                        bits &= ~(0x80000000u >> p);
+                                        list[pos++] = (uint16_t)(vbase + p * T);
+                                    }
+                                }
+                            __syncwarp();
+                            for (int base = 0; base < total; base += 32) {
+                                const bool has = base + lane < total;
+                                const int v = has ? (int)list[base + lane] : 0;
+                                const uint32_t p = s_pts[tree_slot<T>(v)];
+                                double cn = CUDART_INF;
+                                if (has) cn = reach_cost(cost[v], dist2(p, x, y));
+                                consider(has, v, p, cn);
+                            }
+                            __syncwarp();
+                        } else {
+                            // very large radius sets: test every vertex directly, 32 per step
+                            for (int base = 0; base < j; base += 32) {
+                                const int v = base + lane;
+                                const uint32_t p = s_pts[tree_slot<T>(v < j ? v : 0)];
+                                const uint32_t dd = dist2(p, x, y);
+                                const bool has = v < j && dd < r2x;
+                                double cn = CUDART_INF;
+                                if (has) cn = reach_cost(cost[v], dd);
+                                consider(has, v, p, cn);
+                            }
+                        }
+                    }
+                }
+            }
+            if (lane == 0) {
+                SampleRec r;
+                r.pnew = pack_xy(x, y); r.bd = bd; r.vnear = vnear; r.flags = flags; r.bv = wv; r.ring = ring;
+                r.c0 = c0; r.bc = wc; r.ell = ellipse_mode ? s_qc[k] : 0.0;
+                s_rec[k] = r;
+            }
+        }
+        __syncthreads();                                                   // ---- barrier: K results visible
+
+        // ---- commit phase: warp 0 replays the results in sample order; lane m holds the m-th vertex
+        //      accepted in this round ----------------------------------------------------------------
+        if (warp == 0) {
+            // the stream samples the next round can start with (it0 + consumed + k, consumed <= kact <= K)
+            short2 ahead = make_short2(0, 0);
+            if (lane < 2 * K) ahead = samples[min(it0 + lane, n - 1)];
+            uint32_t newp = 0;
+            double newc = 0.0;
+            int nnew = 0, consumed = 0, jc = j;
+            bool hs = have_sol, finished = false, cut = false;
+            int vs = vsol;
+            double cs = csol;
+            long long fs = first_sol;
+            for (int k = 0; k < kact; ++k) {
+                const SampleRec r = s_rec[k];
+                if (KIND != RRTK_INFORMED && jc == n) { finished = true; break; }
+                const int x = px(r.pnew), y = py(r.pnew);
+                bool reject = (r.flags & 2) || jc == n || !(r.flags & 4);
+                double bc = r.bc;
+                int bv = r.bv;
+                // vertices accepted earlier in this round are not in the scan this sample was compared with
+                const bool mine = lane < nnew;
+                const uint32_t du = mine ? dist2(newp, x, y) : 0xffffffffu;
+                if (__any_sync(RRTK_FULL, mine && du != 0 && du < r.bd)) { cut = true; break; }   // it would be the nearest vertex: redo
+                if (__any_sync(RRTK_FULL, mine && du == 0)) reject = true;             // now in `sampled` (rrt.py:426/508/708)
+                int ringm = r.ring;
+                if (KIND != RRTK_STANDARD && !reject) {
+                    const bool inr = mine && du < r2x;
+                    const unsigned inm = __ballot_sync(RRTK_FULL, inr);
+                    ringm += __popc(inm);
+                    if (inm) {
+                        double cn = CUDART_INF;
+                        if (inr) cn = reach_cost(newc, du);
+                        bool live = inr && cn < r.c0 && cn < bc;              // higher index: loses cost ties
+                        for (;;) {                                            // cheapest first; equal cost -> lower lane
+                            if (!__any_sync(RRTK_FULL, live)) break;
+                            const uint32_t hi = live ? (uint32_t)__double2hiint(cn) : 0xffffffffu;
+                            const uint32_t mhi = warp_min_u32(hi);
+                            const uint32_t lo = (live && hi == mhi) ? (uint32_t)__double2loint(cn) : 0xffffffffu;
+                            const uint32_t mlo = warp_min_u32(lo);
+                            const int src = __ffs(__ballot_sync(RRTK_FULL, live && hi == mhi && lo == mlo)) - 1;
+                            const uint32_t pp = __shfl_sync(RRTK_FULL, newp, src);
+                            const int h = WALK(px(pp), py(pp), x, y);
+                            my_checks += 1; my_cells += cells_tested(h);
+                            if (h < 0) { bc = __hiloint2double((int)mhi, (int)mlo); bv = j + src; break; }
+                            if (lane == src) live = false;
+                        }
+                    }
+                }
+                ++consumed;
+                nn_pairs += jc;
+                if (KIND == RRTK_INFORMED && ellipse_mode) {
+                    if (lane == 0) ell_c[jc] = r.ell;                          // rrt.py:701
+                    ++ell_iters;
+                }
+                if (reject) continue;
+                ring_members += ringm;
+                const int vbest = (bv != 0x7fffffff) ? bv : r.vnear;
+                const double cbest = (bv != 0x7fffffff) ? bc : r.c0;
+                if (lane == 0) { s_pts[tree_slot<T>(jc)] = r.pnew; cost[jc] = cbest; parent[jc] = vbest; }   // rrt.py:524-529
+                if (lane == nnew) { newp = r.pnew; newc = cbest; }
+                ++nnew;
+                ++accepted;
+                bool changed = false;
+                if (KIND == RRTK_INFORMED) {
+                    const uint32_t dg = dist2(r.pnew, gx, gy);
+                    if (__dsqrt_rn((double)dg) < P.r_goal) {                   // rrt.py:744-745
+                        changed = !hs || cbest < cs;
+                        if (!hs) fs = it0 + k;
+                        if (changed) { cs = cbest; vs = jc; }
+                        hs = true;
+                    }
+                }
+                ++jc;
+                if (changed) break;                                            // later samples of the round used the old sampler state
+            }
+            if (it0 + consumed >= n) finished = true;
+            // stage the next round's samples
+            const int itn = it0 + consumed;
+            __syncwarp();                                                      // lane 0's tree writes -> all lanes
+            if (KIND == RRTK_INFORMED && hs && balls != nullptr) {
+                if (lane < K && itn + lane < n) {
+                    const double c = reach_cost(cs, dist2(s_pts[tree_slot<T>(vs)], gx, gy));   // rrt.py:698-699
+                    int ex, ey;
+                    ellipse_sample(P.W, P.H, dsc->rot, sx, sy, gx, gy, c, balls[itn + lane], ex, ey);
+                    s_q[lane] = make_short2((short)ex, (short)ey);
+                    s_qc[lane] = c;
+                }
+            } else {
+                const int src = min(consumed + lane, 31);
+                const int ax_ = __shfl_sync(RRTK_FULL, (int)ahead.x, src), ay_ = __shfl_sync(RRTK_FULL, (int)ahead.y, src);
+                if (lane < K) s_q[lane] = make_short2((short)ax_, (short)ay_);
+            }
+            if (lane == 0) {
+                RoundSummary s;
+                s.j = jc; s.consumed = consumed; s.flags = (hs ? 1 : 0) | (finished ? 2 : 0);
+                s.vsol = vs; s.csol = cs; s.first_sol = fs;
+                s_sum = s;
+            }
+            (void)cut;
+        }
+        __syncthreads();                                                   // ---- barrier: tree updated
+        {
+            const RoundSummary s = s_sum;
+            j = s.j;
+            it0 += s.consumed;
+            have_sol = s.flags & 1;
+            vsol = s.vsol; csol = s.csol; first_sol = s.first_sol;
+            if (s.flags & 2) break;
+        }
+    }
+
+    // ---- goal connection: rrt.py:284-332, ascending (cost, index), filled vertices only ------
+    if (tid == 0) { s_goalc = 0x7ff0000000000000ull; s_goalv = 0x7fffffff; }
+    __syncthreads();
+    for (int base = warp * 32; base < j; base += NW * 32) {
+        const int v = base + lane;
+        const bool valid = v < j;
+        const uint32_t p = s_pts[tree_slot<T>(valid ? v : 0)];
+        double cg = CUDART_INF;
+        if (valid) cg = reach_cost(cost[v], dist2(p, gx, gy));
+        unsigned m = __ballot_sync(RRTK_FULL, valid && cg < __longlong_as_double(*(volatile unsigned long long *)&s_goalc));
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            const double cv = __shfl_sync(RRTK_FULL, cg, l);
+            const uint32_t pp = __shfl_sync(RRTK_FULL, p, l);
+            if (cv < __longlong_as_double(*(volatile unsigned long long *)&s_goalc)) {
+                const int h = WALK(px(pp), py(pp), gx, gy);
+                my_checks += 1; my_cells += cells_tested(h);
+                if (h < 0 && lane == 0) atomicMin(&s_goalc, (unsigned long long)__double_as_longlong(cv));
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned long long cstar_bits = s_goalc;
+    const bool reachable = cstar_bits != 0x7ff0000000000000ull;
+    if (reachable) {   // lowest index among vertices with exactly the minimum cost and a free walk
+        for (int base = warp * 32; base < j; base += NW * 32) {
+            const int v = base + lane;
+            const bool valid = v < j;
+            const uint32_t p = s_pts[tree_slot<T>(valid ? v : 0)];
+            double cg = CUDART_INF;
+            if (valid) cg = reach_cost(cost[v], dist2(p, gx, gy));
+            unsigned m = __ballot_sync(RRTK_FULL, valid && (unsigned long long)__double_as_longlong(cg) == cstar_bits);
+            while (m) {
+                const int l = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t pp = __shfl_sync(RRTK_FULL, p, l);
+                const int h = WALK(px(pp), py(pp), gx, gy);
+                my_checks += 1; my_cells += cells_tested(h);
+                if (h < 0 && lane == 0) atomicMin(&s_goalv, base + l);
+            }
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&s_checks, (unsigned long long)my_checks);
+        atomicAdd(&s_cells, (unsigned long long)my_cells);
+    }
+    __syncthreads();
+
+    // ---- outputs -------------------------------------------------------------------------------
+    const int vparent = s_goalv;
+    const bool found = reachable && vparent != 0x7fffffff;
+    const int top = found ? j + 1 : j;     // rows holding real vertices
+    short2 *opts = P.pts + (size_t)plan * (n + 1);
+    for (int v = tid; v <= n; v += T) {
+        short2 o = make_short2(-32768, -32768);
+        if (v < j) {
+            const uint32_t p = s_pts[tree_slot<T>(v)];
+            o = make_short2((short)px(p), (short)py(p));
+        } else if (v == j && found) {
+            o = make_short2((short)gx, (short)gy);
+        }
+        opts[v] = o;
+        if (v >= top) { cost[v] = CUDART_INF; parent[v] = -1; }
+    }
+    if (tid == 0) {      // warp 0 carries the commit-phase counters
+        if (found) { cost[j] = __longlong_as_double((long long)cstar_bits); parent[j] = vparent; }
+        long long *st = P.stats + (size_t)plan * RRTK_STAT_COUNT;
+        st[RRTK_STAT_J] = j;
+        st[RRTK_STAT_VGOAL] = found ? j : 0;
+        st[RRTK_STAT_FOUND] = found ? 1 : 0;
+        st[RRTK_STAT_CHECKS] = (long long)s_checks;
+        st[RRTK_STAT_CELLS] = (long long)s_cells;
+        st[RRTK_STAT_FIRST_SOL_ITER] = first_sol;
+        st[RRTK_STAT_ELL_ITERS] = ell_iters;
+        st[RRTK_STAT_NN_PAIRS] = nn_pairs;
+        st[RRTK_STAT_RING_MEMBERS] = ring_members;
+        st[RRTK_STAT_ACCEPTED] = accepted;
+        st[RRTK_STAT_RESERVED0] = 0;
+        st[RRTK_STAT_RESERVED1] = 0;
+    }
+#undef WALK
+}
+
+}  // namespace rrtk

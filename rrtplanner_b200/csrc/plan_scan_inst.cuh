@@ -1,0 +1,41 @@
+// One planner kind of the packed-key plan kernel per translation unit (compiled in parallel):
+// the including .cu defines RRTK_SCAN_KIND and RRTK_SCAN_FN.
+#include "plan_scan.cuh"
+
+namespace rrtk {
+
+template <int K, int T>
+static int scan_launch_kt(const PlanParams &P, int nplans, size_t smem, cudaStream_t st)
+{
+    auto kern = plan_scan_kernel<RRTK_SCAN_KIND, K, T>;
+    RRTK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nplans, T, smem, st>>>(P);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
+template <int K>
+static int scan_launch_k(const PlanParams &P, int nplans, int T, size_t smem, cudaStream_t st)
+{
+    switch (T) {
+        case 64: return scan_launch_kt<K, 64>(P, nplans, smem, st);
+        case 128: return scan_launch_kt<K, 128>(P, nplans, smem, st);
+        case 160: return scan_launch_kt<K, 160>(P, nplans, smem, st);
+        case 256: return scan_launch_kt<K, 256>(P, nplans, smem, st);
+        case 512: return scan_launch_kt<K, 512>(P, nplans, smem, st);
+    }
+    set_error("packed-key plan kernel: unsupported block size %d", T);
+    return RRTK_ERR_INVALID;
+}
+
+int RRTK_SCAN_FN(const PlanParams &P, int nplans, int T, int K, size_t smem, cudaStream_t st)
+{
+    switch (K) {
+        case 4: return scan_launch_k<4>(P, nplans, T, smem, st);
+        case 8: return scan_launch_k<8>(P, nplans, T, smem, st);
+    }
+    set_error("packed-key plan kernel: unsupported samples per round %d", K);
+    return RRTK_ERR_INVALID;
+}
+
+}  // namespace rrtk
