@@ -166,6 +166,76 @@ def reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# cfg2: collision-check microbenchmark (BASELINE.json configs[1]; the "collision checks/sec" half of the metric)
+# ------------------------------------------------------------------------------------------------
+CC_SIZE = 2048
+CC_NSEG = 1 << 20
+
+
+def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz: float, peaks: dict):
+    """1 Mi segments with iid uniform integer endpoints (default_rng(0)) on one 2048x2048 value-noise world
+    (seed 1000), bit-packed = 512 KB: larger than one SM's shared memory, L2-resident.  Timed with CUDA
+    events around `steps` launches of rrtk_collision_segments on torch's current stream."""
+    import torch
+
+    from rrtplanner_b200 import _lib, batch, worlds
+    dev = torch.device("cuda", local)
+    db = batch.DeviceBatch("standard", CC_SIZE, CC_SIZE, 8, device=local).gen_worlds([worlds.world_seed(0)])
+    L = db.L
+    segs_h = np.random.default_rng(0).integers(0, CC_SIZE, size=(CC_NSEG, 4)).astype(np.int32)
+    segs = torch.from_numpy(segs_h).to(dev)
+    free = torch.empty((CC_NSEG,), dtype=torch.uint8, device=dev)
+    cells = torch.empty((CC_NSEG,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def launch():
+        _lib.check(L.rrtk_collision_segments(db.bits.data_ptr(), CC_SIZE, CC_SIZE, segs.data_ptr(), None, CC_NSEG,
+                                             free.data_ptr(), cells.data_ptr(), stream.cuda_stream), "collision_segments")
+
+    for _ in range(max(3, warmup)):
+        launch()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(steps, 10)
+    e0.record(stream)
+    for _ in range(reps):
+        launch()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    ncells = int(cells.sum(dtype=torch.int64).item())
+    nfree = int(free.sum(dtype=torch.int64).item())
+    alg = 4.0 * ncells                                          # SURVEY.md 8(d): 4 B per cell the reference would test
+    achieved = alg / (ms / 1e3) / 1e9
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    l2_peak = 6300.0 * sm_mhz * 1e6 / 1e9                       # B300_MICROARCH.md: LTS cap ~6300 B/clk full chip
+    out = {
+        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
+        "segments_per_s": CC_NSEG / (ms / 1e3), "cells_per_s": ncells / (ms / 1e3), "ms_per_launch": ms,
+        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
+        "obstacle_fraction": float(db.og.float().mean().item()), "gpu_launches": reps,
+        "roofline": {"kernel": "rrtk::collision_global_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
+                     "frac": achieved / l2_peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                     "bytes_model": "4 B (one grid word) x cells the reference's walk tests (first hit inclusive)",
+                     "peak_source": "L2: ~6300 B/clk full chip (B300_MICROARCH.md LTS cap; no L2 figure in MEASURED_PEAKS.json) x %.0f MHz" % sm_mhz,
+                     "smem_view": {"peak": 128.0 * sms * sm_mhz * 1e6 / 1e9, "frac": achieved / (128.0 * sms * sm_mhz * 1e6 / 1e9)}},
+    }
+    if cpu:
+        from oracle import c_oracle                            # checker + CPU baseline only
+        m = 1 << 17
+        og_h = db.og[0].cpu().numpy()
+        c_oracle.collision_batch(og_h, segs_h[:1024])
+        t0 = time.perf_counter()
+        wf, wc = c_oracle.collision_batch(og_h, segs_h[:m])
+        dt = time.perf_counter() - t0
+        out["matches_oracle"] = bool(np.array_equal(free[:m].cpu().numpy().astype(bool), wf) and np.array_equal(cells[:m].cpu().numpy(), wc))
+        out["cpu_baseline"] = {"value": m / dt, "unit": "segments/s", "cores": 1, "kind": "port",
+                               "sample": "first %d segments through oracle/rrt_oracle.c:orc_collision_batch (compiled C walk of "
+                                         "rrt.py:183-229 on the uint8 grid), %.3f s" % (m, dt)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def gpu_arm(args):
@@ -329,7 +399,7 @@ def gpu_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     smem_b, blocks_per_sm = db.footprint()
     roofline = {
-        "kernel": "rrtk::plan_kernel<RRTK_STAR, K=%d samples per round>" % ((args.threads or 128) // 32), "bound": "smem", "achieved": achieved, "peak": smem_peak,
+        "kernel": "rrtk::plan_scan_kernel<RRTK_STAR, K=%s samples per round, T=%s threads>" % (os.environ.get("RRTK_PLAN_K", "8"), args.threads or "160 (default)"), "bound": "smem", "achieved": achieved, "peak": smem_peak,
         "unit": "GB/s", "frac": achieved / smem_peak, "traffic": None,
         "peak_source": f"128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz SM clock sampled during the timed region (SURVEY.md 8(d)); "
                        "MEASURED_PEAKS.json has no shared-memory figure",
@@ -360,6 +430,8 @@ def gpu_arm(args):
     }
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_plans)
+    if world == 1 and not args.no_collision:
+        line["collision_microbench"] = collision_microbench(local, args.steps, args.warmup, not args.no_cpu, sm_mhz, peaks)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -368,7 +440,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--plans", type=int, default=4096, help="plans per GPU per step")
@@ -378,6 +450,7 @@ def main():
     ap.add_argument("--cpu-plans", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-collision", action="store_true", help="skip the cfg2 collision microbenchmark")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
