@@ -451,10 +451,15 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-collision", action="store_true", help="skip the cfg2 collision microbenchmark")
+    ap.add_argument("--collision-only", action="store_true", help="run only the cfg2 collision microbenchmark (profiling aid)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.collision_only:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(collision_microbench(0, args.steps, args.warmup, not args.no_cpu, 1965.0, {})), flush=True)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)
