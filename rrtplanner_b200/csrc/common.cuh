@@ -62,36 +62,68 @@ __device__ __forceinline__ int small_div(int num, int den, int &rem)
 // warp tests cell 32*c + l of chunk c, and a ballot finds the first occupied one.  All 32 lanes
 // must call this with the same segment.  Returns k >= 0 = index of the first occupied cell, or
 // -(L + 1) when the walk is free -- i.e. |ret| or ret + 1 is the number of cells the reference reads.
+// The walk comes in two halves so that a caller can put independent work between the issue of the
+// first chunk's grid load and the first ballot (walk_begin ... walk_finish); warp_first_hit is the
+// two back to back.
+struct WalkState {
+    int ax, ay, sx, sy;
+    int major, den;
+    int k, q, r, dq, dr;
+    bool xmajor;
+    uint32_t word;        // grid word of this lane's cell in the first chunk (0 beyond the segment's end)
+    int bitpos;
+};
+
+template <class Grid>
+__device__ __forceinline__ WalkState walk_begin(const Grid &g, int TY, int ax, int ay, int bx, int by, int lane)
+{
+    WalkState s;
+    const int dx = bx - ax, dy = by - ay;
+    const int adx = abs(dx), ady = abs(dy);
+    s.ax = ax; s.ay = ay;
+    s.sx = dx > 0 ? 1 : -1; s.sy = dy > 0 ? 1 : -1;
+    s.xmajor = adx >= ady;
+    s.major = s.xmajor ? adx : ady;
+    const int minor = s.xmajor ? ady : adx;
+    s.den = 2 * s.major;
+    s.k = lane;
+    s.q = 0; s.r = 0;
+    if (s.major > 0) s.q = small_div(2 * lane * minor + s.major, s.den, s.r);   // num < 63 * 16384 + ... < 2^24
+    s.dq = 0; s.dr = 0;
+    if (s.major >= 32) s.dq = small_div(64 * minor, s.den, s.dr);             // per-chunk increment of (q, r)
+    const int cx = s.xmajor ? ax + s.sx * s.k : ax + s.sx * s.q;
+    const int cy = s.xmajor ? ay + s.sy * s.q : ay + s.sy * s.k;
+    s.word = 0;
+    s.bitpos = cy & 31;
+    if (s.k <= s.major) s.word = g.load(word_index(cx, cy, TY));
+    return s;
+}
+
+template <class Grid>
+__device__ __forceinline__ int walk_finish(const Grid &g, int TY, WalkState &s, int lane)
+{
+    unsigned m = __ballot_sync(RRTK_FULL, (s.word >> s.bitpos) & 1u);
+    if (m) return __ffs(m) - 1;
+    for (int base = 32; base <= s.major; base += 32) {
+        s.k += 32;
+        s.q += s.dq;
+        s.r += s.dr;
+        if (s.r >= s.den) { s.r -= s.den; ++s.q; }
+        const int cx = s.xmajor ? s.ax + s.sx * s.k : s.ax + s.sx * s.q;
+        const int cy = s.xmajor ? s.ay + s.sy * s.q : s.ay + s.sy * s.k;
+        bool hit = false;
+        if (s.k <= s.major) hit = (g.load(word_index(cx, cy, TY)) >> (cy & 31)) & 1u;
+        m = __ballot_sync(RRTK_FULL, hit);
+        if (m) return base + __ffs(m) - 1;
+    }
+    return -(s.major + 1);
+}
+
 template <class Grid>
 __device__ __forceinline__ int warp_first_hit(const Grid &g, int TY, int ax, int ay, int bx, int by, int lane)
 {
-    const int dx = bx - ax, dy = by - ay;
-    const int adx = abs(dx), ady = abs(dy);
-    const int sx = dx > 0 ? 1 : -1, sy = dy > 0 ? 1 : -1;
-    const bool xmajor = adx >= ady;
-    const int major = xmajor ? adx : ady;
-    const int minor = xmajor ? ady : adx;
-    const int den = 2 * major;
-
-    int k = lane;
-    int q = 0, r = 0;
-    if (major > 0) q = small_div(2 * lane * minor + major, den, r);   // num < 63 * 16384 + ... < 2^24
-    int dq = 0, dr = 0;
-    if (major >= 32) dq = small_div(64 * minor, den, dr);             // per-chunk increment of (q, r)
-
-    for (int base = 0; base <= major; base += 32) {
-        const int cx = xmajor ? ax + sx * k : ax + sx * q;
-        const int cy = xmajor ? ay + sy * q : ay + sy * k;
-        bool hit = false;
-        if (k <= major) hit = (g.load(word_index(cx, cy, TY)) >> (cy & 31)) & 1u;
-        const unsigned m = __ballot_sync(RRTK_FULL, hit);
-        if (m) return base + __ffs(m) - 1;
-        k += 32;
-        q += dq;
-        r += dr;
-        if (r >= den) { r -= den; ++q; }
-    }
-    return -(major + 1);
+    WalkState s = walk_begin(g, TY, ax, ay, bx, by, lane);
+    return walk_finish(g, TY, s, lane);
 }
 
 __device__ __forceinline__ int cells_tested(int first_hit_ret) { return first_hit_ret < 0 ? -first_hit_ret : first_hit_ret + 1; }

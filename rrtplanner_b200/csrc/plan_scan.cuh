@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     __shared__ SampleRec s_rec[K];
     __shared__ RoundSummary s_sum;
     __shared__ short2 s_q[K];                         // samples of the round
+    __shared__ int4 s_qk[K];                          // their scan constants (ax, ay, thr, 0), staged with the samples
     __shared__ double s_qc[K];                        // informed: cbest each ellipse sample was drawn with
     __shared__ unsigned long long s_goalc;
     __shared__ int s_goalv;
@@ -105,8 +106,21 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     double *ell_c = (KIND == RRTK_INFORMED) ? P.ell_c + (size_t)plan * (n + 1) : nullptr;
     const uint32_t r2x = P.r2_excl;
 
+    // scan constants of a sample (see the header): key = vx * ax + vy * ay + (S |v|^2 + row),  key < thr  <=>  d2 < r2x
+    auto scan_consts = [&](short2 q, bool act) {
+        const int qq = q.x * q.x + q.y * q.y;
+        long long t = (long long)S * ((long long)r2x - qq);
+        t = t > (long long)kKeyDead ? (long long)kKeyDead : t;
+        int thr = (act && KIND != RRTK_STANDARD) ? (int)t : kKeyNever;
+        if (KIND == RRTK_STANDARD && act) thr = 0;                            // any constant: bits unused
+        return make_int4(act ? -2 * S * q.x : 0, act ? -2 * S * q.y : 0, thr, 0);
+    };
     for (int i = tid; i < npts; i += T) s_pts[i] = startp;                // slot 0 = the root; the rest is never read unmasked
-    if (tid < K) s_q[tid] = samples[min(tid, n - 1)];
+    if (tid < K) {
+        const short2 q0 = samples[min(tid, n - 1)];
+        s_q[tid] = q0;
+        s_qk[tid] = scan_consts(q0, tid < min(min(K, n), 1));                 // first round: j = 1 -> one sample
+    }
     if (tid == 0) { s_checks = s_cells = 0ull; cost[0] = 0.0; parent[0] = -1; }
     if (KIND == RRTK_INFORMED)
         for (int i = tid; i <= n; i += T) ell_c[i] = CUDART_NAN;
@@ -126,7 +140,17 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     long long ell_iters = 0, nn_pairs = 0, ring_members = 0, accepted = 0;
     unsigned my_checks = 0, my_cells = 0;
 
+    // -DRRTK_PHASE_CLOCKS (experiment builds, scripts/phase_clocks.py): cycles per phase in spare stats slots
+#ifdef RRTK_PHASE_CLOCKS
+    long long clk_scan = 0, clk_owner = 0, clk_commit = 0, clk_ownwork = 0, rounds = 0;
+#define PHASE_T(var) const long long var = clock64()
+#define PHASE_ADD(acc, a, b) acc += (b) - (a)
+#else
+#define PHASE_T(var)
+#define PHASE_ADD(acc, a, b)
+#endif
     while (it0 < n) {
+        PHASE_T(t_0);
         if (KIND != RRTK_INFORMED && j == n) break;                       // tree full: every later sample is rejected
         if (KIND == RRTK_INFORMED && have_sol && balls == nullptr) break; // probe run: stop at first solution
         const bool ellipse_mode = (KIND == RRTK_INFORMED) && have_sol;
@@ -141,22 +165,9 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             int ax[K], ay[K], thr[K], best[K];
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const short2 s = s_q[k];
-                const int qq = s.x * s.x + s.y * s.y;
-                const bool act = k < kact;
-                ax[k] = act ? -2 * S * s.x : 0;
-                ay[k] = act ? -2 * S * s.y : 0;
-                long long t = (long long)S * ((long long)r2x - qq);           // key < t  <=>  d2 < r2x
-                t = t > (long long)kKeyDead ? (long long)kKeyDead : t;
-                thr[k] = (act && KIND != RRTK_STANDARD) ? (int)t : kKeyNever;
-                if (KIND == RRTK_STANDARD && act) thr[k] = 0;                 // any constant: bits unused
+                const int4 c = s_qk[k];                                       // staged by the commit warp for this round's kact
+                ax[k] = c.x; ay[k] = c.y; thr[k] = c.z;
                 best[k] = 0x7fffffff;
-#ifdef RRTK_UNIFORM_TRICK
-                // warp-uniform by construction; a warp reduction tells the compiler, which can then keep them in uniform registers
-                ax[k] = __reduce_min_sync(RRTK_FULL, ax[k]);
-                ay[k] = __reduce_min_sync(RRTK_FULL, ay[k]);
-                thr[k] = __reduce_min_sync(RRTK_FULL, thr[k]);
-#endif
             }
             const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts) + tid;
             for (int w = 0; w < nwords; ++w) {
@@ -212,6 +223,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             }
         }
         __syncthreads();                                                   // ---- barrier: scan results visible
+        PHASE_T(t_1);
 
         // ---- owner phase: warp (k mod NW) evaluates sample k against the round-start tree ---------
         for (int k = warp; k < K; k += NW) {
@@ -244,72 +256,117 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             // the reference walks nearest -> sample before looking at the duplicate test
             // (rrt.py:424-425 / 506-507 / 706-707); the verdicts are independent, so skip the walk
             if (!dup) {
+                // long-latency operands first: the nearest vertex's cost and the first chunk of the walk
+                // nearest -> sample are in flight while the radius set is compacted
                 const double cnear = cost[vnear];
-                const int hit = WALK(px(pnear), py(pnear), x, y);
+                WalkState wk = walk_begin(gg, TY, px(pnear), py(pnear), x, y, lane);
+                int total = 0;
+                uint16_t *list = s_list + k * cap;
+                if (KIND != RRTK_STANDARD) {
+                    // membership words of this sample: nwords rows of T thread-private words
+                    int mine = 0;
+                    for (int w = 0; w < nwords; ++w)
+                        for (int c = lane; c < T; c += 32) mine += __popc(s_hits[(w * K + k) * T + c]);
+                    total = __reduce_add_sync(RRTK_FULL, mine);
+                    if (total <= cap) {
+                        // compaction: exclusive prefix of the per-lane counts, then every lane lists its members
+                        int incl = mine;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int t = __shfl_up_sync(RRTK_FULL, incl, o);
+                            if (lane >= o) incl += t;
+                        }
+                        int pos = incl - mine;
+                        for (int w = 0; w < nwords; ++w)
+                            for (int c = lane; c < T; c += 32) {
+                                uint32_t bits = s_hits[(w * K + k) * T + c];
+                                const int vbase = 32 * w * T + c;
+                                while (bits) {
+                                    const int p = __clz(bits);
+                                    bits &= ~(0x80000000u >> p);
+                                    list[pos++] = (uint16_t)(vbase + p * T);
+                                }
+                            }
+                        __syncwarp();
+                    }
+                }
+                const int hit = walk_finish(gg, TY, wk, lane);
                 my_checks += 1; my_cells += cells_tested(hit);
                 if (hit < 0) {
                     flags |= 4;
                     c0 = reach_cost(cnear, bd);
                     if (KIND != RRTK_STANDARD) {
-                        // candidates held one per lane: while one beats the incumbent, walk the cheapest
-                        auto consider = [&](bool has, int v, uint32_t p, double cn) {
-                            bool live = has && cn < c0;
-                            for (;;) {
-                                const bool cand = live && (cn < wc || (cn == wc && v < wv));
-                                if (!__any_sync(RRTK_FULL, cand)) break;
-                                // positive doubles order like their bit patterns
-                                const uint32_t hi = cand ? (uint32_t)__double2hiint(cn) : 0xffffffffu;
-                                const uint32_t mhi = warp_min_u32(hi);
-                                const uint32_t lo = (cand && hi == mhi) ? (uint32_t)__double2loint(cn) : 0xffffffffu;
-                                const uint32_t mlo = warp_min_u32(lo);
-                                const uint32_t vv = (cand && hi == mhi && lo == mlo) ? (uint32_t)v : 0xffffffffu;
-                                const uint32_t mv = warp_min_u32(vv);
-                                const int src = __ffs(__ballot_sync(RRTK_FULL, vv == mv && mv != 0xffffffffu)) - 1;
-                                const uint32_t pp = __shfl_sync(RRTK_FULL, p, src);
-                                const int h = WALK(px(pp), py(pp), x, y);
-                                my_checks += 1; my_cells += cells_tested(h);
-                                if (h < 0) { wc = __hiloint2double((int)mhi, (int)mlo); wv = (int)mv; }
-                                else if (lane == src) live = false;
-                            }
-                        };
-                        // membership words of this sample: nwords rows of T thread-private words
-                        int mine = 0;
-                        for (int w = 0; w < nwords; ++w)
-                            for (int c = lane; c < T; c += 32) mine += __popc(s_hits[(w * K + k) * T + c]);
-                        const int total = __reduce_add_sync(RRTK_FULL, mine);
                         ring = total;
                         if (total <= cap) {
-                            // compaction: exclusive prefix of the per-lane counts, then every lane lists its members
-                            int incl = mine;
+                            // choose-parent (rrt.py:510-521), cheapest first: three candidates per lane have their costs
+                            // loaded and evaluated together; the cheapest live one of the warp is walked, and the first
+                            // free one is the minimum over (cost, index) of everything that beats the nearest vertex.
+                            // (the list is in lane order, not index order: every tie is resolved on the vertex index)
+                            for (int base = 0; base < total; base += 96) {
+                                int cv[3];
+                                uint32_t cp[3];
+                                unsigned long long ck[3];                     // cost bits; ~0 = not a candidate
+                                double ccv[3];
 #pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const int t = __shfl_up_sync(RRTK_FULL, incl, o);
-                                if (lane >= o) incl += t;
-                            }
-                            uint16_t *list = s_list + k * cap;
-                            int pos = incl - mine;
-                            for (int w = 0; w < nwords; ++w)
-                                for (int c = lane; c < T; c += 32) {
-                                    uint32_t bits = s_hits[(w * K + k) * T + c];
-                                    const int vbase = 32 * w * T + c;
-                                    while (bits) {
-                                        const int p = __clz(bits);
-                                        bits &= ~(0x80000000u >> p);
-                                        list[pos++] = (uint16_t)(vbase + p * T);
+                                for (int u = 0; u < 3; ++u) {
+                                    const int idx = base + 32 * u + lane;
+                                    const bool has = idx < total;
+                                    cv[u] = has ? (int)list[idx] : 0;
+                                    cp[u] = s_pts[tree_slot<T>(cv[u])];
+                                    ccv[u] = has ? cost[cv[u]] : CUDART_INF;
+                                }
+#pragma unroll
+                                for (int u = 0; u < 3; ++u) {
+                                    const double cn = reach_cost(ccv[u], dist2(cp[u], x, y));
+                                    const bool live = cn < c0 && (cn < wc || (cn == wc && cv[u] < wv));
+                                    ck[u] = live ? (unsigned long long)__double_as_longlong(cn) : ~0ull;   // positive doubles order like their bits
+                                }
+                                for (;;) {
+                                    // this lane's cheapest live candidate, lowest vertex index among equal costs
+                                    unsigned long long bk = ck[0];
+                                    int bu = 0, bvx = cv[0];
+                                    if (ck[1] < bk || (ck[1] == bk && cv[1] < bvx)) { bk = ck[1]; bu = 1; bvx = cv[1]; }
+                                    if (ck[2] < bk || (ck[2] == bk && cv[2] < bvx)) { bk = ck[2]; bu = 2; bvx = cv[2]; }
+                                    const uint32_t hi = (uint32_t)(bk >> 32);
+                                    const uint32_t mhi = warp_min_u32(hi);
+                                    if (mhi == 0xffffffffu) break;                    // nothing left that beats the incumbent
+                                    const uint32_t lo = (hi == mhi) ? (uint32_t)bk : 0xffffffffu;
+                                    const uint32_t mlo = warp_min_u32(lo);
+                                    const uint32_t vv = (hi == mhi && lo == mlo) ? (uint32_t)bvx : 0xffffffffu;
+                                    const uint32_t mv = warp_min_u32(vv);
+                                    const int src = __ffs(__ballot_sync(RRTK_FULL, vv == mv)) - 1;
+                                    const uint32_t bpx = bu == 0 ? cp[0] : bu == 1 ? cp[1] : cp[2];
+                                    const uint32_t pp = __shfl_sync(RRTK_FULL, bpx, src);
+                                    const int h = WALK(px(pp), py(pp), x, y);
+                                    my_checks += 1; my_cells += cells_tested(h);
+                                    if (h < 0) { wc = __hiloint2double((int)mhi, (int)mlo); wv = (int)mv; break; }
+                                    if (lane == src) {
+                                        if (bu == 0) ck[0] = ~0ull; else if (bu == 1) ck[1] = ~0ull; else ck[2] = ~0ull;
                                     }
                                 }
-                            __syncwarp();
-                            for (int base = 0; base < total; base += 32) {
-                                const bool has = base + lane < total;
-                                const int v = has ? (int)list[base + lane] : 0;
-                                const uint32_t p = s_pts[tree_slot<T>(v)];
-                                double cn = CUDART_INF;
-                                if (has) cn = reach_cost(cost[v], dist2(p, x, y));
-                                consider(has, v, p, cn);
                             }
-                            __syncwarp();
                         } else {
-                            // very large radius sets: test every vertex directly, 32 per step
+                            // very large radius sets: test every vertex directly, 32 per step; while one beats the
+                            // incumbent, walk the cheapest
+                            auto consider = [&](bool has, int v, uint32_t p, double cn) {
+                                bool live = has && cn < c0;
+                                for (;;) {
+                                    const bool cand = live && (cn < wc || (cn == wc && v < wv));
+                                    if (!__any_sync(RRTK_FULL, cand)) break;
+                                    const uint32_t hi = cand ? (uint32_t)__double2hiint(cn) : 0xffffffffu;
+                                    const uint32_t mhi = warp_min_u32(hi);
+                                    const uint32_t lo = (cand && hi == mhi) ? (uint32_t)__double2loint(cn) : 0xffffffffu;
+                                    const uint32_t mlo = warp_min_u32(lo);
+                                    const uint32_t vv = (cand && hi == mhi && lo == mlo) ? (uint32_t)v : 0xffffffffu;
+                                    const uint32_t mv = warp_min_u32(vv);
+                                    const int src = __ffs(__ballot_sync(RRTK_FULL, vv == mv && mv != 0xffffffffu)) - 1;
+                                    const uint32_t pp = __shfl_sync(RRTK_FULL, p, src);
+                                    const int h = WALK(px(pp), py(pp), x, y);
+                                    my_checks += 1; my_cells += cells_tested(h);
+                                    if (h < 0) { wc = __hiloint2double((int)mhi, (int)mlo); wv = (int)mv; }
+                                    else if (lane == src) live = false;
+                                }
+                            };
                             for (int base = 0; base < j; base += 32) {
                                 const int v = base + lane;
                                 const uint32_t p = s_pts[tree_slot<T>(v < j ? v : 0)];
@@ -330,7 +387,9 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 s_rec[k] = r;
             }
         }
+        PHASE_T(t_1b);
         __syncthreads();                                                   // ---- barrier: K results visible
+        PHASE_T(t_2);
 
         // ---- commit phase: warp 0 replays the results in sample order; lane m holds the m-th vertex
         //      accepted in this round ----------------------------------------------------------------
@@ -412,18 +471,28 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             // stage the next round's samples
             const int itn = it0 + consumed;
             __syncwarp();                                                      // lane 0's tree writes -> all lanes
+            const int kact_next = min(min(K, n - itn), 1 + (jc >> 3));       // the next round's kact (same formula as above)
             if (KIND == RRTK_INFORMED && hs && balls != nullptr) {
-                if (lane < K && itn + lane < n) {
-                    const double c = reach_cost(cs, dist2(s_pts[tree_slot<T>(vs)], gx, gy));   // rrt.py:698-699
-                    int ex, ey;
-                    ellipse_sample(P.W, P.H, dsc->rot, sx, sy, gx, gy, c, balls[itn + lane], ex, ey);
-                    s_q[lane] = make_short2((short)ex, (short)ey);
-                    s_qc[lane] = c;
+                if (lane < K) {
+                    short2 qn = make_short2(0, 0);
+                    if (itn + lane < n) {
+                        const double c = reach_cost(cs, dist2(s_pts[tree_slot<T>(vs)], gx, gy));   // rrt.py:698-699
+                        int ex, ey;
+                        ellipse_sample(P.W, P.H, dsc->rot, sx, sy, gx, gy, c, balls[itn + lane], ex, ey);
+                        qn = make_short2((short)ex, (short)ey);
+                        s_qc[lane] = c;
+                    }
+                    s_q[lane] = qn;
+                    s_qk[lane] = scan_consts(qn, lane < kact_next);
                 }
             } else {
                 const int src = min(consumed + lane, 31);
                 const int ax_ = __shfl_sync(RRTK_FULL, (int)ahead.x, src), ay_ = __shfl_sync(RRTK_FULL, (int)ahead.y, src);
-                if (lane < K) s_q[lane] = make_short2((short)ax_, (short)ay_);
+                if (lane < K) {
+                    const short2 qn = make_short2((short)ax_, (short)ay_);
+                    s_q[lane] = qn;
+                    s_qk[lane] = scan_consts(qn, lane < kact_next);
+                }
             }
             if (lane == 0) {
                 RoundSummary s;
@@ -434,6 +503,11 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             (void)cut;
         }
         __syncthreads();                                                   // ---- barrier: tree updated
+        PHASE_T(t_3);
+        PHASE_ADD(clk_scan, t_0, t_1); PHASE_ADD(clk_owner, t_1, t_2); PHASE_ADD(clk_commit, t_2, t_3); PHASE_ADD(clk_ownwork, t_1, t_1b);
+#ifdef RRTK_PHASE_CLOCKS
+        ++rounds;
+#endif
         {
             const RoundSummary s = s_sum;
             j = s.j;
@@ -524,6 +598,13 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         st[RRTK_STAT_ACCEPTED] = accepted;
         st[RRTK_STAT_RESERVED0] = 0;
         st[RRTK_STAT_RESERVED1] = 0;
+#ifdef RRTK_PHASE_CLOCKS
+        st[RRTK_STAT_RESERVED0] = clk_scan;
+        st[RRTK_STAT_RESERVED1] = clk_owner;
+        st[RRTK_STAT_ELL_ITERS] = clk_commit;
+        st[RRTK_STAT_FIRST_SOL_ITER] = clk_ownwork;
+        st[RRTK_STAT_RING_MEMBERS] = rounds;
+#endif
     }
 #undef WALK
 }
