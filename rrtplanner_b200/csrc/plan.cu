@@ -41,7 +41,7 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
     s.K = env_int("RRTK_PLAN_K", 8);
     if (s.K != 4 && s.K != 8) return false;
     int T = threads > 0 ? threads : env_int("RRTK_PLAN_T", 0);
-    if (T <= 0) T = n < 2048 ? 64 : n < 4096 ? 128 : n < 5120 ? 160 : n < 32768 ? 256 : 512;
+    if (T <= 0) T = n < 2048 ? 64 : n < 5120 ? 128 : n < 32768 ? 256 : 512;   // measured: scripts/sweep_tk.sh
     if (T != 64 && T != 128 && T != 160 && T != 256 && T != 512) return false;
     const int rows = (n + 1 + T - 1) / T;
     s.T = T;

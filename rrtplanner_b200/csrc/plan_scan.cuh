@@ -23,11 +23,14 @@
 //            on the host (grids up to 4096 / 2896 / 2048 cells a side for 1 / 2 / 4 membership
 //            words); larger grids use the 32-bit-distance kernel of plan_wide.cu.
 //   barrier
-//   owner    warp (k mod warps) owns sample k and evaluates it against the round-start tree:
-//            combine the per-warp minima, duplicate test, walk nearest -> sample
-//            (rrt.py:424/506/706), FP64 cost via the nearest vertex, compaction of the membership
-//            words into a dense list, choose-parent (rrt.py:510-521) best first: the cheapest
-//            candidate that beats the incumbent is walked, the first free one wins.
+//   owner    the warps take the samples one at a time, first come first served (a sample costs
+//            anything between a duplicate test and several walks), and evaluate each against the
+//            round-start tree: combine the per-warp minima, duplicate test, walk nearest -> sample
+//            (rrt.py:424/506/706; its first grid word and the nearest vertex's cost are requested
+//            before the radius set is compacted), FP64 cost via the nearest vertex, compaction of
+//            the membership words into a dense list, choose-parent (rrt.py:510-521) cheapest first:
+//            three members per lane are costed together, the cheapest one of the warp that beats
+//            the nearest vertex is walked, and the first free one wins (ties: lowest index).
 //   barrier
 //   commit   warp 0 replays the K results in sample order against the vertices accepted earlier in
 //            the same round (one per lane): equal cell -> duplicate; inside the radius -> extra
@@ -75,6 +78,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     __shared__ RoundSummary s_sum;
     __shared__ short2 s_q[K];                         // samples of the round
     __shared__ int4 s_qk[K];                          // their scan constants (ax, ay, thr, 0), staged with the samples
+    __shared__ int s_next;                            // owner phase: next sample nobody has taken yet
     __shared__ double s_qc[K];                        // informed: cbest each ellipse sample was drawn with
     __shared__ unsigned long long s_goalc;
     __shared__ int s_goalv;
@@ -120,6 +124,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         const short2 q0 = samples[min(tid, n - 1)];
         s_q[tid] = q0;
         s_qk[tid] = scan_consts(q0, tid < min(min(K, n), 1));                 // first round: j = 1 -> one sample
+        if (tid == 0) s_next = NW;
     }
     if (tid == 0) { s_checks = s_cells = 0ull; cost[0] = 0.0; parent[0] = -1; }
     if (KIND == RRTK_INFORMED)
@@ -226,9 +231,13 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         PHASE_T(t_1);
 
         // ---- owner phase: warp (k mod NW) evaluates sample k against the round-start tree ---------
-        for (int k = warp; k < K; k += NW) {
+        // a sample costs anything between a duplicate test and several walks: warps take the next free one as they finish
+        for (int k = warp; k < K;) {
             if (k >= kact) {
                 if (lane == 0) s_rec[k].flags = 0;
+                int nk = 0;
+                if (lane == 0) nk = atomicAdd(&s_next, 1);
+                k = __shfl_sync(RRTK_FULL, nk, 0);
                 continue;
             }
             const short2 smp = s_q[k];
@@ -386,6 +395,11 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 r.c0 = c0; r.bc = wc; r.ell = ellipse_mode ? s_qc[k] : 0.0;
                 s_rec[k] = r;
             }
+            {
+                int nk = 0;
+                if (lane == 0) nk = atomicAdd(&s_next, 1);
+                k = __shfl_sync(RRTK_FULL, nk, 0);
+            }
         }
         PHASE_T(t_1b);
         __syncthreads();                                                   // ---- barrier: K results visible
@@ -472,6 +486,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             const int itn = it0 + consumed;
             __syncwarp();                                                      // lane 0's tree writes -> all lanes
             const int kact_next = min(min(K, n - itn), 1 + (jc >> 3));       // the next round's kact (same formula as above)
+            if (lane == 0) s_next = NW;
             if (KIND == RRTK_INFORMED && hs && balls != nullptr) {
                 if (lane < K) {
                     short2 qn = make_short2(0, 0);
