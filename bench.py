@@ -399,7 +399,7 @@ def gpu_arm(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     smem_b, blocks_per_sm = db.footprint()
     roofline = {
-        "kernel": "rrtk::plan_scan_kernel<RRTK_STAR, K=%s samples per round, T=%s threads>" % (os.environ.get("RRTK_PLAN_K", "8"), args.threads or "160 (default)"), "bound": "smem", "achieved": achieved, "peak": smem_peak,
+        "kernel": "rrtk::plan_scan_kernel<RRTK_STAR, K=%s samples per round, T=%s threads>" % (os.environ.get("RRTK_PLAN_K", "8"), args.threads or "128 (default)"), "bound": "smem", "achieved": achieved, "peak": smem_peak,
         "unit": "GB/s", "frac": achieved / smem_peak, "traffic": None,
         "peak_source": f"128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz SM clock sampled during the timed region (SURVEY.md 8(d)); "
                        "MEASURED_PEAKS.json has no shared-memory figure",

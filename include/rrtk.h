@@ -90,6 +90,9 @@ size_t rrtk_grid_words(int W, int H);
  * consecutive (W,H) uint8 grids, d_bits receives nworlds * rrtk_grid_words(W,H) words. */
 int rrtk_pack_grid(const uint8_t *d_og, int nworlds, int W, int H, uint32_t *d_bits, void *stream);
 
+/* inverse of rrtk_pack_grid: d_og receives nworlds (W,H) uint8 grids of 0 / 1 */
+int rrtk_unpack_grid(const uint32_t *d_bits, int nworlds, int W, int H, uint8_t *d_og, void *stream);
+
 /* free-space index for RRT.sample_all_free (rrt.py:64,231-240): d_rowcum[w*(W+1) + x] = number of
  * free cells in rows < x of world w (so entry W is nfree, the size of the reference's `free`). */
 int rrtk_free_rows(const uint32_t *d_bits, int nworlds, int W, int H, int32_t *d_rowcum, void *stream);
@@ -99,6 +102,17 @@ int rrtk_free_rows(const uint32_t *d_bits, int nworlds, int W, int H, int32_t *d
  * nworlds * W * H int32 + 2 * nworlds int32. */
 int rrtk_gen_worlds(const int32_t *d_seeds, int nworlds, int W, int H, int thresh_permille,
                     int32_t *d_scratch, uint8_t *d_og, void *stream);
+
+/* Obstacle inflation of the replanning caller (anim.py:79-87, the frame loop that calls set_og + plan):
+ *   dilated = scipy.ndimage.binary_dilation(og, iterations)   -- 4-connected cross, outside = free
+ *   out     = og | (dilated & ~og & ~hole)                     -- hole = clamped square the agent stands in
+ * Output grid o (o < nout, nout >= nworlds) is made from source world o % nworlds, so many agents can share one
+ * dilation of one frame.  d_holes: per OUTPUT grid (px, py, size) int32: cells [px, px+size) x [py, py+size),
+ * clipped to the grid, keep no buffer (anim.py:82-86 uses size = 2 * iterations); NULL or size 0 = no hole.
+ * d_out holds nout grids, d_scratch 2 * nworlds grids (rrtk_grid_words(W,H) words each); neither may alias
+ * d_bits.  iterations >= 0 (0 = no buffer). */
+int rrtk_inflate_grid(const uint32_t *d_bits, int nworlds, int W, int H, int iterations, const int32_t *d_holes,
+                      int nout, uint32_t *d_out, uint32_t *d_scratch, void *stream);
 
 /* ---- K1: RRT.collisionfree (rrt.py:183-229), batched ------------------------------------------- */
 /* d_segs: nseg x (ax, ay, bx, by) int32, all points inside the grid.  d_world: optional per-segment
@@ -148,6 +162,14 @@ int rrtk_sample_streams(const uint32_t *d_bits, const int32_t *d_rowcum, int W, 
                         const rrtk_plan_desc *d_plans, int nplans, const uint64_t *d_state, int n,
                         int16_t *d_samples, void *stream);
 
+/* Same, for a planner object that is used again (the replanning caller, anim.py:92-93: one rand_gen per
+ * object, rrt.py:85, keeps running across plan() calls): d_state is updated in place to the generator
+ * state after the n draws, d_carry (2 x uint32 per plan: numpy's has_uint32, uinteger; zero for a fresh
+ * generator) likewise. */
+int rrtk_sample_streams_carry(const uint32_t *d_bits, const int32_t *d_rowcum, int W, int H,
+                              const rrtk_plan_desc *d_plans, int nplans, uint64_t *d_state, uint32_t *d_carry,
+                              int n, int16_t *d_samples, void *stream);
+
 /* ---- K7: the plan() loops (rrt.py:418-437, 498-548, 690-748) + go2goal (rrt.py:284-332) ---------- */
 /*
  * Runs nplans independent plans, one thread block each, tree and bit grid resident on chip.
@@ -191,6 +213,11 @@ int rrtk_destroy(rrtk_ctx *ctx);
  * state RRT.__init__ / RRT.set_og keep (rrt.py:64-65, 261-272).  h_nfree (optional) receives the
  * number of free cells per world. */
 int rrtk_ctx_set_grids(rrtk_ctx *ctx, const uint8_t *h_og, int nworlds, int W, int H, int32_t *h_nfree);
+
+/* host-buffer form of rrtk_inflate_grid for ONE (W,H) uint8 source grid: h_out receives nout inflated uint8
+ * grids (one per hole triple in h_holes, or a single one without holes when h_holes is NULL and nout = 1) */
+int rrtk_ctx_inflate(rrtk_ctx *ctx, const uint8_t *h_og, int W, int H, int iterations, const int32_t *h_holes, int nout,
+                     uint8_t *h_out);
 
 /* full plan() from host memory: H2D of descriptors (+ samples / balls / PCG64 states), K7, D2H of
  * the trees.  Exactly one of h_samples / h_state must be non-NULL (explicit stream vs. seed mode).

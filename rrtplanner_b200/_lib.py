@@ -39,6 +39,8 @@ SIGNATURES = {
     "rrtk_device_info": (_i, [_vp, _vp]),
     "rrtk_grid_words": (_sz, [_i, _i]),
     "rrtk_pack_grid": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rrtk_unpack_grid": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "rrtk_inflate_grid": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "rrtk_free_rows": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "rrtk_gen_worlds": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "rrtk_collision_segments": (_i, [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
@@ -51,12 +53,14 @@ SIGNATURES = {
     "rrtk_argsort_i64": (_i, [_vp, _i, _vp, _vp, _sz, _vp]),
     "rrtk_argsort_scratch_bytes": (_sz, [_i]),
     "rrtk_sample_streams": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "rrtk_sample_streams_carry": (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _vp, _vp]),
     "rrtk_plan_batch": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rrtk_plan_footprint": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
     "rrtk_extract_paths": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rrtk_create": (_i, [_vp]),
     "rrtk_destroy": (_i, [_vp]),
     "rrtk_ctx_set_grids": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "rrtk_ctx_inflate": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "rrtk_ctx_plan": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrtk_ctx_plan_worlds": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
     "rrtk_ctx_samples": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -207,6 +211,16 @@ class Context:
         states = np.ascontiguousarray(states, dtype=np.uint64)
         out = np.empty((nplans, n, 2), dtype=np.int16)
         check(lib().rrtk_ctx_samples(self._h, ptr(desc), nplans, n, ptr(states), ptr(out)), "rrtk_ctx_samples")
+        return out
+
+    def inflate(self, og_u8: np.ndarray, iterations: int, holes=None) -> np.ndarray:
+        """anim.py:79-87 for one (W,H) grid: (nout, W, H) uint8, one inflated grid per (px, py, size) row of ``holes``."""
+        og_u8 = np.ascontiguousarray(og_u8, dtype=np.uint8)
+        W, H = og_u8.shape
+        h = None if holes is None else np.ascontiguousarray(holes, dtype=np.int32).reshape(-1, 3)
+        nout = 1 if h is None else h.shape[0]
+        out = np.empty((nout, W, H), dtype=np.uint8)
+        check(lib().rrtk_ctx_inflate(self._h, ptr(og_u8), W, H, int(iterations), ptr(h), nout, ptr(out)), "rrtk_ctx_inflate")
         return out
 
     # -- queries -------------------------------------------------------------------------------

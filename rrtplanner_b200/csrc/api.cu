@@ -30,6 +30,8 @@ int free_rows_launch(const uint32_t *, int, int, int, int32_t *, cudaStream_t);
 int worlds_launch(const int32_t *, int, int, int, int, int32_t *, uint8_t *, cudaStream_t);
 int collision_launch(const uint32_t *, int, int, const int32_t *, const int32_t *, int64_t, uint8_t *, int32_t *, int, int,
                      cudaStream_t);
+int unpack_launch(const uint32_t *, int, int, int, uint8_t *, cudaStream_t);
+int inflate_launch(const uint32_t *, int, int, int, int, const int32_t *, int, uint32_t *, uint32_t *, cudaStream_t);
 int nearest_launch(const int32_t *, int, const int32_t *, const int32_t *, int, int32_t *, int64_t *, cudaStream_t);
 int nearest_launch_f64(const double *, int, const double *, const int32_t *, int, int32_t *, double *, cudaStream_t);
 int within_launch(const int32_t *, int, const int32_t *, const int32_t *, int, double, int, int32_t *, int32_t *, cudaStream_t);
@@ -39,7 +41,7 @@ int dist_launch_f64(const double *, int, double, double, double *, cudaStream_t)
 int argsort_launch(const int64_t *, int, int32_t *, void *, size_t, cudaStream_t);
 size_t argsort_scratch(int);
 int sample_streams_launch(const uint32_t *, const int32_t *, int, int, const rrtk_plan_desc *, int, const uint64_t *, int,
-                          int16_t *, int, cudaStream_t);
+                          int16_t *, int, cudaStream_t, uint64_t * = nullptr, uint32_t * = nullptr);
 int plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
                 const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int plan_footprint(int, int, int, int, int, int, int, int *, int *);
@@ -157,6 +159,24 @@ int rrtk_pack_grid(const uint8_t *d_og, int nworlds, int W, int H, uint32_t *d_b
     return pack_launch(d_og, nworlds, W, H, d_bits, (cudaStream_t)stream);
 }
 
+int rrtk_unpack_grid(const uint32_t *d_bits, int nworlds, int W, int H, uint8_t *d_og, void *stream)
+{
+    RRTK_REQUIRE(d_og && d_bits && nworlds >= 0, "rrtk_unpack_grid: null pointer or negative count");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    return unpack_launch(d_bits, nworlds, W, H, d_og, (cudaStream_t)stream);
+}
+
+int rrtk_inflate_grid(const uint32_t *d_bits, int nworlds, int W, int H, int iterations, const int32_t *d_holes,
+                      int nout, uint32_t *d_out, uint32_t *d_scratch, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_out && d_scratch && nworlds >= 0 && iterations >= 0, "rrtk_inflate_grid: null pointer or negative count");
+    RRTK_REQUIRE(nout >= nworlds, "rrtk_inflate_grid: nout must be at least nworlds");
+    RRTK_REQUIRE(d_out != d_bits && d_scratch != d_bits && d_out != d_scratch, "rrtk_inflate_grid: buffers must not alias");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    if (nworlds == 0) return RRTK_OK;
+    return inflate_launch(d_bits, nworlds, W, H, iterations, d_holes, nout, d_out, d_scratch, (cudaStream_t)stream);
+}
+
 int rrtk_free_rows(const uint32_t *d_bits, int nworlds, int W, int H, int32_t *d_rowcum, void *stream)
 {
     RRTK_REQUIRE(d_bits && d_rowcum && nworlds >= 0, "rrtk_free_rows: null pointer or negative count");
@@ -238,6 +258,18 @@ int rrtk_sample_streams(const uint32_t *d_bits, const int32_t *d_rowcum, int W, 
     DevInfo *d;
     RRTK_TRY(dev_info(&d));
     return sample_streams_launch(d_bits, d_rowcum, W, H, d_plans, nplans, d_state, n, d_samples, d->optin, (cudaStream_t)stream);
+}
+
+int rrtk_sample_streams_carry(const uint32_t *d_bits, const int32_t *d_rowcum, int W, int H, const rrtk_plan_desc *d_plans,
+                              int nplans, uint64_t *d_state, uint32_t *d_carry, int n, int16_t *d_samples, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_rowcum && d_plans && d_state && d_carry && d_samples && nplans >= 0 && n >= 0,
+                 "rrtk_sample_streams_carry: bad argument");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return sample_streams_launch(d_bits, d_rowcum, W, H, d_plans, nplans, d_state, n, d_samples, d->optin, (cudaStream_t)stream,
+                                 d_state, d_carry);
 }
 
 int rrtk_plan_batch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans, int nplans, int n,
@@ -322,6 +354,29 @@ int rrtk_ctx_set_grids(rrtk_ctx *c, const uint8_t *h_og, int nworlds, int W, int
                                     cudaMemcpyDeviceToHost, c->stream));
     RRTK_CUDA(cudaStreamSynchronize(c->stream));
     c->W = W; c->H = H; c->nworlds = nworlds;
+    return RRTK_OK;
+}
+
+int rrtk_ctx_inflate(rrtk_ctx *c, const uint8_t *h_og, int W, int H, int iterations, const int32_t *h_holes, int nout,
+                     uint8_t *h_out)
+{
+    RRTK_REQUIRE(c && h_og && h_out && nout >= 1 && iterations >= 0, "rrtk_ctx_inflate: bad argument");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    const size_t cells = (size_t)W * H, wb = grid_words(W, H) * 4;
+    // scratch buffers of the context: a = source uint8 / result uint8, b = source bits, c = result bits, d = passes, e = holes
+    RRTK_TRY(c->a.reserve(cells * nout));
+    RRTK_TRY(c->b.reserve(wb));
+    RRTK_TRY(c->c.reserve(wb * nout));
+    RRTK_TRY(c->d.reserve(wb * 2));
+    RRTK_TRY(c->e.reserve((size_t)nout * 12));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_og, cells, cudaMemcpyHostToDevice, c->stream));
+    if (h_holes) RRTK_CUDA(cudaMemcpyAsync(c->e.p, h_holes, (size_t)nout * 12, cudaMemcpyHostToDevice, c->stream));
+    RRTK_TRY(pack_launch(c->a.as<uint8_t>(), 1, W, H, c->b.as<uint32_t>(), c->stream));
+    RRTK_TRY(inflate_launch(c->b.as<uint32_t>(), 1, W, H, iterations, h_holes ? c->e.as<int32_t>() : nullptr, nout,
+                            c->c.as<uint32_t>(), c->d.as<uint32_t>(), c->stream));
+    RRTK_TRY(unpack_launch(c->c.as<uint32_t>(), nout, W, H, c->a.as<uint8_t>(), c->stream));
+    RRTK_CUDA(cudaMemcpyAsync(h_out, c->a.p, cells * nout, cudaMemcpyDeviceToHost, c->stream));
+    RRTK_CUDA(cudaStreamSynchronize(c->stream));
     return RRTK_OK;
 }
 

@@ -54,6 +54,30 @@ int pack_launch(const uint8_t *d_og, int nworlds, int W, int H, uint32_t *d_bits
     return RRTK_OK;
 }
 
+// inverse of K0: tiled bit grid -> (W,H) uint8 0/1 grid (for callers that want a device-made grid back)
+__global__ void unpack_kernel(const uint32_t *__restrict__ bits, int nworlds, int W, int H, uint8_t *__restrict__ og)
+{
+    const int TY = tiles_y(H);
+    const size_t cells = (size_t)W * H, total = cells * nworlds, words_per = grid_words(W, H);
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int world = (int)(t / cells);
+        const size_t c = t - (size_t)world * cells;
+        const int x = (int)(c / H), y = (int)(c - (size_t)x * H);
+        og[t] = (bits[(size_t)world * words_per + word_index(x, y, TY)] >> (y & 31)) & 1u;
+    }
+}
+
+int unpack_launch(const uint32_t *d_bits, int nworlds, int W, int H, uint8_t *d_og, cudaStream_t st)
+{
+    const size_t total = (size_t)W * H * nworlds;
+    if (total == 0) return RRTK_OK;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 64) blocks = 148 * 64;
+    unpack_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_bits, nworlds, W, H, d_og);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
 // ---- free-space index: rowcum[x] = number of free cells in rows < x ----------------------------
 // The reference's sampler indexes free = argwhere(og == 0) (rrt.py:64), which lists free cells
 // row-major (x, then y); rank -> cell is therefore "row by prefix count, then y by in-row rank".

@@ -84,7 +84,7 @@ __device__ __forceinline__ short2 rank_to_cell(const uint32_t *__restrict__ g, c
 // then the block maps ranks to cells in parallel
 __global__ void sample_stream_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ rowcum, int W, int H,
                                      const rrtk_plan_desc *__restrict__ plans, const unsigned long long *__restrict__ state, int n,
-                                     short2 *__restrict__ samples)
+                                     short2 *__restrict__ samples, unsigned long long *__restrict__ state_out, uint32_t *__restrict__ carry)
 {
     extern __shared__ uint32_t s_rank[];
     const int plan = blockIdx.x;
@@ -96,7 +96,13 @@ __global__ void sample_stream_kernel(const uint32_t *__restrict__ bits, const in
         g.hi = state[4 * plan]; g.lo = state[4 * plan + 1];
         g.inc_hi = state[4 * plan + 2]; g.inc_lo = state[4 * plan + 3];
         g.has32 = false; g.buf32 = 0;
+        if (carry) { g.has32 = carry[2 * plan] != 0; g.buf32 = carry[2 * plan + 1]; }   // numpy's has_uint32 / uinteger
         for (int i = 0; i < n; ++i) s_rank[i] = nfree ? g.bounded(nfree) : 0;
+        if (state_out) {       // the generator as the next plan() of the same planner object finds it (rrt.py:85: one rand_gen per object)
+            state_out[4 * plan] = g.hi; state_out[4 * plan + 1] = g.lo;
+            state_out[4 * plan + 2] = g.inc_hi; state_out[4 * plan + 3] = g.inc_lo;
+        }
+        if (carry) { carry[2 * plan] = g.has32 ? 1u : 0u; carry[2 * plan + 1] = g.buf32; }
     }
     __syncthreads();
     const uint32_t *g = bits + (size_t)world * grid_words(W, H);
@@ -106,7 +112,8 @@ __global__ void sample_stream_kernel(const uint32_t *__restrict__ bits, const in
 }
 
 int sample_streams_launch(const uint32_t *d_bits, const int32_t *d_rowcum, int W, int H, const rrtk_plan_desc *d_plans,
-                          int nplans, const uint64_t *d_state, int n, int16_t *d_samples, int optin, cudaStream_t st)
+                          int nplans, const uint64_t *d_state, int n, int16_t *d_samples, int optin, cudaStream_t st,
+                          uint64_t *d_state_out, uint32_t *d_carry)
 {
     if (nplans == 0 || n == 0) return RRTK_OK;
     const size_t smem = (size_t)n * 4;
@@ -117,7 +124,8 @@ int sample_streams_launch(const uint32_t *d_bits, const int32_t *d_rowcum, int W
     RRTK_CUDA(cudaFuncSetAttribute(sample_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     sample_stream_kernel<<<nplans, 128, smem, st>>>(d_bits, d_rowcum, W, H, d_plans,
                                                     reinterpret_cast<const unsigned long long *>(d_state), n,
-                                                    reinterpret_cast<short2 *>(d_samples));
+                                                    reinterpret_cast<short2 *>(d_samples),
+                                                    reinterpret_cast<unsigned long long *>(d_state_out), d_carry);
     RRTK_CUDA(cudaGetLastError());
     return RRTK_OK;
 }
