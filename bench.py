@@ -220,6 +220,39 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
                      "peak_source": "L2: ~6300 B/clk full chip (B300_MICROARCH.md LTS cap; no L2 figure in MEASURED_PEAKS.json) x %.0f MHz" % sm_mhz,
                      "smem_view": {"peak": 128.0 * sms * sm_mhz * 1e6 / 1e9, "frac": achieved / (128.0 * sms * sm_mhz * 1e6 / 1e9)}},
     }
+    # K1b: same outputs from the clearance field (built once per grid, outside the timed region like the packing)
+    cap = 128
+    clear = torch.empty((CC_SIZE, CC_SIZE), dtype=torch.uint8, device=dev)
+    scratch = torch.empty((2 * db.words,), dtype=torch.int32, device=dev)
+    eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb0.record(stream)
+    _lib.check(L.rrtk_clearance_field(db.bits.data_ptr(), 1, CC_SIZE, CC_SIZE, cap, clear.data_ptr(), scratch.data_ptr(), stream.cuda_stream), "clearance_field")
+    eb1.record(stream)
+    free2 = torch.empty_like(free)
+    cells2 = torch.empty_like(cells)
+
+    def launch_cf():
+        _lib.check(L.rrtk_collision_segments_cf(clear.data_ptr(), CC_SIZE, CC_SIZE, segs.data_ptr(), None, CC_NSEG, free2.data_ptr(),
+                                                cells2.data_ptr(), stream.cuda_stream), "collision_segments_cf")
+
+    for _ in range(max(3, warmup)):
+        launch_cf()
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(reps):
+        launch_cf()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms_cf = e0.elapsed_time(e1) / reps
+    out["clearance_field_kernel"] = {
+        "kernel": "rrtk::collision_cf_kernel (thread per segment on a uint8 clearance field, cap %d)" % cap,
+        "segments_per_s": CC_NSEG / (ms_cf / 1e3), "cells_per_s": ncells / (ms_cf / 1e3), "ms_per_launch": ms_cf,
+        "field_build_ms": eb0.elapsed_time(eb1), "field_bytes": CC_SIZE * CC_SIZE,
+        "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free2) and torch.equal(cells, cells2)),
+        "algorithmic_GBps": alg / (ms_cf / 1e3) / 1e9, "frac_of_l2_peak": alg / (ms_cf / 1e3) / 1e9 / l2_peak,
+        "note": "skips cells the field proves free, so its algorithmic rate (4 B x cells the reference would read) is not bounded by "
+                "the L2 roofline of the cell-by-cell walk; gpu_launches of this leg: %d" % reps,
+    }
     if cpu:
         from oracle import c_oracle                            # checker + CPU baseline only
         m = 1 << 17

@@ -123,6 +123,18 @@ int rrtk_collision_segments(const uint32_t *d_bits, int W, int H, const int32_t 
                             const int32_t *d_world, int64_t nseg, uint8_t *d_free, int32_t *d_cells,
                             void *stream);
 
+/* ---- K1b: the same function on a clearance field ------------------------------------------------- */
+/* d_clear[w*W*H + x*H + y] = min(cap, Chebyshev distance of cell (x, y) of world w to the nearest obstacle
+ * cell or to the outside of the grid); 0 on obstacles.  2 <= cap <= 255.  d_scratch: 2 * nworlds *
+ * rrtk_grid_words(W,H) words.  Built once per grid (cap - 1 dilation passes). */
+int rrtk_clearance_field(const uint32_t *d_bits, int nworlds, int W, int H, int cap, uint8_t *d_clear,
+                         uint32_t *d_scratch, void *stream);
+/* rrtk_collision_segments with identical outputs (verdict and cells the reference's loop reads), walking the
+ * clearance field: a cell with clearance d proves the next d - 1 cells of the walk free (rrt.py:183-229 moves
+ * at most one cell per axis per step), so long free stretches cost one read.  One thread per segment. */
+int rrtk_collision_segments_cf(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world,
+                               int64_t nseg, uint8_t *d_free, int32_t *d_cells, void *stream);
+
 /* ---- K2: RRT.near(points, x)[0] (rrt.py:131-155), batched, pinned tie rule (lowest index) ------- */
 /* d_pts: npts x (x, y) int32.  d_queries: nq x (x, y).  d_count (optional): query q only sees the
  * first d_count[q] points (the filled prefix of the tree); NULL = all npts.  d_idx[q] = nearest

@@ -1,0 +1,215 @@
+// K1b: RRT.collisionfree (rrt.py:183-229) on a clearance field -- same verdicts and the same
+// "cells the reference reads" as K1 (collision.cu), far fewer grid reads for long segments.
+//
+// clear[x*H + y] = min(cap, Chebyshev distance from cell (x, y) to the nearest obstacle cell or to the
+// outside of the grid); 0 on obstacles.  Consecutive cells of the reference's walk differ by one step
+// on the major axis and at most one on the minor axis, so cell k + i lies within Chebyshev distance i
+// of cell k: if clear(cell k) = d > 0 the cells k+1 .. k+d-1 are free and the walk may continue at
+// k + d.  It stops at the first visited cell with clear = 0, which is the first occupied cell of the
+// walk because every skipped cell was proven free -- the returned index (and with it the number of
+// cells the reference's loop would have read) is identical.
+//
+// The field is built from the tiled bit grid by cap-1 passes of 8-connected dilation (one thread per
+// 32-cell word, 9 word loads), each pass writing its distance into the cells it newly reaches.
+// The walk is one thread per segment: every step needs cell k in closed form,
+//     q(k) = floor((2 k minor + major) / (2 major)),
+// taken from an fp32 reciprocal estimate with an exact +-1 integer fix-up (num < 2^31 for grids up to
+// 32768 cells a side), then one byte load.  A warp finishes with its slowest lane, so lanes whose
+// segment is done take the next one from the warp's block of segments while the others keep stepping.
+#include "common.cuh"
+
+namespace rrtk {
+
+// ---- clearance field ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t word_or_ones(const uint32_t *g, int x, int ty, int W32, int TY)
+{
+    if (x < 0 || x >= W32 || ty < 0 || ty >= TY) return 0xffffffffu;          // outside the grid counts as obstacle
+    return g[(((x >> 5) * TY + ty) << 5) | (x & 31)];
+}
+
+__device__ __forceinline__ uint32_t ydilate(const uint32_t *g, int x, int ty, int W32, int TY)
+{
+    const uint32_t c = word_or_ones(g, x, ty, W32, TY);
+    return c | (c << 1) | (c >> 1) | (word_or_ones(g, x, ty - 1, W32, TY) >> 31) | (word_or_ones(g, x, ty + 1, W32, TY) << 31);
+}
+
+__global__ void clearance_init_kernel(const uint32_t *__restrict__ bits, int nworlds, int W, int H, int cap, uint8_t *__restrict__ clear)
+{
+    const int TY = tiles_y(H);
+    const size_t cells = (size_t)W * H, total = cells * nworlds, words_per = grid_words(W, H);
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int world = (int)(t / cells);
+        const size_t c = t - (size_t)world * cells;
+        const int x = (int)(c / H), y = (int)(c - (size_t)x * H);
+        const bool occ = (bits[(size_t)world * words_per + word_index(x, y, TY)] >> (y & 31)) & 1u;
+        clear[t] = occ ? 0 : (uint8_t)cap;
+    }
+}
+
+// one 8-connected dilation pass in -> out; cells reached by this pass get distance `it`
+__global__ void clearance_pass_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int nworlds, int W, int H, int it,
+                                      uint8_t *__restrict__ clear)
+{
+    const int TX = tiles_x(W), TY = tiles_y(H), W32 = TX * 32;
+    const size_t words_per = (size_t)TX * TY * 32;
+    const size_t total = words_per * nworlds;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int world = (int)(t / words_per);
+        const int local = (int)(t - (size_t)world * words_per);
+        const int xl = local & 31, tile = local >> 5;
+        const int ty = tile % TY, x = (tile / TY) * 32 + xl;
+        const uint32_t *g = in + (size_t)world * words_per;
+        const uint32_t prev = g[local];
+        const uint32_t next = ydilate(g, x, ty, W32, TY) | ydilate(g, x - 1, ty, W32, TY) | ydilate(g, x + 1, ty, W32, TY);
+        out[t] = next;
+        uint32_t fresh = next & ~prev;
+        if (x < W) {
+            uint8_t *row = clear + ((size_t)world * W + x) * H + ty * 32;
+            const int valid = min(32, H - ty * 32);
+            while (fresh) {
+                const int b = __ffs(fresh) - 1;
+                fresh &= fresh - 1;
+                if (b < valid) row[b] = (uint8_t)it;
+            }
+        }
+    }
+}
+
+int clearance_launch(const uint32_t *d_bits, int nworlds, int W, int H, int cap, uint8_t *d_clear, uint32_t *d_scratch, cudaStream_t st)
+{
+    const size_t words = grid_words(W, H) * nworlds, cells = (size_t)W * H * nworlds;
+    if (cells == 0) return RRTK_OK;
+    const int threads = 256;
+    size_t cb = (cells + threads - 1) / threads, wb = (words + threads - 1) / threads;
+    if (cb > 148 * 64) cb = 148 * 64;
+    if (wb > 148 * 64) wb = 148 * 64;
+    clearance_init_kernel<<<(unsigned)cb, threads, 0, st>>>(d_bits, nworlds, W, H, cap, d_clear);
+    const uint32_t *src = d_bits;
+    uint32_t *a = d_scratch, *b = d_scratch + words;
+    for (int it = 1; it < cap; ++it) {
+        clearance_pass_kernel<<<(unsigned)wb, threads, 0, st>>>(src, a, nworlds, W, H, it, d_clear);
+        src = a;
+        uint32_t *tmp = a; a = b; b = tmp;
+    }
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
+// ---- the walk ---------------------------------------------------------------------------------------
+// A segment as the walk wants it, 16 bytes, made lane-parallel when the warp stages its block:
+//   .x = ax | ay << 16      .y = major      .z = minor << 3 | flags (1: x is the major axis, 2: sx < 0, 4: sy < 0)
+//   .w = fp32 bits of ~1 / (2 major)
+__device__ __forceinline__ int4 cf_pack(int4 e)
+{
+    const int dx = e.z - e.x, dy = e.w - e.y;
+    const int adx = abs(dx), ady = abs(dy);
+    const bool xmajor = adx >= ady;
+    const int major = xmajor ? adx : ady, minor = xmajor ? ady : adx;
+    float inv = 0.f;
+    if (major > 0) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__int2float_rn(2 * major)));
+    const int flags = (xmajor ? 1 : 0) | (dx > 0 ? 0 : 2) | (dy > 0 ? 0 : 4);         // sx = +1 iff x0 < x1 (rrt.py:207-215)
+    return make_int4(e.x | (e.y << 16), major, (minor << 3) | flags, __float_as_int(inv));
+}
+
+struct CfSeg {
+    int base, step_k, step_q;      // cell k of the walk lives at clear[base + k * step_k + q(k) * step_q]
+    int major, minor, k, slot;
+    float inv;
+};
+
+__device__ __forceinline__ void cf_unpack(CfSeg &s, int4 p, int slot, int H)
+{
+    const int ax = p.x & 0xffff, ay = (p.x >> 16) & 0xffff;
+    const int sxH = (p.z & 2) ? -H : H, sy = (p.z & 4) ? -1 : 1;
+    s.base = ax * H + ay;
+    s.step_k = (p.z & 1) ? sxH : sy;
+    s.step_q = (p.z & 1) ? sy : sxH;
+    s.major = p.y;
+    s.minor = p.z >> 3;
+    s.inv = __int_as_float(p.w);
+    s.k = 0;
+    s.slot = slot;
+}
+
+constexpr int kCfPerWarp = 128;      // segments per warp: staged in shared memory, drawn by the lanes as they finish
+constexpr int kCfThreads = 256;
+
+__global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t *__restrict__ clear, size_t cells_per, int W, int H,
+                                                                  const int4 *__restrict__ segs, const int *__restrict__ world,
+                                                                  int64_t nseg, uint8_t *__restrict__ free_out, int *__restrict__ cells_out)
+{
+    __shared__ int4 s_seg[kCfThreads / 32][kCfPerWarp];      // a finished segment's slot holds its result in .x
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * kCfThreads + threadIdx.x) >> 5;
+    const int64_t first = warp * kCfPerWarp;
+    if (first >= nseg) return;
+    const int cnt = (int)min((int64_t)kCfPerWarp, nseg - first);
+    int4 *mine = s_seg[wib];
+    for (int i = lane; i < cnt; i += 32) mine[i] = cf_pack(__ldg(segs + first + i));   // coalesced: 512 bytes per step
+    __syncwarp();
+    int next = 32;                                   // next undistributed slot (warp-uniform)
+    CfSeg s;
+    bool active = lane < cnt;
+    const uint8_t *field = clear;
+    if (active) {
+        cf_unpack(s, mine[lane], lane, H);
+        if (world) field = clear + (size_t)__ldg(world + first + lane) * cells_per;
+    }
+    while (__any_sync(RRTK_FULL, active)) {
+        bool done = false;
+        if (active) {
+            // cell k of the walk: q(k) = floor((2 k minor + major) / (2 major))
+            int q = 0;
+            if (s.major > 0) {
+                const unsigned den = 2u * (unsigned)s.major;
+                const unsigned num = 2u * (unsigned)s.k * (unsigned)s.minor + (unsigned)s.major;      // < 2^31
+                q = __float2int_rz(__uint2float_rn(num) * s.inv);
+                int r = (int)(num - (unsigned)q * den);
+                if (r < 0) { --q; r += (int)den; }
+                if (r >= (int)den) ++q;
+            }
+            const int d = __ldg(field + (s.base + s.k * s.step_k + q * s.step_q));
+            int result = 0;
+            if (d == 0) { done = true; result = s.k; }                               // first occupied cell
+            else {
+                s.k += d;                                                            // cells k+1 .. k+d-1 are free
+                if (s.k > s.major) { done = true; result = -(s.major + 1); }
+            }
+            if (done) mine[s.slot].x = result;
+        }
+        // lanes that finished take the next slots of the block, in lane order
+        const unsigned fin = __ballot_sync(RRTK_FULL, active && done);
+        if (fin) {
+            if (active && done) {
+                const int slot = next + __popc(fin & ((1u << lane) - 1u));
+                active = slot < cnt;
+                if (active) {
+                    cf_unpack(s, mine[slot], slot, H);
+                    if (world) field = clear + (size_t)__ldg(world + first + slot) * cells_per;
+                }
+            }
+            next += __popc(fin);
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {                                            // coalesced results
+        const int r = mine[i].x;
+        free_out[first + i] = r < 0;
+        if (cells_out) cells_out[first + i] = cells_tested(r);
+    }
+}
+
+int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int64_t nseg,
+                        uint8_t *d_free, int32_t *d_cells, int sm_count, cudaStream_t st)
+{
+    if (nseg == 0) return RRTK_OK;
+    const int64_t warps = (nseg + kCfPerWarp - 1) / kCfPerWarp;
+    int64_t blocks = (warps * 32 + kCfThreads - 1) / kCfThreads;
+    (void)sm_count;
+    collision_cf_kernel<<<(unsigned)blocks, kCfThreads, 0, st>>>(d_clear, (size_t)W * H, W, H, reinterpret_cast<const int4 *>(d_segs), d_world,
+                                                               nseg, d_free, d_cells);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
+}  // namespace rrtk
