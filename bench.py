@@ -10,9 +10,11 @@ only per-plan statistics are gathered at the end of each step.
 
 The JSON line carries, besides the contract keys: `roofline` (plan kernel: algorithmic bytes /
 CUDA-event time against the shared-memory bandwidth of SURVEY.md section 8(d), plus an HBM view), `e2e`
-(same metric through the host-buffer C-ABI call rrtk_ctx_plan: H2D of grids/descriptors/seeds and
+(same metric through the host-buffer C-ABI call rrtk_ctx_plan_worlds: H2D of grids/descriptors/seeds and
 D2H of all trees inside the timed region), `cpu_baseline` (the oracle's Python/Numba port of the
-reference, one core, a bounded sample of the same plans) and `clocks`.
+reference, one core, a bounded sample of the same plans), `clocks`, and `collision_microbench`
+(BASELINE cfg2, the "collision checks/sec" half of the metric: both collision kernels with their own
+roofline object and the C oracle on one core; N=1 only).
 
 `--impl reference` times the reference's CPU algorithm (oracle/rrt_oracle.py: the numpy/Numba port
 with the reference's cost profile -- the Python reference itself cannot travel to the GPU box) on
