@@ -371,6 +371,8 @@ def gpu_arm(args):
 
     # ---- end-to-end through the host-buffer C ABI (what a Python caller of plan_batch gets) ----
     e2e = None
+    blocks_per_sm_e2e = db.footprint()[1]
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
     if not args.no_e2e:
         Pe = min(P, args.e2e_plans)
         og_pinned = torch.empty((Pe, W, H), dtype=torch.uint8, pin_memory=True)
@@ -407,7 +409,7 @@ def gpu_arm(args):
                "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8 + 4)),
                "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt / args.steps,
                "api": "rrtk_ctx_plan_worlds (seed mode, chunks of %d plans on 3 streams) via rrtplanner_b200._lib.Context, "
-                      "pinned host buffers" % (args.e2e_chunk or 512),
+                      "pinned host buffers" % (args.e2e_chunk or sms * blocks_per_sm_e2e),
                "matches_device_arm": bool(same)}
         ctx.close()
 

@@ -481,7 +481,16 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
     RRTK_REQUIRE(nworlds >= 1 && nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan_worlds: need nworlds >= 1, nplans >= 0, 1 <= n <= 65534");
     RRTK_TRY(check_grid_dims(W, H, 16384));
     if (nplans == 0) return RRTK_OK;
-    if (chunk_plans <= 0) chunk_plans = 512;
+    if (chunk_plans <= 0) {
+        // one chunk = one wave of plan blocks (what the device runs concurrently): smaller chunks leave SMs idle
+        // between kernels, larger ones delay the first download (measured: scripts/e2e_chunks.sh)
+        DevInfo *di;
+        RRTK_TRY(dev_info(&di));
+        int smem = 0, per_sm = 0;
+        chunk_plans = 512;
+        if (plan_footprint(kind, W, H, n, 0, di->optin, di->sm_smem, &smem, &per_sm) == RRTK_OK && per_sm > 0)
+            chunk_plans = di->sms * per_sm;
+    }
     for (int p = 0; p < nplans; ++p) {
         const rrtk_plan_desc &d = h_plans[p];
         if (d.world < 0 || d.world >= nworlds || d.start_x < 0 || d.start_x >= W || d.goal_x < 0 || d.goal_x >= W ||

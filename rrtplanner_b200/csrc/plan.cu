@@ -30,7 +30,10 @@ static int env_int(const char *name, int dflt)
 }
 
 // registers: the launch bounds of plan_scan_kernel (ScanCfg::kMinBlocks)
-static int scan_min_blocks(int T) { return T <= 64 ? 12 : T <= 128 ? 6 : T <= 160 ? 5 : T <= 256 ? 3 : 1; }
+#ifndef RRTK_MINB128
+#define RRTK_MINB128 7
+#endif
+static int scan_min_blocks(int T) { return T <= 64 ? 12 : T <= 128 ? RRTK_MINB128 : T <= 160 ? 5 : T <= 256 ? 3 : 1; }
 
 static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, int sm_smem, ScanShape *out)
 {
@@ -55,10 +58,10 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
     const int need = (n + 1 + 31) & ~31;
     s.list_cap = kind == RRTK_STANDARD ? 0 : (cap < need ? cap : need);
     s.smem = (size_t)4 * 4 * T * s.steps_max;
-    if (kind != RRTK_STANDARD) s.smem += (size_t)4 * s.hit_words * s.K * T + (size_t)2 * s.K * s.list_cap;
+    if (kind != RRTK_STANDARD) s.smem += (size_t)4 * s.hit_words * s.K * T + (size_t)2 * (T / 32) * s.list_cap;   // one list per warp
     s.smem = (s.smem + 15) & ~(size_t)15;
     if (s.smem > (size_t)optin - 2048) return false;
-    int by_smem = (int)((size_t)sm_smem / (s.smem + 1024 + 1024));       // + static + per-block reservation
+    int by_smem = (int)((size_t)sm_smem / (s.smem + 896 + 1024));        // + static + per-block reservation
     int by_threads = 2048 / T;
     int b = by_smem < by_threads ? by_smem : by_threads;
     const int by_regs = 65536 / (T * (65536 / (T * scan_min_blocks(T)) / 8 * 8));

@@ -61,10 +61,13 @@ __device__ __forceinline__ int tree_slot(int v)
     return ((((row >> 2) * T) + col) << 2) | (row & 3);
 }
 
+#ifndef RRTK_MINB128
+#define RRTK_MINB128 7
+#endif
 template <int KIND, int K, int T>
 struct ScanCfg {
     // resident blocks per SM the register allocation aims for
-    static constexpr int kMinBlocks = (T <= 64) ? 12 : (T <= 128) ? 6 : (T <= 160) ? 5 : (T <= 256) ? 3 : 1;
+    static constexpr int kMinBlocks = (T <= 64) ? 12 : (T <= 128) ? RRTK_MINB128 : (T <= 160) ? 5 : (T <= 256) ? 3 : 1;
 };
 
 template <int KIND, int K, int T>
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     const int npts = 4 * T * P.steps_max;
     uint32_t *s_pts = smem;                                               // npts words
     uint32_t *s_hits = smem + npts;                                       // [HW][K][T] thread-private membership words
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_hits + (KIND == RRTK_STANDARD ? 0 : HW * K * T));   // [K][cap]
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_hits + (KIND == RRTK_STANDARD ? 0 : HW * K * T));   // [NW][cap]: one list per owner warp
 
     const rrtk_plan_desc *dsc = P.plans + plan;
     const uint32_t *gbits = P.bits + (size_t)dsc->world * P.words_per_grid;
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 const double cnear = cost[vnear];
                 WalkState wk = walk_begin(gg, TY, px(pnear), py(pnear), x, y, lane);
                 int total = 0;
-                uint16_t *list = s_list + k * cap;
+                uint16_t *list = s_list + warp * cap;
                 if (KIND != RRTK_STANDARD) {
                     // membership words of this sample: nwords rows of T thread-private words
                     int mine = 0;
