@@ -39,6 +39,7 @@ W = H = 512
 N_ITER = 5000
 R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
+NCU_DRAM_BYTES_PER_PLAN = 104936448.0 / 1036          # profiles/r1_v6_plan_kernel_ncu.txt
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
 
 
@@ -217,7 +218,10 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
         "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
         "obstacle_fraction": float(db.og.float().mean().item()), "gpu_launches": reps,
         "roofline": {"kernel": "rrtk::collision_global_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
-                     "frac": achieved / l2_peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                     "frac": achieved / l2_peak, "traffic": 17309440.0,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r1_v6_cc_ncu.txt): "
+                                       "16 MB of segment records + the 512 KB grid, once",
+                     "algorithmic_bytes_per_launch": alg,
                      "bytes_model": "4 B (one grid word) x cells the reference's walk tests (first hit inclusive)",
                      "peak_source": "L2: ~6300 B/clk full chip (B300_MICROARCH.md LTS cap; no L2 figure in MEASURED_PEAKS.json) x %.0f MHz" % sm_mhz,
                      "smem_view": {"peak": 128.0 * sms * sm_mhz * 1e6 / 1e9, "frac": achieved / (128.0 * sms * sm_mhz * 1e6 / 1e9)}},
@@ -437,7 +441,9 @@ def gpu_arm(args):
     smem_b, blocks_per_sm = db.footprint()
     roofline = {
         "kernel": "rrtk::plan_scan_kernel<RRTK_STAR, K=%s samples per round, T=%s threads>" % (os.environ.get("RRTK_PLAN_K", "8"), args.threads or "128 (default)"), "bound": "smem", "achieved": achieved, "peak": smem_peak,
-        "unit": "GB/s", "frac": achieved / smem_peak, "traffic": None,
+        "unit": "GB/s", "frac": achieved / smem_peak, "traffic": NCU_DRAM_BYTES_PER_PLAN * P,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_v6_plan_kernel_ncu.txt: 104.94 MB for "
+                          "1036 plans), scaled to the plans of this launch; the tree, grid and sample stream of a plan cross HBM once",
         "peak_source": f"128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz SM clock sampled during the timed region (SURVEY.md 8(d)); "
                        "MEASURED_PEAKS.json has no shared-memory figure",
         "algorithmic_bytes_per_launch": alg_bytes,
