@@ -216,6 +216,76 @@ int rrtk_plan_footprint(int kind, int W, int H, int n, int threads, int *smem_by
 int rrtk_extract_paths(const int32_t *d_parent, const int64_t *d_stats, int nplans, int n, int cap,
                        int32_t *d_path, int32_t *d_len, void *stream);
 
+/* ---- K8: planners the reference advertises but does not ship ---------------------------------------- */
+/*
+ * README.md:12,18-19 of the reference lists a "Dubins Primitive Module", a "Dubins Vehicle RRT Planner" and a
+ * "Dubins Vehicle RRT(star) Planner"; none of them exists in its tree, and its RRT* rewire block (rrt.py:532-546)
+ * can never fire (it compares cost(vn -> xnew) with vcosts[vn]).  These entry points supply them.  There is no
+ * reference behaviour to match: the specification is oracle/rewire_oracle.c (parity UNPINNED), except that
+ * model EUCLID with rewire = 0 reproduces rrtk_plan_batch / the reference's RRTStandard and RRTStar trees exactly.
+ *
+ *   vertex       (x, y, h): cell and heading index h in [0, nheadings), angle h * 2 pi / nheadings
+ *   edge length  EUCLID: straight line (rrt.py:70-78);  DUBINS: shortest of LSL RSR LSR RSL RLR LRL at turning
+ *                radius rho (cells), first word on ties, in IEEE double with the specification's own atan2/sin/cos
+ *   edge test    EUCLID: rrt.py:183-229 walked parent -> child;  DUBINS: path points every ds cells, rounded to
+ *                the nearest cell, plus the end cell; leaving the grid blocks
+ *   loop         rrt.py:498-548 with nearest / within Euclidean on (x, y); rewire != 0 adds, for every member vn
+ *                of the radius set in ascending order with  cost[vnew] + len(vnew -> vn) < cost[vn]  and a free
+ *                edge: parent[vn] = vnew and the costs of vn's subtree recomputed from the edge lengths
+ */
+typedef enum { RRTK_MODEL_EUCLID = 0, RRTK_MODEL_DUBINS = 1 } rrtk_model;
+
+typedef struct {
+    int32_t model;           /* rrtk_model */
+    int32_t star;            /* 0: parent = nearest vertex (RRT)   1: choose parent within r_rewire (RRT*) */
+    int32_t rewire;          /* 0: none (what the reference computes)   1: rewire as specified above (needs star) */
+    int32_t nheadings;       /* DUBINS: 1 .. 255 heading values */
+    double r_rewire;
+    double rho;              /* DUBINS: turning radius in cells, > 0 */
+    double ds;               /* DUBINS: arc-length step of the collision samples in cells, > 0 */
+} rrtk_plan2_cfg;
+
+/* statistics slots rrtk_plan2_batch writes (RRTK_STAT_COUNT int64 per plan; J / VGOAL / FOUND / CHECKS as above) */
+enum {
+    RRTK_STAT2_ACCEPTED = 4,   /* accepted samples */
+    RRTK_STAT2_REWIRES,        /* rewire operations applied */
+    RRTK_STAT2_PROPAGATED,     /* descendant costs recomputed after rewires */
+    RRTK_STAT2_RING_MEMBERS,   /* sum over accepted iterations of |within(r_rewire)| */
+    RRTK_STAT2_LEN_EVALS,      /* edge lengths evaluated on the device (parallel form) */
+    RRTK_STAT2_OVERFLOW        /* 1: a radius set exceeded the kernel's 1024-entry list; the plan is INVALID */
+};
+
+/* bytes of device scratch rrtk_plan2_batch needs for nplans plans of n iterations */
+size_t rrtk_plan2_scratch_bytes(int nplans, int n);
+
+/*
+ * nplans independent plans, one thread block each.  Plan p starts at (start_x, start_y, heading reserved[0]) and
+ * ends at (goal_x, goal_y, heading reserved[1]) of its descriptor (headings ignored by EUCLID).
+ *   d_samples  nplans x n x (x, y) int16 as for rrtk_plan_batch;  d_heads  nplans x n uint8 heading of sample i
+ *              (DUBINS; may be NULL = heading 0)
+ *   outputs, (n + 1) rows per plan, row j = goal vertex when connected:
+ *   d_pts int16 (x, y) (-32768 unfilled), d_head uint8 (255 unfilled), d_cost / d_elen float64 cost-to-come and
+ *   length of the edge from the parent (+inf unfilled), d_parent int32 (-1 root / unfilled), d_stats int64.
+ * threads: 0 (default 256), 128 or 256.  n <= 65534.
+ */
+int rrtk_plan2_batch(const rrtk_plan2_cfg *cfg, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans,
+                     int nplans, int n, const int16_t *d_samples, const uint8_t *d_heads, int16_t *d_pts, uint8_t *d_head,
+                     double *d_cost, double *d_elen, int32_t *d_parent, int64_t *d_stats, void *d_scratch, int threads,
+                     void *stream);
+int rrtk_plan2_footprint(int n, int threads, int *smem_bytes, int *blocks_per_sm);
+
+/* Dubins primitive, batched.  d_q: nq x (x0, y0, h0, x1, y1, h1) int32.  Outputs (each optional): d_word 0..5 =
+ * LSL RSR LSR RSL RLR LRL, d_tpq nq x 3 segment lengths in units of rho, d_len path length in cells. */
+int rrtk_dubins_paths(const int32_t *d_q, int64_t nq, int nheadings, double rho, int32_t *d_word, double *d_tpq,
+                      double *d_len, void *stream);
+/* sampled collision test of the shortest path of each query (the edge test above); d_world optional per query */
+int rrtk_dubins_collision(const uint32_t *d_bits, int W, int H, const int32_t *d_q, const int32_t *d_world, int64_t nq,
+                          int nheadings, double rho, double ds, uint8_t *d_free, void *stream);
+/* poses (x, y, theta) of each query's shortest path every ds cells: d_xyth nq x cap x 3, d_count[q] = number of
+ * poses the path has (floor(len / ds) + 1; only the first cap are stored) */
+int rrtk_dubins_sample(const int32_t *d_q, int64_t nq, int nheadings, double rho, double ds, int cap, double *d_xyth,
+                       int32_t *d_count, void *stream);
+
 /* ---- host-buffer entry points (the call a Python planner object makes; copies inside) ------------ */
 typedef struct rrtk_ctx rrtk_ctx;    /* owns device scratch; one per planner object / thread */
 int rrtk_create(rrtk_ctx **out);
@@ -267,6 +337,18 @@ int rrtk_ctx_nearest_f64(rrtk_ctx *ctx, const double *h_pts, int npts, const dou
 int rrtk_ctx_within_f64(rrtk_ctx *ctx, const double *h_pts, int npts, const double *h_queries, int nq,
                         double r, int cap, int32_t *h_out, int32_t *h_len);
 int rrtk_ctx_near_order_f64(rrtk_ctx *ctx, const double *h_pts, int npts, double qx, double qy, int32_t *h_perm);
+
+/* host-buffer forms of K8 (rrtk_plan2_batch on the context's worlds; exactly one of h_samples / h_state as for
+ * rrtk_ctx_plan) and of the Dubins primitive */
+int rrtk_ctx_plan2(rrtk_ctx *ctx, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc *h_plans, int nplans, int n,
+                   const int16_t *h_samples, const uint64_t *h_state, const uint8_t *h_heads, int16_t *h_pts,
+                   uint8_t *h_head, double *h_cost, double *h_elen, int32_t *h_parent, int64_t *h_stats);
+int rrtk_ctx_dubins_paths(rrtk_ctx *ctx, const int32_t *h_q, int64_t nq, int nheadings, double rho, int32_t *h_word,
+                          double *h_tpq, double *h_len);
+int rrtk_ctx_dubins_collision(rrtk_ctx *ctx, int world, const int32_t *h_q, int64_t nq, int nheadings, double rho,
+                              double ds, uint8_t *h_free);
+int rrtk_ctx_dubins_sample(rrtk_ctx *ctx, const int32_t *h_q, int64_t nq, int nheadings, double rho, double ds, int cap,
+                           double *h_xyth, int32_t *h_count);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,23 @@ STAT_NAMES = ("j", "vgoal", "found", "checks", "cells", "first_solution_iter", "
               "nn_pairs", "ring_members", "accepted", "reserved0", "reserved1")
 STAT_COUNT = len(STAT_NAMES)
 
+MODEL_EUCLID, MODEL_DUBINS = 0, 1
+STAT2_NAMES = ("j", "vgoal", "found", "checks", "accepted", "rewires", "propagated", "ring_members", "len_evals", "overflow",
+               "reserved0", "reserved1")
+DUBINS_WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
+# numpy mirror of rrtk_plan2_cfg (40 bytes)
+PLAN2_CFG = np.dtype([("model", "<i4"), ("star", "<i4"), ("rewire", "<i4"), ("nheadings", "<i4"), ("r_rewire", "<f8"),
+                      ("rho", "<f8"), ("ds", "<f8")], align=True)
+assert PLAN2_CFG.itemsize == 40
+
+
+def plan2_cfg(model, star, rewire, r_rewire=0.0, nheadings=1, rho=1.0, ds=1.0) -> np.ndarray:
+    c = np.zeros(1, dtype=PLAN2_CFG)
+    c["model"], c["star"], c["rewire"], c["nheadings"] = int(model), int(bool(star)), int(bool(rewire)), int(nheadings)
+    c["r_rewire"], c["rho"], c["ds"] = float(r_rewire), float(rho), float(ds)
+    return c
+
+
 # numpy mirror of rrtk_plan_desc (64 bytes)
 PLAN_DESC = np.dtype([("world", "<i4"), ("start_x", "<i4"), ("start_y", "<i4"), ("goal_x", "<i4"),
                       ("goal_y", "<i4"), ("reserved", "<i4", (3,)), ("rot", "<f8", (4,))], align=True)
@@ -73,6 +90,16 @@ SIGNATURES = {
     "rrtk_ctx_within_f64": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp]),
     "rrtk_ctx_near_order": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rrtk_ctx_near_order_f64": (_i, [_vp, _vp, _i, _d, _d, _vp]),
+    "rrtk_plan2_scratch_bytes": (_sz, [_i, _i]),
+    "rrtk_plan2_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "rrtk_plan2_footprint": (_i, [_i, _i, _vp, _vp]),
+    "rrtk_dubins_paths": (_i, [_vp, _i64, _i, _d, _vp, _vp, _vp, _vp]),
+    "rrtk_dubins_collision": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _d, _d, _vp, _vp]),
+    "rrtk_dubins_sample": (_i, [_vp, _i64, _i, _d, _d, _i, _vp, _vp, _vp]),
+    "rrtk_ctx_plan2": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rrtk_ctx_dubins_paths": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _vp]),
+    "rrtk_ctx_dubins_collision": (_i, [_vp, _i, _vp, _i64, _i, _d, _d, _vp]),
+    "rrtk_ctx_dubins_sample": (_i, [_vp, _vp, _i64, _i, _d, _d, _i, _vp, _vp]),
 }
 
 _lib = None
@@ -224,6 +251,57 @@ class Context:
         out = np.empty((nout, W, H), dtype=np.uint8)
         check(lib().rrtk_ctx_inflate(self._h, ptr(og_u8), W, H, int(iterations), ptr(h), nout, ptr(out)), "rrtk_ctx_inflate")
         return out
+
+    # -- K8: rewire / Dubins planners, Dubins primitive ---------------------------------------
+    def plan2(self, cfg, desc, n, samples=None, states=None, heads=None):
+        """rrtk_ctx_plan2: returns (pts, head, cost, elen, parent, stats); desc["reserved"][:, :2] = start / goal heading."""
+        nplans = desc.shape[0]
+        desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
+        cfg = np.ascontiguousarray(cfg, dtype=PLAN2_CFG)
+        pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
+        head = np.empty((nplans, n + 1), dtype=np.uint8)
+        cost = np.empty((nplans, n + 1), dtype=np.float64)
+        elen = np.empty((nplans, n + 1), dtype=np.float64)
+        parent = np.empty((nplans, n + 1), dtype=np.int32)
+        stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, dtype=np.int16)
+            assert samples.shape == (nplans, n, 2), samples.shape
+        if states is not None:
+            states = np.ascontiguousarray(states, dtype=np.uint64)
+            assert states.shape == (nplans, 4)
+        if heads is not None:
+            heads = np.ascontiguousarray(heads, dtype=np.uint8)
+            assert heads.shape == (nplans, n), heads.shape
+        check(lib().rrtk_ctx_plan2(self._h, ptr(cfg), ptr(desc), nplans, n, ptr(samples), ptr(states), ptr(heads), ptr(pts), ptr(head),
+                                   ptr(cost), ptr(elen), ptr(parent), ptr(stats)), "rrtk_ctx_plan2")
+        return pts, head, cost, elen, parent, stats
+
+    def dubins_paths(self, q, nheadings, rho):
+        """q: (nq, 6) (x0, y0, h0, x1, y1, h1) -> (word, tpq, length)."""
+        q = np.ascontiguousarray(q, dtype=np.int32).reshape(-1, 6)
+        word = np.empty(q.shape[0], dtype=np.int32)
+        tpq = np.empty((q.shape[0], 3), dtype=np.float64)
+        ln = np.empty(q.shape[0], dtype=np.float64)
+        check(lib().rrtk_ctx_dubins_paths(self._h, ptr(q), q.shape[0], int(nheadings), float(rho), ptr(word), ptr(tpq), ptr(ln)),
+              "rrtk_ctx_dubins_paths")
+        return word, tpq, ln
+
+    def dubins_collision(self, q, nheadings, rho, ds, world=0):
+        q = np.ascontiguousarray(q, dtype=np.int32).reshape(-1, 6)
+        free = np.empty(q.shape[0], dtype=np.uint8)
+        check(lib().rrtk_ctx_dubins_collision(self._h, int(world), ptr(q), q.shape[0], int(nheadings), float(rho), float(ds), ptr(free)),
+              "rrtk_ctx_dubins_collision")
+        return free.astype(bool)
+
+    def dubins_sample(self, q, nheadings, rho, ds, cap):
+        """Poses every ds cells: (xyth (nq, cap, 3), count (nq,))."""
+        q = np.ascontiguousarray(q, dtype=np.int32).reshape(-1, 6)
+        xyth = np.empty((q.shape[0], cap, 3), dtype=np.float64)
+        cnt = np.empty(q.shape[0], dtype=np.int32)
+        check(lib().rrtk_ctx_dubins_sample(self._h, ptr(q), q.shape[0], int(nheadings), float(rho), float(ds), int(cap), ptr(xyth),
+                                           ptr(cnt)), "rrtk_ctx_dubins_sample")
+        return xyth, cnt
 
     # -- queries -------------------------------------------------------------------------------
     def collision(self, segs, world=0, cells=False):

@@ -48,6 +48,13 @@ int plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, in
                 const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int plan_footprint(int, int, int, int, int, int, int, int *, int *);
 int paths_launch(const int32_t *, const int64_t *, int, int, int, int32_t *, int32_t *, cudaStream_t);
+int plan2_launch(const rrtk_plan2_cfg &, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, const int16_t *, const uint8_t *,
+                 int16_t *, uint8_t *, double *, double *, int32_t *, int64_t *, void *, int, int, cudaStream_t);
+size_t plan2_scratch_bytes(int, int);
+int plan2_footprint(int, int, int, int, int *, int *);
+int dubins_paths_launch(const int32_t *, int64_t, int, double, int32_t *, double *, double *, cudaStream_t);
+int dubins_walk_launch(const uint32_t *, int, int, const int32_t *, const int32_t *, int64_t, int, double, double, uint8_t *, int,
+                       double *, int32_t *, cudaStream_t);
 
 struct DevInfo { int dev = -1, sms = 0, optin = 0, sm_smem = 0; };
 static thread_local DevInfo g_dev;
@@ -123,6 +130,7 @@ struct rrtk_ctx {
     DevBuf plans, samples, state, balls;        // plan inputs
     DevBuf pts, cost, parent, stats, ell;       // plan outputs
     DevBuf a, b, c, d, e;                       // query scratch
+    DevBuf heads, head_out, elen, scratch2;     // K8 (rrtk_ctx_plan2)
     PipeSlot pipe[kPipeSlots];
 };
 
@@ -347,7 +355,8 @@ int rrtk_destroy(rrtk_ctx *c)
 {
     if (!c) return RRTK_OK;
     DevBuf *all[] = {&c->og, &c->bits, &c->rowcum, &c->plans, &c->samples, &c->state, &c->balls, &c->pts,
-                     &c->cost, &c->parent, &c->stats, &c->ell, &c->a, &c->b, &c->c, &c->d, &c->e};
+                     &c->cost, &c->parent, &c->stats, &c->ell, &c->a, &c->b, &c->c, &c->d, &c->e,
+                     &c->heads, &c->head_out, &c->elen, &c->scratch2};
     for (DevBuf *b : all) b->release();
     for (PipeSlot &p : c->pipe) {
         DevBuf *pb[] = {&p.og, &p.bits, &p.rowcum, &p.plans, &p.samples, &p.state, &p.balls, &p.pts, &p.cost, &p.parent, &p.stats, &p.ell};
@@ -718,6 +727,234 @@ int rrtk_ctx_near_order_f64(rrtk_ctx *c, const double *h_pts, int npts, double q
     // non-negative doubles order like their bit patterns, so the int64 sorter applies
     RRTK_TRY(dist_launch_f64(c->a.as<double>(), npts, qx, qy, c->b.as<double>(), c->stream));
     return near_order_common(c, npts, h_perm);
+}
+
+// ---- K8: rewire / Dubins planners and the Dubins primitive ----------------------------------------------
+static int check_plan2_cfg(const rrtk_plan2_cfg *cfg)
+{
+    RRTK_REQUIRE(cfg, "rrtk_plan2: null configuration");
+    RRTK_REQUIRE(cfg->model == RRTK_MODEL_EUCLID || cfg->model == RRTK_MODEL_DUBINS, "rrtk_plan2: unknown model");
+    RRTK_REQUIRE(cfg->r_rewire == cfg->r_rewire, "rrtk_plan2: NaN radius");
+    if (cfg->model == RRTK_MODEL_DUBINS) {
+        RRTK_REQUIRE(cfg->nheadings >= 1 && cfg->nheadings <= 255, "rrtk_plan2: need 1 <= nheadings <= 255");
+        RRTK_REQUIRE(cfg->rho > 0.0 && cfg->ds > 0.0 && cfg->rho < 1e9 && cfg->ds < 1e9, "rrtk_plan2: need rho > 0 and ds > 0");
+    }
+    return RRTK_OK;
+}
+
+static int check_dubins_args(int nheadings, double rho, double ds)
+{
+    RRTK_REQUIRE(nheadings >= 1 && nheadings <= 255, "dubins: need 1 <= nheadings <= 255");
+    RRTK_REQUIRE(rho > 0.0 && rho < 1e9 && ds > 0.0 && ds < 1e9, "dubins: need rho > 0 and ds > 0");
+    return RRTK_OK;
+}
+
+size_t rrtk_plan2_scratch_bytes(int nplans, int n) { return (nplans < 0 || n < 1) ? 0 : plan2_scratch_bytes(nplans, n); }
+
+int rrtk_plan2_batch(const rrtk_plan2_cfg *cfg, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans, int nplans, int n,
+                     const int16_t *d_samples, const uint8_t *d_heads, int16_t *d_pts, uint8_t *d_head, double *d_cost, double *d_elen,
+                     int32_t *d_parent, int64_t *d_stats, void *d_scratch, int threads, void *stream)
+{
+    RRTK_TRY(check_plan2_cfg(cfg));
+    RRTK_REQUIRE(d_bits && d_plans && d_samples && d_pts && d_head && d_cost && d_elen && d_parent && d_stats && d_scratch,
+                 "rrtk_plan2_batch: null pointer");
+    RRTK_REQUIRE(nplans >= 0 && n >= 1 && n <= 65534, "rrtk_plan2_batch: need nplans >= 0 and 1 <= n <= 65534");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    if (nplans == 0) return RRTK_OK;
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return plan2_launch(*cfg, d_bits, W, H, d_plans, nplans, n, d_samples, d_heads, d_pts, d_head, d_cost, d_elen, d_parent, d_stats,
+                        d_scratch, threads, d->optin, (cudaStream_t)stream);
+}
+
+int rrtk_plan2_footprint(int n, int threads, int *smem_bytes, int *blocks_per_sm)
+{
+    RRTK_REQUIRE(n >= 1 && n <= 65534, "rrtk_plan2_footprint: need 1 <= n <= 65534");
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    int rc = plan2_footprint(n, threads, d->optin, d->sm_smem, smem_bytes, blocks_per_sm);
+    if (rc) set_error("plan with n=%d does not fit shared memory", n);
+    return rc;
+}
+
+int rrtk_dubins_paths(const int32_t *d_q, int64_t nq, int nheadings, double rho, int32_t *d_word, double *d_tpq, double *d_len,
+                      void *stream)
+{
+    RRTK_REQUIRE(d_q && nq >= 0, "rrtk_dubins_paths: bad argument");
+    RRTK_TRY(check_dubins_args(nheadings, rho, 1.0));
+    if (nq == 0) return RRTK_OK;
+    return dubins_paths_launch(d_q, nq, nheadings, rho, d_word, d_tpq, d_len, (cudaStream_t)stream);
+}
+
+int rrtk_dubins_collision(const uint32_t *d_bits, int W, int H, const int32_t *d_q, const int32_t *d_world, int64_t nq, int nheadings,
+                          double rho, double ds, uint8_t *d_free, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_q && d_free && nq >= 0, "rrtk_dubins_collision: bad argument");
+    RRTK_TRY(check_dubins_args(nheadings, rho, ds));
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    if (nq == 0) return RRTK_OK;
+    return dubins_walk_launch(d_bits, W, H, d_q, d_world, nq, nheadings, rho, ds, d_free, 0, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int rrtk_dubins_sample(const int32_t *d_q, int64_t nq, int nheadings, double rho, double ds, int cap, double *d_xyth, int32_t *d_count,
+                       void *stream)
+{
+    RRTK_REQUIRE(d_q && d_xyth && d_count && nq >= 0 && cap >= 1, "rrtk_dubins_sample: bad argument");
+    RRTK_TRY(check_dubins_args(nheadings, rho, ds));
+    if (nq == 0) return RRTK_OK;
+    return dubins_walk_launch(nullptr, 1, 1, d_q, nullptr, nq, nheadings, rho, ds, nullptr, cap, d_xyth, d_count, (cudaStream_t)stream);
+}
+
+int rrtk_ctx_plan2(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc *h_plans, int nplans, int n, const int16_t *h_samples,
+                   const uint64_t *h_state, const uint8_t *h_heads, int16_t *h_pts, uint8_t *h_head, double *h_cost, double *h_elen,
+                   int32_t *h_parent, int64_t *h_stats)
+{
+    RRTK_TRY(check_plan2_cfg(cfg));
+    RRTK_REQUIRE(c && h_plans && h_pts && h_head && h_cost && h_elen && h_parent && h_stats, "rrtk_ctx_plan2: null pointer");
+    RRTK_REQUIRE(c->nworlds > 0, "rrtk_ctx_plan2: call rrtk_ctx_set_grids first");
+    RRTK_REQUIRE((h_samples != nullptr) != (h_state != nullptr), "rrtk_ctx_plan2: pass exactly one of h_samples / h_state");
+    RRTK_REQUIRE(nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan2: need nplans >= 0 and 1 <= n <= 65534");
+    if (nplans == 0) return RRTK_OK;
+    const bool dub = cfg->model == RRTK_MODEL_DUBINS;
+    for (int p = 0; p < nplans; ++p) {
+        const rrtk_plan_desc &d = h_plans[p];
+        if (d.world < 0 || d.world >= c->nworlds || d.start_x < 0 || d.start_x >= c->W || d.goal_x < 0 || d.goal_x >= c->W ||
+            d.start_y < 0 || d.start_y >= c->H || d.goal_y < 0 || d.goal_y >= c->H) {
+            set_error("plan %d: world index or start/goal outside the grid", p);
+            return RRTK_ERR_INVALID;
+        }
+        if (dub && (d.reserved[0] < 0 || d.reserved[0] >= cfg->nheadings || d.reserved[1] < 0 || d.reserved[1] >= cfg->nheadings)) {
+            set_error("plan %d: start / goal heading outside [0, %d)", p, cfg->nheadings);
+            return RRTK_ERR_INVALID;
+        }
+    }
+    const size_t total = (size_t)nplans * n;
+    if (h_samples)
+        for (size_t i = 0; i < total; ++i) {
+            const int x = h_samples[2 * i], y = h_samples[2 * i + 1];
+            if (x < 0 || x >= c->W || y < 0 || y >= c->H) {
+                set_error("sample %zu of plan %zu lies outside the grid", i % n, i / n);
+                return RRTK_ERR_INVALID;
+            }
+        }
+    if (dub && h_heads)
+        for (size_t i = 0; i < total; ++i)
+            if (h_heads[i] >= cfg->nheadings) {
+                set_error("heading of sample %zu of plan %zu outside [0, %d)", i % n, i / n, cfg->nheadings);
+                return RRTK_ERR_INVALID;
+            }
+    const size_t rows = (size_t)nplans * (n + 1);
+    cudaStream_t st = c->stream;
+    RRTK_TRY(c->plans.reserve(sizeof(rrtk_plan_desc) * nplans));
+    RRTK_TRY(c->samples.reserve(total * 4));
+    RRTK_TRY(c->heads.reserve(total));
+    RRTK_TRY(c->pts.reserve(rows * 4));
+    RRTK_TRY(c->head_out.reserve(rows));
+    RRTK_TRY(c->cost.reserve(rows * 8));
+    RRTK_TRY(c->elen.reserve(rows * 8));
+    RRTK_TRY(c->parent.reserve(rows * 4));
+    RRTK_TRY(c->stats.reserve((size_t)nplans * RRTK_STAT_COUNT * 8));
+    RRTK_TRY(c->scratch2.reserve(plan2_scratch_bytes(nplans, n)));
+    RRTK_CUDA(cudaMemcpyAsync(c->plans.p, h_plans, sizeof(rrtk_plan_desc) * nplans, cudaMemcpyHostToDevice, st));
+    if (h_samples) {
+        RRTK_CUDA(cudaMemcpyAsync(c->samples.p, h_samples, total * 4, cudaMemcpyHostToDevice, st));
+    } else {
+        DevInfo *d;
+        RRTK_TRY(dev_info(&d));
+        RRTK_TRY(c->state.reserve((size_t)nplans * 32));
+        RRTK_CUDA(cudaMemcpyAsync(c->state.p, h_state, (size_t)nplans * 32, cudaMemcpyHostToDevice, st));
+        RRTK_TRY(sample_streams_launch(c->bits.as<uint32_t>(), c->rowcum.as<int32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(),
+                                       nplans, c->state.as<uint64_t>(), n, c->samples.as<int16_t>(), d->optin, st));
+    }
+    if (h_heads) RRTK_CUDA(cudaMemcpyAsync(c->heads.p, h_heads, total, cudaMemcpyHostToDevice, st));
+    RRTK_TRY(rrtk_plan2_batch(cfg, c->bits.as<uint32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(), nplans, n, c->samples.as<int16_t>(),
+                              h_heads ? c->heads.as<uint8_t>() : nullptr, c->pts.as<int16_t>(), c->head_out.as<uint8_t>(),
+                              c->cost.as<double>(), c->elen.as<double>(), c->parent.as<int32_t>(), c->stats.as<int64_t>(),
+                              c->scratch2.p, 0, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_pts, c->pts.p, rows * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_head, c->head_out.p, rows, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_cost, c->cost.p, rows * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_elen, c->elen.p, rows * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_parent, c->parent.p, rows * 4, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaMemcpyAsync(h_stats, c->stats.p, (size_t)nplans * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    RRTK_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < nplans; ++p)
+        if (h_stats[(size_t)p * RRTK_STAT_COUNT + RRTK_STAT2_OVERFLOW]) {
+            set_error("plan %d: a rewire-radius set exceeded the kernel's list (1024 vertices); reduce r_rewire", p);
+            return RRTK_ERR_CAPACITY;
+        }
+    return RRTK_OK;
+}
+
+int rrtk_ctx_dubins_paths(rrtk_ctx *c, const int32_t *h_q, int64_t nq, int nheadings, double rho, int32_t *h_word, double *h_tpq,
+                          double *h_len)
+{
+    RRTK_REQUIRE(c && h_q && nq >= 0, "rrtk_ctx_dubins_paths: bad argument");
+    if (nq == 0) return RRTK_OK;
+    RRTK_TRY(c->a.reserve((size_t)nq * 24));
+    RRTK_TRY(c->b.reserve((size_t)nq * 4));
+    RRTK_TRY(c->c.reserve((size_t)nq * 24));
+    RRTK_TRY(c->d.reserve((size_t)nq * 8));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_q, (size_t)nq * 24, cudaMemcpyHostToDevice, c->stream));
+    RRTK_TRY(rrtk_dubins_paths(c->a.as<int32_t>(), nq, nheadings, rho, c->b.as<int32_t>(), c->c.as<double>(), c->d.as<double>(), c->stream));
+    if (h_word) RRTK_CUDA(cudaMemcpyAsync(h_word, c->b.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (h_tpq) RRTK_CUDA(cudaMemcpyAsync(h_tpq, c->c.p, (size_t)nq * 24, cudaMemcpyDeviceToHost, c->stream));
+    if (h_len) RRTK_CUDA(cudaMemcpyAsync(h_len, c->d.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->stream));
+    RRTK_CUDA(cudaStreamSynchronize(c->stream));
+    return RRTK_OK;
+}
+
+static int check_dubins_queries(const rrtk_ctx *c, const int32_t *h_q, int64_t nq, int nheadings, bool in_grid)
+{
+    for (int64_t i = 0; i < nq; ++i) {
+        const int32_t *e = h_q + 6 * i;
+        if (e[2] < 0 || e[2] >= nheadings || e[5] < 0 || e[5] >= nheadings) {
+            set_error("dubins query %lld: heading outside [0, %d)", (long long)i, nheadings);
+            return RRTK_ERR_INVALID;
+        }
+        if (in_grid && (e[0] < 0 || e[0] >= c->W || e[3] < 0 || e[3] >= c->W || e[1] < 0 || e[1] >= c->H || e[4] < 0 || e[4] >= c->H)) {
+            set_error("dubins query %lld: end point outside the grid", (long long)i);
+            return RRTK_ERR_INVALID;
+        }
+    }
+    return RRTK_OK;
+}
+
+int rrtk_ctx_dubins_collision(rrtk_ctx *c, int world, const int32_t *h_q, int64_t nq, int nheadings, double rho, double ds,
+                              uint8_t *h_free)
+{
+    RRTK_REQUIRE(c && h_q && h_free && nq >= 0, "rrtk_ctx_dubins_collision: bad argument");
+    RRTK_REQUIRE(c->nworlds > 0 && world >= 0 && world < c->nworlds, "rrtk_ctx_dubins_collision: no such world (rrtk_ctx_set_grids first)");
+    RRTK_TRY(check_dubins_args(nheadings, rho, ds));
+    RRTK_TRY(check_dubins_queries(c, h_q, nq, nheadings, true));
+    if (nq == 0) return RRTK_OK;
+    RRTK_TRY(c->a.reserve((size_t)nq * 24));
+    RRTK_TRY(c->b.reserve((size_t)nq));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_q, (size_t)nq * 24, cudaMemcpyHostToDevice, c->stream));
+    RRTK_TRY(rrtk_dubins_collision(c->bits.as<uint32_t>() + (size_t)world * grid_words(c->W, c->H), c->W, c->H, c->a.as<int32_t>(), nullptr,
+                                   nq, nheadings, rho, ds, c->b.as<uint8_t>(), c->stream));
+    RRTK_CUDA(cudaMemcpyAsync(h_free, c->b.p, (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+    RRTK_CUDA(cudaStreamSynchronize(c->stream));
+    return RRTK_OK;
+}
+
+int rrtk_ctx_dubins_sample(rrtk_ctx *c, const int32_t *h_q, int64_t nq, int nheadings, double rho, double ds, int cap, double *h_xyth,
+                           int32_t *h_count)
+{
+    RRTK_REQUIRE(c && h_q && h_xyth && h_count && nq >= 0 && cap >= 1, "rrtk_ctx_dubins_sample: bad argument");
+    RRTK_TRY(check_dubins_args(nheadings, rho, ds));
+    RRTK_TRY(check_dubins_queries(c, h_q, nq, nheadings, false));
+    if (nq == 0) return RRTK_OK;
+    RRTK_TRY(c->a.reserve((size_t)nq * 24));
+    RRTK_TRY(c->b.reserve((size_t)nq * cap * 24));
+    RRTK_TRY(c->c.reserve((size_t)nq * 4));
+    RRTK_CUDA(cudaMemcpyAsync(c->a.p, h_q, (size_t)nq * 24, cudaMemcpyHostToDevice, c->stream));
+    RRTK_CUDA(cudaMemsetAsync(c->b.p, 0, (size_t)nq * cap * 24, c->stream));
+    RRTK_TRY(rrtk_dubins_sample(c->a.as<int32_t>(), nq, nheadings, rho, ds, cap, c->b.as<double>(), c->c.as<int32_t>(), c->stream));
+    RRTK_CUDA(cudaMemcpyAsync(h_xyth, c->b.p, (size_t)nq * cap * 24, cudaMemcpyDeviceToHost, c->stream));
+    RRTK_CUDA(cudaMemcpyAsync(h_count, c->c.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->stream));
+    RRTK_CUDA(cudaStreamSynchronize(c->stream));
+    return RRTK_OK;
 }
 
 }  // extern "C"

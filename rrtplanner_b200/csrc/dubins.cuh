@@ -1,0 +1,263 @@
+// Dubins primitive on the device ("Dubins Primitive Module", README.md:12 of the reference -- advertised there, absent
+// from its tree; the specification is oracle/rewire_oracle.c and every function here must agree with it bit for bit).
+//
+// All arithmetic is IEEE-754 double add / sub / mul / div / sqrt / floor in the order the specification fixes; the
+// library is compiled with --fmad=false so nothing is contracted.  atan2 / sin / cos are the specification's own
+// polynomials (dm_*), not CUDA's libm, because last-ulp differences would change strict cost comparisons and hence trees.
+#pragma once
+#include "common.cuh"
+
+namespace rrtk {
+
+#define DM_PI 3.14159265358979323846
+#define DM_TWO_PI 6.28318530717958647692
+#define DM_HALF_PI 1.57079632679489661923
+#define DM_QUARTER_PI 0.78539816339744830962
+#define DM_TWO_OVER_PI 0.63661977236758134308
+#define DM_TAN_PI_8 0.41421356237309504880
+
+// atan(z), |z| <= tan(pi/8): z * sum_{k<22} (-1)^k z^(2k) / (2k+1), Horner in z^2
+__device__ __forceinline__ double dm_atan_small(double z)
+{
+    const double s = z * z;
+    double p = -1.0 / 43.0;
+#pragma unroll
+    for (int k = 20; k >= 0; --k) {
+        const double c = (k & 1) ? -1.0 / (double)(2 * k + 1) : 1.0 / (double)(2 * k + 1);
+        p = p * s + c;
+    }
+    return z * p;
+}
+
+__device__ __noinline__ double dm_atan2(double y, double x)
+{
+    if (x == 0.0 && y == 0.0) return 0.0;
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double num = swap ? ax : ay, den = swap ? ay : ax;
+    const double a = num / den;
+    double r;
+    if (a > DM_TAN_PI_8) r = DM_QUARTER_PI + dm_atan_small((a - 1.0) / (a + 1.0));
+    else r = dm_atan_small(a);
+    if (swap) r = DM_HALF_PI - r;
+    if (x < 0.0) r = DM_PI - r;
+    if (y < 0.0) r = -r;
+    return r;
+}
+
+// quadrant k = floor(a * 2/pi + 1/2), r = a - k * pi/2, Taylor polynomials on |r| <= pi/4
+__device__ __noinline__ void dm_sincos(double a, double &sn, double &cs)
+{
+    const double kf = floor(a * DM_TWO_OVER_PI + 0.5);
+    const double r = a - kf * DM_HALF_PI;
+    const double s = r * r;
+    double ps = -1.0 / 1307674368000.0;
+    ps = ps * s + 1.0 / 6227020800.0;
+    ps = ps * s - 1.0 / 39916800.0;
+    ps = ps * s + 1.0 / 362880.0;
+    ps = ps * s - 1.0 / 5040.0;
+    ps = ps * s + 1.0 / 120.0;
+    ps = ps * s - 1.0 / 6.0;
+    ps = ps * s + 1.0;
+    ps = ps * r;
+    double pc = 1.0 / 20922789888000.0;
+    pc = pc * s - 1.0 / 87178291200.0;
+    pc = pc * s + 1.0 / 479001600.0;
+    pc = pc * s - 1.0 / 3628800.0;
+    pc = pc * s + 1.0 / 40320.0;
+    pc = pc * s - 1.0 / 720.0;
+    pc = pc * s + 1.0 / 24.0;
+    pc = pc * s - 1.0 / 2.0;
+    pc = pc * s + 1.0;
+    const long long k = (long long)kf;
+    switch ((int)(k & 3)) {
+        case 0: sn = ps; cs = pc; break;
+        case 1: sn = pc; cs = -ps; break;
+        case 2: sn = -ps; cs = -pc; break;
+        default: sn = -pc; cs = ps; break;
+    }
+}
+
+__device__ __forceinline__ double dm_mod2pi(double x) { return x - DM_TWO_PI * floor(x / DM_TWO_PI); }
+__device__ __forceinline__ double dm_acos(double v) { return dm_atan2(sqrt(1.0 - v * v), v); }
+
+struct DubinsPath {
+    int word;               // 0..5 = LSL RSR LSR RSL RLR LRL, -1 none
+    double t, p, q, len;    // normalised segment lengths, total length in cells
+};
+
+struct DubinsIn { double d, dd, alpha, beta, sa, ca, sb, cb, cab; };
+
+// tab[h] = (sin, cos) of heading h, i.e. dm_sincos(h * 2 pi / NH) -- the same values the specification recomputes
+__device__ __forceinline__ void dubins_setup(int dx, int dy, int h0, int h1, int NH, double rho, const double2 *tab, DubinsIn &g)
+{
+    const double dth = DM_TWO_PI / (double)NH;
+    const double th0 = (double)h0 * dth, th1 = (double)h1 * dth;
+    const double2 a0 = tab[h0], a1 = tab[h1];
+    int hd = (h0 - h1) % NH;
+    if (hd < 0) hd += NH;
+    const double D = sqrt((double)((long long)dx * dx + (long long)dy * dy));
+    g.d = D / rho;
+    g.dd = g.d * g.d;
+    double cphi = 1.0, sphi = 0.0;
+    if (D > 0.0) { cphi = (double)dx / D; sphi = (double)dy / D; }
+    const double phi = dm_atan2((double)dy, (double)dx);
+    g.alpha = dm_mod2pi(th0 - phi);
+    g.beta = dm_mod2pi(th1 - phi);
+    g.sa = a0.x * cphi - a0.y * sphi; g.ca = a0.y * cphi + a0.x * sphi;
+    g.sb = a1.x * cphi - a1.y * sphi; g.cb = a1.y * cphi + a1.x * sphi;
+    g.cab = tab[hd].y;
+}
+
+__device__ __forceinline__ bool dubins_word(const DubinsIn &g, int w, double &t, double &p, double &q)
+{
+    const double d = g.d, dd = g.dd, alpha = g.alpha, beta = g.beta;
+    const double sa = g.sa, ca = g.ca, sb = g.sb, cb = g.cb, cab = g.cab;
+    double tmp, psq;
+    switch (w) {
+        case 0:
+            psq = 2.0 + dd - 2.0 * cab + 2.0 * d * (sa - sb);
+            if (psq < 0.0) return false;
+            tmp = dm_atan2(cb - ca, d + sa - sb);
+            t = dm_mod2pi(tmp - alpha); p = sqrt(psq); q = dm_mod2pi(beta - tmp);
+            return true;
+        case 1:
+            psq = 2.0 + dd - 2.0 * cab + 2.0 * d * (sb - sa);
+            if (psq < 0.0) return false;
+            tmp = dm_atan2(ca - cb, d - sa + sb);
+            t = dm_mod2pi(alpha - tmp); p = sqrt(psq); q = dm_mod2pi(tmp - beta);
+            return true;
+        case 2:
+            psq = dd - 2.0 + 2.0 * cab + 2.0 * d * (sa + sb);
+            if (psq < 0.0) return false;
+            p = sqrt(psq);
+            tmp = dm_atan2(-ca - cb, d + sa + sb) - dm_atan2(-2.0, p);
+            t = dm_mod2pi(tmp - alpha); q = dm_mod2pi(tmp - dm_mod2pi(beta));
+            return true;
+        case 3:
+            psq = dd - 2.0 + 2.0 * cab - 2.0 * d * (sa + sb);
+            if (psq < 0.0) return false;
+            p = sqrt(psq);
+            tmp = dm_atan2(ca + cb, d - sa - sb) - dm_atan2(2.0, p);
+            t = dm_mod2pi(alpha - tmp); q = dm_mod2pi(beta - tmp);
+            return true;
+        case 4:
+            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
+            if (fabs(tmp) > 1.0) return false;
+            p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
+            t = dm_mod2pi(alpha - dm_atan2(ca - cb, d - sa + sb) + p / 2.0);
+            q = dm_mod2pi(alpha - beta - t + p);
+            return true;
+        default:
+            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sb - sa)) / 8.0;
+            if (fabs(tmp) > 1.0) return false;
+            p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
+            t = dm_mod2pi(p / 2.0 - alpha - dm_atan2(ca - cb, d + sa - sb));
+            q = dm_mod2pi(dm_mod2pi(beta) - alpha - t + p);
+            return true;
+    }
+}
+
+// shortest word from (0, 0, h0) to (dx, dy, h1); ties to the first word in the order above
+__device__ __noinline__ void dubins_shortest(int dx, int dy, int h0, int h1, int NH, double rho, const double2 *tab, DubinsPath &out)
+{
+    DubinsIn g;
+    dubins_setup(dx, dy, h0, h1, NH, rho, tab, g);
+    out.word = -1; out.len = CUDART_INF; out.t = out.p = out.q = 0.0;
+#pragma unroll 1
+    for (int w = 0; w < 6; ++w) {
+        double t, p, q;
+        if (!dubins_word(g, w, t, p, q)) continue;
+        const double len = ((t + p) + q) * rho;
+        if (len < out.len) { out.len = len; out.word = w; out.t = t; out.p = p; out.q = q; }
+    }
+}
+
+// segment kinds of word w, 2 bits each (0 left arc, 1 straight, 2 right arc): LSL RSR LSR RSL RLR LRL
+__device__ __forceinline__ int dubins_seg(int word, int i)
+{
+    const unsigned codes[6] = {0u | 1u << 2 | 0u << 4, 2u | 1u << 2 | 2u << 4, 0u | 1u << 2 | 2u << 4,
+                               2u | 1u << 2 | 0u << 4, 2u | 0u << 2 | 2u << 4, 0u | 2u << 2 | 0u << 4};
+    return (int)((codes[word] >> (2 * i)) & 3u);
+}
+
+struct Pose { double x, y, th; };
+
+__device__ __forceinline__ Pose dubins_advance(Pose a, int kind, double len, double rho)
+{
+    double s0, c0, s1, c1;
+    dm_sincos(a.th, s0, c0);
+    if (kind == 1) {
+        a.x = a.x + rho * len * c0;
+        a.y = a.y + rho * len * s0;
+    } else if (kind == 0) {
+        dm_sincos(a.th + len, s1, c1);
+        a.x = a.x + rho * (s1 - s0);
+        a.y = a.y + rho * (c0 - c1);
+        a.th = a.th + len;
+    } else {
+        dm_sincos(a.th - len, s1, c1);
+        a.x = a.x + rho * (s0 - s1);
+        a.y = a.y + rho * (c1 - c0);
+        a.th = a.th - len;
+    }
+    return a;
+}
+
+// the path cut at its two junctions: q0 start, q1 after the first segment, q2 after the second
+struct DubinsTrack {
+    Pose q0, q1, q2;
+    int k0, k1, k2;
+    double t, p, rho;
+};
+
+__device__ __forceinline__ DubinsTrack dubins_track(int x0, int y0, int h0, int NH, double rho, const DubinsPath &w)
+{
+    DubinsTrack tr;
+    tr.k0 = dubins_seg(w.word, 0); tr.k1 = dubins_seg(w.word, 1); tr.k2 = dubins_seg(w.word, 2);
+    tr.t = w.t; tr.p = w.p; tr.rho = rho;
+    tr.q0.x = (double)x0; tr.q0.y = (double)y0; tr.q0.th = (double)h0 * (DM_TWO_PI / (double)NH);
+    tr.q1 = dubins_advance(tr.q0, tr.k0, w.t, rho);
+    tr.q2 = dubins_advance(tr.q1, tr.k1, w.p, rho);
+    return tr;
+}
+
+// pose at arc length s (cells) from the start
+__device__ __forceinline__ Pose dubins_point(const DubinsTrack &tr, double s)
+{
+    const double u = s / tr.rho;
+    if (u < tr.t) return dubins_advance(tr.q0, tr.k0, u, tr.rho);
+    const double u2 = u - tr.t;
+    if (u2 < tr.p) return dubins_advance(tr.q1, tr.k1, u2, tr.rho);
+    return dubins_advance(tr.q2, tr.k2, u2 - tr.p, tr.rho);
+}
+
+__device__ __forceinline__ bool cell_blocked(const uint32_t *bits, int W, int H, int TY, double x, double y)
+{
+    const double fx = floor(x + 0.5), fy = floor(y + 0.5);
+    if (!(fx >= 0.0 && fx < (double)W && fy >= 0.0 && fy < (double)H)) return true;
+    const int cx = (int)fx, cy = (int)fy;
+    return (__ldg(bits + word_index(cx, cy, TY)) >> (cy & 31)) & 1u;
+}
+
+// warp-cooperative sampled collision test of the path w from (x0, y0, h0) to cell (x1, y1): points at arc length
+// k * ds, k = 0 .. floor(len / ds), one per lane and round, plus the target cell.  All lanes must pass the same path.
+__device__ __forceinline__ bool dubins_free_warp(const uint32_t *bits, int W, int H, int TY, int x0, int y0, int h0, int x1, int y1,
+                                                 int NH, double rho, double ds, const DubinsPath &w, int lane)
+{
+    if (w.word < 0) return false;
+    const DubinsTrack tr = dubins_track(x0, y0, h0, NH, rho, w);
+    const long long ns = (long long)floor(w.len / ds);
+    for (long long base = 0; base <= ns; base += 32) {
+        const long long k = base + lane;
+        bool hit = false;
+        if (k <= ns) {
+            const Pose a = dubins_point(tr, (double)k * ds);
+            hit = cell_blocked(bits, W, H, TY, a.x, a.y);
+        }
+        if (__any_sync(RRTK_FULL, hit)) return false;
+    }
+    return !((__ldg(bits + word_index(x1, y1, TY)) >> (y1 & 31)) & 1u);
+}
+
+}  // namespace rrtk

@@ -1,0 +1,581 @@
+// K8: planners the reference advertises but does not contain -- RRT* whose rewire step fires (the reference's
+// predicate rrt.py:532-536 never does) and the Dubins-vehicle RRT / RRT* (README.md:12,18-19).  Specification and
+// bit-exact oracle: oracle/rewire_oracle.c (parity UNPINNED: there is no reference code for these; with the Euclidean
+// model and rewire off this kernel reproduces the pinned reference trees, tests/test_gpu_rewire.py).
+//
+// One thread block per plan, one sample per round (a rewire changes costs the next sample's choose-parent reads, so
+// the K-samples-per-round replay of plan_scan.cuh does not apply).  Per round:
+//   A  scan      each warp owns a contiguous slice of the tree: nearest vertex (lowest index on ties), duplicate test,
+//                membership of the rewire radius as one ballot word per 32 vertices
+//   B  gate      ascending radius list from the ballot words; warp 0 builds the edge nearest -> sample and tests it
+//   C  parents   one thread per radius-set member: Euclidean prefilter, edge length (Dubins: shortest of six words)
+//   D  choose    warps test the candidates' edges, cheapest free one wins (cost, then vertex index)
+//   E  insert    vertex j; one thread per member: rewire prefilter + edge length sample -> member
+//   F  test      warps test the rewire candidates' edges
+//   G  apply     warp 0, ascending vertex order, re-testing against costs already lowered this round; the rewired
+//                subtree's costs are recomputed breadth-first over child lists kept in shared memory
+// The goal connection evaluates every vertex, prunes with a shared 64-bit minimum and breaks ties by index.
+#include <math_constants.h>
+
+#include "dubins.cuh"
+
+namespace rrtk {
+
+enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROPAGATED, S2_RING, S2_LEN_EVALS, S2_OVERFLOW };
+
+struct Plan2Params {
+    const uint32_t *bits;
+    size_t words_per_grid;
+    int W, H, TY;
+    const rrtk_plan_desc *plans;
+    int n;
+    int star, rewire, NH;
+    uint32_t r2_excl;
+    double rho, ds;
+    const short2 *samples;
+    const uint8_t *heads;
+    short2 *pts;
+    uint8_t *head;
+    double *cost;
+    double *elen;
+    int *parent;
+    long long *stats;
+    double *gcost;          // scratch: (n + 1) doubles per plan
+    uint16_t *queue;        // scratch: (n + 1) vertex ids per plan
+    int ring_cap;
+};
+
+constexpr uint16_t kNil = 0xffffu;
+
+template <int MODEL>
+struct Edge {
+    // length of a -> b
+    static __device__ __forceinline__ double length(const Plan2Params &P, const double2 *tab, uint32_t pa, int ha, uint32_t pb, int hb,
+                                                    DubinsPath &w)
+    {
+        if (MODEL == RRTK_MODEL_EUCLID) {
+            w.word = 0;
+            return __dsqrt_rn((double)dist2(pa, px(pb), py(pb)));
+        }
+        dubins_shortest(px(pb) - px(pa), py(pb) - py(pa), ha, hb, P.NH, P.rho, tab, w);
+        return w.len;
+    }
+    // warp-cooperative: is a -> b free (w = the path length() returned for the same pair)
+    static __device__ __forceinline__ bool is_free(const Plan2Params &P, const uint32_t *bits, uint32_t pa, int ha, uint32_t pb,
+                                                   const DubinsPath &w, int lane)
+    {
+        if (MODEL == RRTK_MODEL_EUCLID)
+            return warp_first_hit(GlobalGrid{bits}, P.TY, px(pa), py(pa), px(pb), py(pb), lane) < 0;
+        return dubins_free_warp(bits, P.W, P.H, P.TY, px(pa), py(pa), ha, px(pb), py(pb), P.NH, P.rho, P.ds, w, lane);
+    }
+};
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(RRTK_FULL, v, o);
+        v = other < v ? other : v;
+    }
+    return v;
+}
+
+template <int MODEL, int T>
+__global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
+{
+    constexpr int NW = T / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = P.n, cap = P.ring_cap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int plan = blockIdx.x;
+
+    // ---- shared-memory carve-up -------------------------------------------------------------------
+    unsigned char *sp = smem_raw;
+    double *valL = reinterpret_cast<double *>(sp); sp += sizeof(double) * cap;       // edge length per radius-set slot
+    double *valC = reinterpret_cast<double *>(sp); sp += sizeof(double) * cap;       // cost through that edge
+    double2 *tab = reinterpret_cast<double2 *>(sp); sp += sizeof(double2) * 256;     // (sin, cos) per heading
+    uint32_t *spts = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * (size_t)((n + 2) & ~1);
+    uint32_t *mask = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * (size_t)(((n + 1 + 31) / 32 + 1) & ~1);
+    uint16_t *first = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * (size_t)((n + 4) & ~3);
+    uint16_t *next = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * (size_t)((n + 4) & ~3);
+    uint16_t *ring = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * (size_t)cap;
+    uint8_t *flag = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
+    uint8_t *shead = reinterpret_cast<uint8_t *>(sp);
+
+    __shared__ unsigned long long s_wmin[NW];
+    __shared__ int s_wcnt[NW];
+    __shared__ int s_wdup[NW];
+    __shared__ unsigned long long s_best;       // bit pattern of the cheapest free candidate cost
+    __shared__ int s_bestv, s_bestslot;
+    __shared__ int s_accept, s_tail;
+    __shared__ double s_c0, s_l0, s_cbest, s_lbest;
+    __shared__ int s_vbest;
+    __shared__ long long s_stat[10];
+
+    const rrtk_plan_desc pd = P.plans[plan];
+    const uint32_t *bits = P.bits + (size_t)pd.world * P.words_per_grid;
+    const short2 *samples = P.samples + (size_t)plan * n;
+    const uint8_t *heads = P.heads ? P.heads + (size_t)plan * n : nullptr;
+    short2 *o_pts = P.pts + (size_t)plan * (n + 1);
+    uint8_t *o_head = P.head + (size_t)plan * (n + 1);
+    double *cost = P.cost + (size_t)plan * (n + 1);
+    double *elen = P.elen + (size_t)plan * (n + 1);
+    int *parent = P.parent + (size_t)plan * (n + 1);
+    double *gcost = P.gcost + (size_t)plan * (n + 1);
+    uint16_t *queue = P.queue + (size_t)plan * (n + 1);
+
+    // ---- initialise ---------------------------------------------------------------------------------
+    for (int v = tid; v <= n; v += T) {
+        spts[v] = RRTK_FAR_VERTEX; shead[v] = 255; first[v] = kNil; next[v] = kNil;
+        o_pts[v] = make_short2(-32768, -32768); o_head[v] = 255;
+        cost[v] = CUDART_INF; elen[v] = CUDART_INF; parent[v] = -1;
+    }
+    if (MODEL == RRTK_MODEL_DUBINS) {
+        const double dth = DM_TWO_PI / (double)P.NH;
+        for (int h = tid; h < P.NH; h += T) {
+            double s, c;
+            dm_sincos((double)h * dth, s, c);
+            tab[h] = make_double2(s, c);
+        }
+    }
+    if (tid < 10) s_stat[tid] = 0;
+    __syncthreads();
+    const int start_h = MODEL == RRTK_MODEL_DUBINS ? pd.reserved[0] : 0;
+    const int goal_h = MODEL == RRTK_MODEL_DUBINS ? pd.reserved[1] : 0;
+    if (tid == 0) {
+        spts[0] = pack_xy(pd.start_x, pd.start_y); shead[0] = (uint8_t)start_h;
+        o_pts[0] = make_short2((short)pd.start_x, (short)pd.start_y); o_head[0] = (uint8_t)start_h;
+        cost[0] = 0.0; elen[0] = 0.0;
+    }
+    __syncthreads();
+
+    int j = 1;
+    long long my_checks = 0, my_lens = 0;      // per-thread counters, reduced at the end
+
+    for (int it = 0; it < n; ++it) {
+        const short2 sm = samples[it];
+        const int qx = sm.x, qy = sm.y;
+        const int qh = (MODEL == RRTK_MODEL_DUBINS && heads) ? heads[it] : 0;
+        const uint32_t pnew = pack_xy(qx, qy);
+
+        // ---- A: scan ---------------------------------------------------------------------------------
+        const int chunk = (((j + NW - 1) / NW) + 31) & ~31;
+        const int v0 = warp * chunk, v1 = min(j, v0 + chunk);
+        {
+            uint32_t bd = 0xffffffffu;
+            int bv = 0, cnt = 0;
+            bool dup = false;
+            for (int base = v0; base < v1; base += 32) {
+                const int v = base + lane;
+                const bool in = v < v1;
+                const uint32_t d2 = in ? dist2(spts[v], qx, qy) : 0xffffffffu;
+                if (d2 < bd) { bd = d2; bv = v; }
+                dup |= in && d2 == 0u && v >= 1;
+                const unsigned m = __ballot_sync(RRTK_FULL, in && d2 < P.r2_excl);
+                if (lane == 0) mask[base >> 5] = m;
+                cnt += __popc(m);
+            }
+            const unsigned long long key = warp_min_u64(((unsigned long long)bd << 32) | (unsigned)bv);
+            const bool anydup = __any_sync(RRTK_FULL, dup);
+            if (lane == 0) { s_wmin[warp] = key; s_wcnt[warp] = cnt; s_wdup[warp] = anydup; }
+        }
+        __syncthreads();
+
+        // ---- B: radius list (ascending) + gate ---------------------------------------------------------
+        unsigned long long nk = s_wmin[0];
+        int m_total = 0, my_off = 0, dup_any = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            nk = s_wmin[w] < nk ? s_wmin[w] : nk;
+            if (w < warp) my_off += s_wcnt[w];
+            m_total += s_wcnt[w];
+            dup_any |= s_wdup[w];
+        }
+        const int vnear = (int)(nk & 0xffffffffu);
+        const bool overflow = P.star && m_total > cap;
+        if (P.star && !overflow) {
+            int off = my_off;
+            for (int base = v0; base < v1; base += 32) {
+                const unsigned m = mask[base >> 5];
+                if ((m >> lane) & 1u) ring[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base + lane);
+                off += __popc(m);
+            }
+        }
+        if (warp == 0) {
+            DubinsPath w0;
+            const uint32_t pn = spts[vnear];
+            const int hn = shead[vnear];
+            const double l0 = Edge<MODEL>::length(P, tab, pn, hn, pnew, qh, w0);
+            const bool ok = Edge<MODEL>::is_free(P, bits, pn, hn, pnew, w0, lane);
+            if (lane == 0) {
+                ++my_checks; ++my_lens;
+                const bool acc = ok && !dup_any && j != n && !overflow;
+                s_accept = acc;
+                if (overflow) s_stat[S2_OVERFLOW] = 1;
+                const double c0 = __dadd_rn(cost[vnear], l0);
+                s_c0 = c0; s_l0 = l0;
+                s_best = 0xffffffffffffffffull; s_bestv = 0x7fffffff; s_bestslot = -1;
+            }
+        }
+        __syncthreads();
+        if (!s_accept) continue;                 // uniform: every thread reads the same shared flag
+        const double c0 = s_c0;
+        const int m = P.star ? m_total : 0;
+
+        // ---- C: parent candidates -----------------------------------------------------------------------
+        for (int i = tid; i < m; i += T) {
+            const int vn = ring[i];
+            uint8_t f = 0;
+            if (vn != vnear) {
+                const uint32_t pv = spts[vn];
+                const double cv = cost[vn];
+                const double D = __dsqrt_rn((double)dist2(pv, qx, qy));
+                if (__dadd_rn(cv, D) < c0) {
+                    DubinsPath w;
+                    const double lc = Edge<MODEL>::length(P, tab, pv, shead[vn], pnew, qh, w);
+                    ++my_lens;
+                    const double cn = __dadd_rn(cv, lc);
+                    if (cn < c0) { valL[i] = lc; valC[i] = cn; f = 1; }
+                }
+            }
+            flag[i] = f;
+        }
+        __syncthreads();
+
+        // ---- D: choose the parent ------------------------------------------------------------------------
+        for (int i = warp; i < m; i += NW) {
+            if (!flag[i]) continue;
+            const double cn = valC[i];
+            if ((unsigned long long)__double_as_longlong(cn) > s_best) continue;    // a cheaper free edge is known
+            const int vn = ring[i];
+            const uint32_t pv = spts[vn];
+            DubinsPath w;
+            if (MODEL == RRTK_MODEL_DUBINS) Edge<MODEL>::length(P, tab, pv, shead[vn], pnew, qh, w);
+            const bool ok = Edge<MODEL>::is_free(P, bits, pv, shead[vn], pnew, w, lane);
+            if (lane == 0) {
+                ++my_checks;
+                if (ok) { flag[i] = 2; atomicMin(&s_best, (unsigned long long)__double_as_longlong(cn)); }
+            }
+        }
+        __syncthreads();
+        if (s_best != 0xffffffffffffffffull) {
+            const unsigned long long best = s_best;
+            for (int i = tid; i < m; i += T)
+                if (flag[i] == 2 && (unsigned long long)__double_as_longlong(valC[i]) == best) atomicMin(&s_bestv, (int)ring[i]);
+            __syncthreads();
+            const int bv = s_bestv;
+            for (int i = tid; i < m; i += T)
+                if (ring[i] == bv) s_bestslot = i;
+            __syncthreads();
+        }
+        // ---- E: insert vertex j, rewire candidates ---------------------------------------------------------
+        int vbest = vnear;
+        double cbest = c0, lbest = s_l0;
+        if (s_bestslot >= 0) { vbest = s_bestv; cbest = valC[s_bestslot]; lbest = valL[s_bestslot]; }
+        __syncthreads();                         // valC / valL / flag are rewritten below
+        if (tid == 0) {
+            spts[j] = pnew; shead[j] = (uint8_t)qh;
+            o_pts[j] = make_short2((short)qx, (short)qy); o_head[j] = (uint8_t)qh;
+            cost[j] = cbest; elen[j] = lbest; parent[j] = vbest;
+            next[j] = first[vbest]; first[vbest] = (uint16_t)j;
+            s_stat[S2_ACCEPTED] += 1; s_stat[S2_RING] += m;
+        }
+        if (P.rewire) {
+            for (int i = tid; i < m; i += T) {
+                const int vn = ring[i];
+                uint8_t f = 0;
+                if (vn != vbest) {
+                    const uint32_t pv = spts[vn];
+                    const double cv = cost[vn];
+                    const double D = __dsqrt_rn((double)dist2(pv, qx, qy));
+                    if (__dadd_rn(cbest, D) < cv) {
+                        DubinsPath w;
+                        const double lr = Edge<MODEL>::length(P, tab, pnew, qh, pv, shead[vn], w);
+                        ++my_lens;
+                        const double cm = __dadd_rn(cbest, lr);
+                        if (cm < cv) { valL[i] = lr; valC[i] = cm; f = 1; }
+                    }
+                }
+                flag[i] = f;
+            }
+            __syncthreads();
+            // ---- F: test the rewire edges sample -> member -------------------------------------------------
+            for (int i = warp; i < m; i += NW) {
+                if (!flag[i]) continue;
+                const int vn = ring[i];
+                const uint32_t pv = spts[vn];
+                DubinsPath w;
+                if (MODEL == RRTK_MODEL_DUBINS) Edge<MODEL>::length(P, tab, pnew, qh, pv, shead[vn], w);
+                const bool ok = Edge<MODEL>::is_free(P, bits, pnew, qh, pv, w, lane);
+                if (lane == 0) { ++my_checks; flag[i] = ok ? 2 : 0; }
+            }
+            __syncthreads();
+            // ---- G: apply in ascending vertex order ----------------------------------------------------------
+            if (warp == 0) {
+                for (int base = 0; base < m; base += 32) {
+                    const int i = base + lane;
+                    unsigned todo = __ballot_sync(RRTK_FULL, i < m && flag[i] == 2);
+                    while (todo) {
+                        const int b = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const int slot = base + b;
+                        const int vn = ring[slot];
+                        const double cm = valC[slot], lr = valL[slot];
+                        const double cv = cost[vn];              // may have been lowered by an earlier rewire of this round
+                        const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
+                        if (!(__dadd_rn(cbest, D) < cv && cm < cv)) continue;       // warp-uniform
+                        if (lane == 0) {
+                            const int op = parent[vn];
+                            if (first[op] == vn) first[op] = next[vn];
+                            else { int c = first[op]; while (next[c] != vn) c = next[c]; next[c] = next[vn]; }
+                            next[vn] = first[j]; first[j] = (uint16_t)vn;
+                            parent[vn] = j; elen[vn] = lr; cost[vn] = cm;
+                            queue[0] = (uint16_t)vn;
+                            s_tail = 1;
+                            s_stat[S2_REWIRES] += 1;
+                        }
+                        __syncwarp();
+                        int qhd = 0, qtl = 1;
+                        while (qhd < qtl) {                       // breadth-first: a level's costs are final before its children read them
+                            const int take = min(32, qtl - qhd);
+                            if (lane < take) {
+                                const int u = queue[qhd + lane];
+                                const double cu = cost[u];
+                                for (int c = first[u]; c != kNil; c = next[c]) {
+                                    cost[c] = __dadd_rn(cu, elen[c]);
+                                    queue[atomicAdd(&s_tail, 1)] = (uint16_t)c;
+                                }
+                            }
+                            qhd += take;
+                            __syncwarp();
+                            qtl = s_tail;
+                            __syncwarp();
+                        }
+                        if (lane == 0) s_stat[S2_PROPAGATED] += qtl - 1;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        ++j;
+        __syncthreads();
+    }
+
+    // ---- goal connection (rrt.py:284-332 with this model's edges) ----------------------------------------
+    const uint32_t pgoal = pack_xy(pd.goal_x, pd.goal_y);
+    if (tid == 0) { s_best = 0xffffffffffffffffull; s_bestv = 0x7fffffff; }
+    for (int v = tid; v < j; v += T) {
+        DubinsPath w;
+        const double lg = Edge<MODEL>::length(P, tab, spts[v], shead[v], pgoal, goal_h, w);
+        ++my_lens;
+        gcost[v] = __dadd_rn(cost[v], lg);
+    }
+    __syncthreads();
+    // every vertex whose cost is not already beaten is tested; the shared minimum only prunes
+    for (int v = warp; v < j; v += NW) {
+        const double cg = gcost[v];
+        if ((unsigned long long)__double_as_longlong(cg) > s_best) continue;        // a cheaper free edge is known
+        DubinsPath w;
+        if (MODEL == RRTK_MODEL_DUBINS) Edge<MODEL>::length(P, tab, spts[v], shead[v], pgoal, goal_h, w);
+        const bool ok = Edge<MODEL>::is_free(P, bits, spts[v], shead[v], pgoal, w, lane);
+        if (lane == 0) {
+            ++my_checks;
+            if (ok) atomicMin(&s_best, (unsigned long long)__double_as_longlong(cg));
+            queue[v] = ok ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    const unsigned long long gbest = s_best;
+    if (gbest != 0xffffffffffffffffull) {
+        for (int v = tid; v < j; v += T) {
+            const unsigned long long b = (unsigned long long)__double_as_longlong(gcost[v]);
+            // a vertex with cost == gbest was never pruned (pruning needs cost > best >= gbest), so queue[v] is its verdict
+            if (b == gbest && queue[v] == 1) atomicMin(&s_bestv, v);
+        }
+    }
+    __syncthreads();
+    // reduce the per-thread counters
+    for (int o = 16; o > 0; o >>= 1) {
+        my_checks += __shfl_xor_sync(RRTK_FULL, my_checks, o);
+        my_lens += __shfl_xor_sync(RRTK_FULL, my_lens, o);
+    }
+    if (lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_stat[S2_CHECKS]), (unsigned long long)my_checks);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&s_stat[S2_LEN_EVALS]), (unsigned long long)my_lens);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int vgoal = 0, found = 0;
+        if (gbest != 0xffffffffffffffffull) {
+            const int v = s_bestv;
+            DubinsPath w;
+            const double lg = Edge<MODEL>::length(P, tab, spts[v], shead[v], pgoal, goal_h, w);
+            vgoal = j; found = 1;
+            o_pts[j] = make_short2((short)pd.goal_x, (short)pd.goal_y); o_head[j] = (uint8_t)goal_h;
+            cost[j] = gcost[v]; elen[j] = lg; parent[j] = v;
+        }
+        long long *st = P.stats + (size_t)plan * RRTK_STAT_COUNT;
+        for (int k = 0; k < RRTK_STAT_COUNT; ++k) st[k] = k < 10 ? s_stat[k] : 0;
+        st[S2_J] = j; st[S2_VGOAL] = vgoal; st[S2_FOUND] = found;
+    }
+}
+
+// ---- launch -----------------------------------------------------------------------------------------------
+static size_t plan2_smem(int n, int cap)
+{
+    size_t b = 0;
+    b += sizeof(double) * 2 * (size_t)cap;
+    b += sizeof(double2) * 256;
+    b += sizeof(uint32_t) * (size_t)((n + 2) & ~1);
+    b += sizeof(uint32_t) * (size_t)(((n + 1 + 31) / 32 + 1) & ~1);
+    b += sizeof(uint16_t) * 2 * (size_t)((n + 4) & ~3);
+    b += sizeof(uint16_t) * (size_t)cap;
+    b += (size_t)cap;
+    b += (size_t)(n + 1);
+    return (b + 15) & ~(size_t)15;
+}
+
+static int plan2_ring_cap(int n)
+{
+    int cap = (n + 1 + 31) & ~31;
+    return cap < 1024 ? cap : 1024;
+}
+
+size_t plan2_scratch_bytes(int nplans, int n)
+{
+    return (size_t)nplans * (n + 1) * (sizeof(double) + sizeof(uint16_t)) + 16;
+}
+
+template <int MODEL, int T>
+static int plan2_launch_t(const Plan2Params &P, int nplans, size_t smem, cudaStream_t st)
+{
+    RRTK_CUDA(cudaFuncSetAttribute(plan_rewire_kernel<MODEL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plan_rewire_kernel<MODEL, T><<<nplans, T, smem, st>>>(P);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
+int plan2_footprint(int n, int threads, int optin, int sm_smem, int *smem_bytes, int *blocks_per_sm)
+{
+    const size_t smem = plan2_smem(n, plan2_ring_cap(n));
+    if (smem + 1024 > (size_t)optin) return RRTK_ERR_CAPACITY;
+    const int T = threads > 0 ? threads : 256;
+    int b = (int)((size_t)sm_smem / (smem + 1024 + 512));
+    if (b > 2048 / T) b = 2048 / T;
+    if (smem_bytes) *smem_bytes = (int)smem;
+    if (blocks_per_sm) *blocks_per_sm = b < 1 ? 1 : b;
+    return RRTK_OK;
+}
+
+int plan2_launch(const rrtk_plan2_cfg &cfg, const uint32_t *d_bits, int W, int H, const rrtk_plan_desc *d_plans, int nplans, int n,
+                 const int16_t *d_samples, const uint8_t *d_heads, int16_t *d_pts, uint8_t *d_head, double *d_cost, double *d_elen,
+                 int32_t *d_parent, int64_t *d_stats, void *d_scratch, int threads, int optin, cudaStream_t st)
+{
+    Plan2Params P;
+    P.bits = d_bits;
+    P.words_per_grid = grid_words(W, H);
+    P.W = W; P.H = H; P.TY = tiles_y(H);
+    P.plans = d_plans;
+    P.n = n;
+    P.star = cfg.star != 0; P.rewire = cfg.star != 0 && cfg.rewire != 0; P.NH = cfg.nheadings;
+    const double lim = ceil(cfg.r_rewire * cfg.r_rewire);
+    P.r2_excl = !P.star ? 0u : (lim >= 1073741824.0 ? 1073741824u : (lim <= 0.0 ? 0u : (uint32_t)lim));
+    P.rho = cfg.rho; P.ds = cfg.ds;
+    P.samples = reinterpret_cast<const short2 *>(d_samples);
+    P.heads = d_heads;
+    P.pts = reinterpret_cast<short2 *>(d_pts);
+    P.head = d_head;
+    P.cost = d_cost; P.elen = d_elen; P.parent = d_parent;
+    P.stats = reinterpret_cast<long long *>(d_stats);
+    uintptr_t s = (reinterpret_cast<uintptr_t>(d_scratch) + 15) & ~(uintptr_t)15;
+    P.gcost = reinterpret_cast<double *>(s);
+    P.queue = reinterpret_cast<uint16_t *>(P.gcost + (size_t)nplans * (n + 1));
+    P.ring_cap = plan2_ring_cap(n);
+    const size_t smem = plan2_smem(n, P.ring_cap);
+    if (smem + 1024 > (size_t)optin) {
+        set_error("plan with n=%d needs %zu bytes of shared memory (limit %d)", n, smem, optin);
+        return RRTK_ERR_CAPACITY;
+    }
+    const int T = threads > 0 ? threads : 256;
+    if (T != 128 && T != 256) {
+        set_error("rrtk_plan2_batch: threads must be 0, 128 or 256");
+        return RRTK_ERR_INVALID;
+    }
+    if (cfg.model == RRTK_MODEL_EUCLID)
+        return T == 128 ? plan2_launch_t<RRTK_MODEL_EUCLID, 128>(P, nplans, smem, st) : plan2_launch_t<RRTK_MODEL_EUCLID, 256>(P, nplans, smem, st);
+    return T == 128 ? plan2_launch_t<RRTK_MODEL_DUBINS, 128>(P, nplans, smem, st) : plan2_launch_t<RRTK_MODEL_DUBINS, 256>(P, nplans, smem, st);
+}
+
+// ---- Dubins primitive, batched (README.md:12 "Dubins Primitive Module") --------------------------------------
+__global__ void dubins_paths_kernel(const int *q, long long nq, int NH, double rho, int *word, double *tpq, double *len)
+{
+    __shared__ double2 tab[256];
+    const double dth = DM_TWO_PI / (double)NH;
+    for (int h = threadIdx.x; h < NH; h += blockDim.x) {
+        double s, c;
+        dm_sincos((double)h * dth, s, c);
+        tab[h] = make_double2(s, c);
+    }
+    __syncthreads();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const int *e = q + 6 * i;
+    DubinsPath w;
+    dubins_shortest(e[3] - e[0], e[4] - e[1], e[2], e[5], NH, rho, tab, w);
+    if (word) word[i] = w.word;
+    if (tpq) { tpq[3 * i] = w.t; tpq[3 * i + 1] = w.p; tpq[3 * i + 2] = w.q; }
+    if (len) len[i] = w.len;
+}
+
+// one warp per query: sampled collision test, and optionally the sampled poses (cap per query)
+__global__ void dubins_walk_kernel(const uint32_t *bits, size_t words_per_grid, int W, int H, const int *q, const int *world,
+                                   long long nq, int NH, double rho, double ds, uint8_t *free_out, int cap, double *xyth, int *count)
+{
+    __shared__ double2 tab[256];
+    const double dth = DM_TWO_PI / (double)NH;
+    for (int h = threadIdx.x; h < NH; h += blockDim.x) {
+        double s, c;
+        dm_sincos((double)h * dth, s, c);
+        tab[h] = make_double2(s, c);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nq) return;
+    const int *e = q + 6 * i;
+    DubinsPath w;
+    dubins_shortest(e[3] - e[0], e[4] - e[1], e[2], e[5], NH, rho, tab, w);
+    if (free_out) {
+        const uint32_t *g = bits + (size_t)(world ? world[i] : 0) * words_per_grid;
+        const bool ok = dubins_free_warp(g, W, H, tiles_y(H), e[0], e[1], e[2], e[3], e[4], NH, rho, ds, w, lane);
+        if (lane == 0) free_out[i] = ok ? 1 : 0;
+    }
+    if (xyth) {
+        const DubinsTrack tr = dubins_track(e[0], e[1], e[2], NH, rho, w);
+        const long long ns = (long long)floor(w.len / ds);
+        double *o = xyth + (size_t)i * cap * 3;
+        for (long long k = lane; k <= ns && k < cap; k += 32) {
+            const Pose a = dubins_point(tr, (double)k * ds);
+            o[3 * k] = a.x; o[3 * k + 1] = a.y; o[3 * k + 2] = a.th;
+        }
+        if (lane == 0) count[i] = (int)(ns + 1);
+    }
+}
+
+int dubins_paths_launch(const int32_t *d_q, int64_t nq, int NH, double rho, int32_t *d_word, double *d_tpq, double *d_len, cudaStream_t st)
+{
+    dubins_paths_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(d_q, nq, NH, rho, d_word, d_tpq, d_len);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
+int dubins_walk_launch(const uint32_t *d_bits, int W, int H, const int32_t *d_q, const int32_t *d_world, int64_t nq, int NH, double rho,
+                       double ds, uint8_t *d_free, int cap, double *d_xyth, int32_t *d_count, cudaStream_t st)
+{
+    dubins_walk_kernel<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(d_bits, grid_words(W, H), W, H, d_q, d_world, nq, NH, rho, ds, d_free,
+                                                              cap, d_xyth, d_count);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
+}  // namespace rrtk

@@ -1,0 +1,196 @@
+"""GPU parity of K8 (csrc/plan_rewire.cu, csrc/dubins.cuh) through the C ABI against oracle/rewire_oracle.c.
+
+The planners tested here (rewire that fires, Dubins RRT / RRT*) do not exist in the reference, so the oracle is a
+specification, not a restatement (parity UNPINNED).  The pinned part: Euclidean model with rewire off must give the
+golden trees the real reference produced."""
+import numpy as np
+import pytest
+
+from oracle import rewire_oracle as R
+from rrtplanner_b200 import _lib, worlds
+from tests.conftest import golden_plans, load_plan
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = _lib.Context()
+    yield c
+    c.close()
+
+
+def _queries(rng, nq, W, H, nh):
+    return np.stack([rng.integers(0, W, nq), rng.integers(0, H, nq), rng.integers(0, nh, nq),
+                     rng.integers(0, W, nq), rng.integers(0, H, nq), rng.integers(0, nh, nq)], axis=1).astype(np.int32)
+
+
+@pytest.mark.parametrize("nh,rho", [(16, 6.0), (32, 2.5), (1, 10.0), (255, 0.75), (8, 40.0)])
+def test_dubins_paths_bit_exact(ctx, nh, rho):
+    rng = np.random.default_rng(nh)
+    q = _queries(rng, 20000, 200, 160, nh)
+    q[:50, 3:5] = q[:50, 0:2]                        # coincident positions
+    q[50:100, 2] = q[50:100, 5]                      # equal headings
+    q[100:150, 3] = q[100:150, 0]                    # vertical displacement
+    word, tpq, ln = ctx.dubins_paths(q, nh, rho)
+    w2, t2, l2 = R.dubins(q, nh, rho)
+    assert np.array_equal(word, w2)
+    assert np.array_equal(tpq.view(np.int64), t2.view(np.int64))
+    assert np.array_equal(ln.view(np.int64), l2.view(np.int64))
+    assert len(set(word.tolist())) >= (4 if nh > 1 else 2)
+
+
+@pytest.mark.parametrize("nh,rho,ds", [(16, 6.0, 1.0), (32, 3.0, 0.5), (12, 12.0, 2.0)])
+def test_dubins_collision_bit_exact(ctx, nh, rho, ds):
+    og = worlds.perlin_occupancygrid(160, 130, seed=4).astype(np.uint8)
+    ctx.set_grids(og[None])
+    rng = np.random.default_rng(1)
+    q = _queries(rng, 6000, 160, 130, nh)
+    got = ctx.dubins_collision(q, nh, rho, ds)
+    want = R.dubins_free(og, q, nh, rho, ds)
+    assert np.array_equal(got, want)
+    assert 0.02 < got.mean() < 0.98
+
+
+def test_dubins_sample_bit_exact(ctx):
+    nh, rho, ds = 16, 5.0, 0.75
+    rng = np.random.default_rng(2)
+    q = _queries(rng, 64, 90, 90, nh)
+    xyth, cnt = ctx.dubins_sample(q, nh, rho, ds, 400)
+    _, _, ln = R.dubins(q, nh, rho)
+    for i in range(q.shape[0]):
+        k = int(np.floor(ln[i] / ds)) + 1
+        assert cnt[i] == k
+        want = R.dubins_points(q[i], nh, rho, np.arange(min(k, 400)) * ds)
+        assert np.array_equal(xyth[i, : min(k, 400)].view(np.int64), want.view(np.int64))
+
+
+def _desc(start, goal):
+    d = np.zeros(1, dtype=_lib.PLAN_DESC)
+    d["start_x"], d["start_y"], d["goal_x"], d["goal_y"] = int(start[0]), int(start[1]), int(goal[0]), int(goal[1])
+    d["reserved"][0, 0], d["reserved"][0, 1] = int(start[2]), int(goal[2])
+    return d
+
+
+def _run(ctx, model, og, n, start, goal, smp, star, rewire, r, nh=16, rho=1.0, ds=1.0):
+    ctx.set_grids((og != 0).astype(np.uint8)[None])
+    cfg = _lib.plan2_cfg(_lib.MODEL_DUBINS if model == "dubins" else _lib.MODEL_EUCLID, star, rewire, r, nh, rho, ds)
+    pts, head, cost, elen, par, st = ctx.plan2(cfg, _desc(start, goal), n, samples=smp[None, :, :2].astype(np.int16),
+                                               heads=smp[None, :, 2].astype(np.uint8))
+    return pts[0], head[0], cost[0], elen[0], par[0], dict(zip(_lib.STAT2_NAMES, (int(v) for v in st[0])))
+
+
+def _compare(got, want, model):
+    pts, head, cost, elen, par, st = got
+    ws = want["stats"]
+    for k in ("j", "vgoal", "found", "accepted", "rewires", "propagated", "ring_members"):
+        assert st[k] == ws[k], (k, st[k], ws[k])
+    assert st["overflow"] == 0
+    top = ws["j"] + (1 if ws["found"] else 0)
+    assert np.array_equal(pts[:top].astype(np.int32), want["pts"][:top])
+    assert np.array_equal(par[:top], want["parent"][:top])
+    assert np.array_equal(cost[:top].view(np.int64), want["cost"][:top].view(np.int64))
+    assert np.array_equal(elen[:top].view(np.int64), want["elen"][:top].view(np.int64))
+    if model == "dubins":
+        assert np.array_equal(head[:top].astype(np.int32), want["head"][:top])
+    assert (pts[top:] == -32768).all() and (par[top:] == -1).all() and np.isinf(cost[top:]).all()
+
+
+@pytest.mark.parametrize("path", [p for p in golden_plans() if "informed" not in p], ids=lambda p: p.split("plan_")[-1][:-4])
+def test_euclid_without_rewire_reproduces_the_reference_trees(ctx, path):
+    g = load_plan(path)
+    n = g["n"]
+    smp = np.concatenate([g["samples"], np.zeros((n, 1), dtype=np.int64)], axis=1)
+    pts, head, cost, elen, par, st = _run(ctx, "euclid", g["og"], n, [*g["xstart"], 0], [*g["xgoal"], 0], smp,
+                                          g["kind"] == "star", False, float(g["r_rewire"]))
+    found = bool(st["found"])
+    top = st["j"] + (1 if found else 0)
+    assert int(g["vgoal"]) == (st["vgoal"] if found else 0)
+    assert np.array_equal(pts[:top].astype(np.int64), g["points"][:top])
+    assert np.array_equal(cost[:top].view(np.int64), g["vcosts"][:top].view(np.int64))
+    assert np.array_equal(par[1:top].astype(np.int64), g["parents"][1:top])
+
+
+CASES = [
+    # model, W, H, n, r, star, rewire, nh, rho, ds, world seed
+    ("euclid", 96, 96, 600, 20.0, True, True, 1, 1.0, 1.0, 7),
+    ("euclid", 128, 100, 1500, 30.0, True, True, 1, 1.0, 1.0, 8),
+    ("euclid", 256, 256, 3000, 50.0, True, True, 1, 1.0, 1.0, 9),
+    ("dubins", 96, 96, 500, 20.0, True, True, 16, 3.0, 1.0, 7),
+    ("dubins", 96, 96, 500, 20.0, True, False, 16, 3.0, 1.0, 7),
+    ("dubins", 96, 96, 300, 0.0, False, False, 16, 3.0, 1.0, 7),
+    ("dubins", 128, 160, 1200, 30.0, True, True, 32, 5.0, 0.5, 10),
+    ("dubins", 256, 256, 2500, 50.0, True, True, 16, 6.0, 1.0, 11),
+    ("dubins", 64, 64, 400, 200.0, True, True, 8, 2.0, 1.0, 12),      # radius covers the grid: every vertex is a member
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_n{c[3]}_r{c[4]:g}_s{int(c[5])}{int(c[6])}_h{c[7]}")
+def test_plans_bit_exact_against_the_specification(ctx, case):
+    model, W, H, n, r, star, rewire, nh, rho, ds, seed = case
+    og = worlds.perlin_occupancygrid(W, H, seed=seed).astype(np.uint8)
+    free = np.argwhere(og == 0)
+    rng = np.random.default_rng(seed)
+    smp = np.concatenate([free[rng.integers(0, len(free), n)], rng.integers(0, nh, (n, 1))], axis=1)
+    smp[5] = smp[2]                                                      # a duplicate sample
+    start = [*free[rng.integers(0, len(free))], int(rng.integers(0, nh))]
+    goal = [*free[rng.integers(0, len(free))], int(rng.integers(0, nh))]
+    smp[9, :2] = start[:2]                                               # a sample on the start cell
+    want = R.plan(model, og, n, start, goal, smp, star=star, rewire=rewire, r_rewire=r, nh=nh, rho=rho, ds=ds)
+    got = _run(ctx, model, og, n, start, goal, smp, star, rewire, r, nh, rho, ds)
+    _compare(got, want, model)
+    if rewire:
+        assert want["stats"]["rewires"] > 0
+
+
+def test_full_size_dubins_rrtstar_plan(ctx):
+    """BASELINE cfg5 shape: 512 x 512 world, n = 5000, r = 50."""
+    og = worlds.perlin_occupancygrid(512, 512, seed=1000).astype(np.uint8)
+    free = np.argwhere(og == 0)
+    rng = np.random.default_rng(0)
+    n, nh = 5000, 16
+    smp = np.concatenate([free[rng.integers(0, len(free), n)], rng.integers(0, nh, (n, 1))], axis=1)
+    start, goal = [*free[100], 2], [*free[-100], 9]
+    want = R.plan("dubins", og, n, start, goal, smp, star=True, rewire=True, r_rewire=50.0, nh=nh, rho=6.0, ds=1.0)
+    got = _run(ctx, "dubins", og, n, start, goal, smp, True, True, 50.0, nh, 6.0, 1.0)
+    _compare(got, want, "dubins")
+    assert want["stats"]["j"] > 1000
+
+
+def test_several_plans_in_one_launch(ctx):
+    W = H = 128
+    n, nh, nplans = 400, 16, 6
+    ogs = np.stack([worlds.perlin_occupancygrid(W, H, seed=20 + w).astype(np.uint8) for w in range(nplans)])
+    ctx.set_grids(ogs)
+    desc = np.zeros(nplans, dtype=_lib.PLAN_DESC)
+    smp = np.zeros((nplans, n, 3), dtype=np.int64)
+    starts, goals = [], []
+    for p in range(nplans):
+        free = np.argwhere(ogs[p] == 0)
+        rng = np.random.default_rng(100 + p)
+        smp[p] = np.concatenate([free[rng.integers(0, len(free), n)], rng.integers(0, nh, (n, 1))], axis=1)
+        s, g = [*free[3], p % nh], [*free[-3], (3 * p) % nh]
+        starts.append(s); goals.append(g)
+        desc[p]["world"] = p
+        desc[p]["start_x"], desc[p]["start_y"], desc[p]["goal_x"], desc[p]["goal_y"] = s[0], s[1], g[0], g[1]
+        desc[p]["reserved"][0], desc[p]["reserved"][1] = s[2], g[2]
+    cfg = _lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 25.0, nh, 4.0, 1.0)
+    pts, head, cost, elen, par, st = ctx.plan2(cfg, desc, n, samples=smp[:, :, :2].astype(np.int16), heads=smp[:, :, 2].astype(np.uint8))
+    for p in range(nplans):
+        want = R.plan("dubins", ogs[p], n, starts[p], goals[p], smp[p], star=True, rewire=True, r_rewire=25.0, nh=nh, rho=4.0, ds=1.0)
+        _compare((pts[p], head[p], cost[p], elen[p], par[p], dict(zip(_lib.STAT2_NAMES, (int(v) for v in st[p])))), want, "dubins")
+
+
+def test_bad_arguments_raise(ctx):
+    og = np.zeros((32, 32), dtype=np.uint8)
+    ctx.set_grids(og[None])
+    smp = np.zeros((1, 10, 2), dtype=np.int16)
+    with pytest.raises(ValueError):
+        ctx.plan2(_lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 16, 0.0, 1.0), _desc([1, 1, 0], [5, 5, 0]), 10, samples=smp)
+    with pytest.raises(ValueError):
+        ctx.plan2(_lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 16, 2.0, 1.0), _desc([1, 1, 16], [5, 5, 0]), 10, samples=smp)
+    with pytest.raises(ValueError):
+        ctx.plan2(_lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 4, 2.0, 1.0), _desc([1, 1, 0], [5, 5, 0]), 10, samples=smp,
+                  heads=np.full((1, 10), 7, dtype=np.uint8))
+    with pytest.raises(ValueError):
+        ctx.dubins_collision(np.array([[0, 0, 0, 40, 3, 0]]), 16, 2.0, 1.0)
