@@ -275,6 +275,86 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
 
 
 # ------------------------------------------------------------------------------------------------
+# cfg5: Dubins-vehicle RRT* (BASELINE.json configs[4]); no reference code exists for it -- parity UNPINNED
+# ------------------------------------------------------------------------------------------------
+DUB_PLANS, DUB_NH, DUB_RHO, DUB_DS = 1024, 16, 6.0, 1.0
+
+
+def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, threads: int = 0):
+    """1024 Dubins RRT* plans (rewire on) on independent 512x512 worlds, n=5000, r=50, 16 headings, rho=6, ds=1;
+    sample cells from the device PCG64 stream of plan p, headings = default_rng(7000+p).integers(0, 16, n) (host).
+    Also times the same shape with the Euclidean model + rewire (the RRT* the reference's rewire block intends)."""
+    import torch
+
+    from rrtplanner_b200 import _lib, batch, worlds
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+    out = {"workload": "cfg5: %d Dubins RRT* plans (choose-parent + rewire), independent %dx%d worlds, n=%d, r_rewire=%g, "
+                       "%d headings, rho=%g cells, ds=%g" % (plans, W, H, N_ITER, R_REWIRE, DUB_NH, DUB_RHO, DUB_DS),
+           "parity": "UNPINNED: the reference ships no Dubins code; bit-exact against this project's specification oracle/rewire_oracle.c"}
+    keep = {}
+    for model in ("dubins", "euclid"):
+        db = batch.DeviceBatch2(model, W, H, N_ITER, r_rewire=R_REWIRE, nheadings=DUB_NH, rho=DUB_RHO, ds=DUB_DS, device=local,
+                                threads=threads)
+        db.gen_worlds([worlds.world_seed(p) for p in range(plans)])
+        pair_db = batch.DeviceBatch("star", W, H, 8, device=local)
+        pair_db.bits, pair_db.rowcum = db.bits, db.rowcum
+        pair_db.set_plans(batch.make_desc(np.arange(plans), np.zeros((plans, 2)), np.zeros((plans, 2))))
+        pair_db.seed_samples(2000 + np.arange(plans))
+        draws = pair_db.samples.cpu().numpy().astype(np.int64)
+        starts = draws[:, 0]
+        differs = (draws[:, 1:] != starts[:, None]).any(axis=2)
+        goals = draws[np.arange(plans), 1 + differs.argmax(axis=1)]
+        hs = np.random.default_rng(6000).integers(0, DUB_NH, size=(plans, 2))
+        db.set_plans(batch.make_desc2(np.arange(plans), np.concatenate([starts, hs[:, :1]], axis=1),
+                                      np.concatenate([goals, hs[:, 1:]], axis=1)))
+        db.seed_samples(np.arange(plans))
+        if model == "dubins":
+            db.seed_heads(7000 + np.arange(plans))
+        for _ in range(2):
+            db.run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(2, min(steps, 5))
+        e0.record(stream)
+        for _ in range(reps):
+            db.run()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / reps
+        st = db.out["stats"].cpu().numpy()
+        smem, blocks = db.footprint()
+        rec = {"plans_per_s": plans / (ms / 1e3), "ms_per_launch": ms, "gpu_launches": reps, "mean_vertices": float(st[:, 0].mean()),
+               "goal_found_frac": float(st[:, 2].mean()), "rewires_per_plan": float(st[:, 5].mean()),
+               "edge_length_evals_per_s": float(st[:, 8].sum()) / (ms / 1e3), "edge_tests_per_s": float(st[:, 3].sum()) / (ms / 1e3),
+               "smem_bytes_per_block": smem, "blocks_per_sm": blocks, "overflow": int(st[:, 9].sum()),
+               "kernel": "rrtk::plan_rewire_kernel<%s, T=%d>" % (model.upper(), threads or 256)}
+        out["dubins_rrtstar" if model == "dubins" else "euclid_rrtstar_with_rewire"] = rec
+        keep[model] = (db, starts, goals, hs)
+    if cpu:
+        from oracle import rewire_oracle as O2                # checker + CPU baseline only
+        for model, key in (("dubins", "dubins_rrtstar"), ("euclid", "euclid_rrtstar_with_rewire")):
+            db, starts, goals, hs = keep[model]
+            res = db.download()
+            ok, dt, m = True, 0.0, 4
+            for p in range(m):
+                og = db.og[p].cpu().numpy()
+                smp = db.samples[p].cpu().numpy().astype(np.int64)
+                hd = db.heads[p].cpu().numpy().astype(np.int64) if model == "dubins" else np.zeros(N_ITER, dtype=np.int64)
+                t0 = time.perf_counter()
+                want = O2.plan(model, og, N_ITER, [*starts[p], hs[p, 0]], [*goals[p], hs[p, 1]], np.concatenate([smp, hd[:, None]], axis=1),
+                               star=True, rewire=True, r_rewire=R_REWIRE, nh=DUB_NH, rho=DUB_RHO, ds=DUB_DS)
+                dt += time.perf_counter() - t0
+                top = want["stats"]["j"] + want["stats"]["found"]
+                ok = ok and np.array_equal(res.parent[p, :top], want["parent"][:top]) and \
+                    np.array_equal(res.cost[p, :top].view(np.int64), want["cost"][:top].view(np.int64))
+            out[key]["matches_oracle"] = bool(ok)
+            out[key]["cpu_baseline"] = {"value": m / dt, "unit": "plans/s", "cores": 1, "kind": "port",
+                                        "sample": "plans 0..%d of the workload through oracle/rewire_oracle.c (compiled C), %.2f s" % (m - 1, dt)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def gpu_arm(args):
@@ -475,6 +555,8 @@ def gpu_arm(args):
         line["cpu_baseline"] = cpu_baseline_single(args.cpu_plans)
     if world == 1 and not args.no_collision:
         line["collision_microbench"] = collision_microbench(local, args.steps, args.warmup, not args.no_cpu, sm_mhz, peaks)
+    if world == 1 and not args.no_dubins:
+        line["dubins_bench"] = dubins_bench(local, args.steps, not args.no_cpu)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -495,6 +577,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-collision", action="store_true", help="skip the cfg2 collision microbenchmark")
     ap.add_argument("--collision-only", action="store_true", help="run only the cfg2 collision microbenchmark (profiling aid)")
+    ap.add_argument("--no-dubins", action="store_true", help="skip the cfg5 Dubins RRT* leg")
+    ap.add_argument("--dubins-only", action="store_true", help="run only the cfg5 Dubins RRT* leg (profiling aid)")
+    ap.add_argument("--dubins-plans", type=int, default=DUB_PLANS)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
@@ -502,6 +587,10 @@ def main():
         import torch
         torch.cuda.set_device(0)
         print(json.dumps(collision_microbench(0, args.steps, args.warmup, not args.no_cpu, 1965.0, {})), flush=True)
+    elif args.dubins_only:
+        import torch
+        torch.cuda.set_device(0)
+        print(json.dumps(dubins_bench(0, args.steps, not args.no_cpu, args.dubins_plans, args.threads)), flush=True)
     elif args.impl == "reference":
         reference_arm(args)
     else:

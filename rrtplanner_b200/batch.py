@@ -316,3 +316,82 @@ class DeviceBatch:
         self.torch.cuda.synchronize(self.dev)
         return BatchResult(o["pts"].cpu().numpy(), o["cost"].cpu().numpy(), o["parent"].cpu().numpy(), o["stats"].cpu().numpy(),
                            None if o["ell"] is None else o["ell"].cpu().numpy())
+
+
+@dataclass
+class Batch2Result:
+    """Host copies of K8 trees (rrtk_plan2_batch layout)."""
+    pts: np.ndarray        # (P, n+1, 2) int16
+    head: np.ndarray       # (P, n+1) uint8, 255 in unfilled rows
+    cost: np.ndarray       # (P, n+1) float64
+    elen: np.ndarray       # (P, n+1) float64 length of the edge from the parent
+    parent: np.ndarray     # (P, n+1) int32
+    stats: np.ndarray      # (P, STAT_COUNT) int64, slots named by _lib.STAT2_NAMES
+
+    def stat(self, name: str) -> np.ndarray:
+        return self.stats[:, _lib.STAT2_NAMES.index(name)]
+
+
+def make_desc2(world_ids, starts, goals) -> np.ndarray:
+    """Descriptors for K8: starts / goals are (P, 3) configurations (x, y, heading index)."""
+    starts = np.asarray(starts).reshape(-1, 3)
+    goals = np.asarray(goals).reshape(-1, 3)
+    d = make_desc(world_ids, starts[:, :2], goals[:, :2])
+    d["reserved"][:, 0], d["reserved"][:, 1] = starts[:, 2], goals[:, 2]
+    return d
+
+
+class DeviceBatch2(DeviceBatch):
+    """HBM-resident batch of K8 plans (RRT* with a firing rewire, Dubins RRT / RRT*; include/rrtk.h rrtk_plan2_batch)."""
+
+    def __init__(self, model, W: int, H: int, n: int, r_rewire=0.0, star=True, rewire=True, nheadings=16, rho=6.0, ds=1.0,
+                 device=None, threads: int = 0):
+        super().__init__("star" if star else "standard", W, H, n, r_rewire=r_rewire, device=device, threads=threads)
+        m = {"euclid": _lib.MODEL_EUCLID, "dubins": _lib.MODEL_DUBINS}[model] if isinstance(model, str) else int(model)
+        self.cfg = _lib.plan2_cfg(m, star, rewire, r_rewire, nheadings if m == _lib.MODEL_DUBINS else 1, rho, ds)
+        self.nheadings = int(self.cfg["nheadings"][0])
+        self.heads = None
+        self.scratch = None
+
+    def set_plans(self, desc: np.ndarray):
+        t = self.torch
+        desc = np.ascontiguousarray(desc, dtype=_lib.PLAN_DESC)
+        self.nplans = desc.shape[0]
+        self.desc = t.from_numpy(desc.view(np.uint8).reshape(self.nplans, 64)).to(self.dev)
+        P, n = self.nplans, self.n
+        self.out = dict(pts=self._empty((P, n + 1, 2), t.int16), head=self._empty((P, n + 1), t.uint8),
+                        cost=self._empty((P, n + 1), t.float64), elen=self._empty((P, n + 1), t.float64),
+                        parent=self._empty((P, n + 1), t.int32), stats=self._empty((P, _lib.STAT_COUNT), t.int64))
+        self.scratch = self._empty((int(self.L.rrtk_plan2_scratch_bytes(P, n)),), t.uint8)
+        return self
+
+    def set_heads_host(self, heads: np.ndarray):
+        h = np.ascontiguousarray(heads, dtype=np.uint8)
+        assert h.shape == (self.nplans, self.n) and (h.size == 0 or h.max() < self.nheadings)
+        self.heads = self.torch.from_numpy(h).to(self.dev)
+        return self
+
+    def seed_heads(self, seeds: Sequence[int]):
+        """Heading stream of plan p = default_rng(seeds[p]).integers(0, nheadings, n), drawn on the host."""
+        return self.set_heads_host(np.stack([np.random.default_rng(int(s)).integers(0, self.nheadings, self.n) for s in seeds]))
+
+    def run(self):
+        o = self.out
+        with self.torch.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_plan2_batch(_lib.ptr(self.cfg), self._p(self.bits), self.W, self.H, self._p(self.desc), self.nplans,
+                                               self.n, self._p(self.samples), self._p(self.heads), self._p(o["pts"]), self._p(o["head"]),
+                                               self._p(o["cost"]), self._p(o["elen"]), self._p(o["parent"]), self._p(o["stats"]),
+                                               self._p(self.scratch), self.threads, self._stream()), "plan2_batch")
+        return self
+
+    def footprint(self):
+        import ctypes as C
+        smem, blocks = C.c_int(0), C.c_int(0)
+        with self.torch.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_plan2_footprint(self.n, self.threads, C.byref(smem), C.byref(blocks)), "plan2_footprint")
+        return smem.value, blocks.value
+
+    def download(self) -> Batch2Result:
+        o = self.out
+        self.torch.cuda.synchronize(self.dev)
+        return Batch2Result(*(o[k].cpu().numpy() for k in ("pts", "head", "cost", "elen", "parent", "stats")))

@@ -277,19 +277,37 @@ class RRTStandard(RRT):
 
 
 class RRTStar(RRT):
-    """RRT* (rrt.py:453-556)."""
+    """RRT* (rrt.py:453-556).
+
+    ``rewire`` (not in the reference, keyword-only, default = the reference's behaviour):
+    ``"reference"`` keeps the reference's rewire block, whose predicate ``cost(vn -> xnew) < vcosts[vn]``
+    (rrt.py:532-536) can never hold, i.e. no rewiring; ``"rrtstar"`` rewires with the textbook predicate
+    ``vcosts[vnew] + |xnew - xn| < vcosts[vn]`` and keeps the costs of the rewired subtree consistent
+    (kernel K8, csrc/plan_rewire.cu; specification oracle/rewire_oracle.c -- there is no reference
+    behaviour to match for this mode)."""
 
     _KIND = _lib.KIND_STAR
 
-    def __init__(self, og: np.ndarray, n: int, r_rewire: float, costfn: callable = None, pbar=True, seed: int = 0):
+    def __init__(self, og: np.ndarray, n: int, r_rewire: float, costfn: callable = None, pbar=True, seed: int = 0, *,
+                 rewire: str = "reference"):
         super().__init__(og, n, costfn=costfn, pbar=pbar, seed=seed)
         self.r_rewire = r_rewire
+        if rewire not in ("reference", "rrtstar"):
+            raise ValueError("rewire must be 'reference' or 'rrtstar'")
+        self.rewire = rewire
 
     def plan(self, xstart: np.ndarray, xgoal: np.ndarray):
         shape = np.asarray(self.og).shape
         xstart, xgoal = _as_point(xstart, shape, "xstart"), _as_point(xgoal, shape, "xgoal")
         ctx = self._device()
         samples = self._draw_samples(self.n).astype(np.int16)[None]
+        if self.rewire == "rrtstar":
+            cfg = _lib.plan2_cfg(_lib.MODEL_EUCLID, True, True, self.r_rewire)
+            pts, _, cost, _, parent, stats = ctx.plan2(cfg, self._desc(xstart, xgoal), self.n, samples=samples)
+            self._tick()
+            T, gv = self._finish(pts[0], cost[0], parent[0], stats[0])
+            self.last_stats = dict(zip(_lib.STAT2_NAMES, (int(v) for v in stats[0])))
+            return T, gv
         pts, cost, parent, stats, _ = ctx.plan(self._KIND, self._desc(xstart, xgoal), self.n,
                                                r_rewire=self.r_rewire, samples=samples)
         self._tick()
