@@ -54,36 +54,38 @@ enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROP
 /* ---- deterministic elementary functions (part of the specification) ------------------------------ */
 #define DM_PI 3.14159265358979323846
 #define DM_TWO_PI 6.28318530717958647692
+#define DM_INV_TWO_PI 0.15915494309189533577
 #define DM_HALF_PI 1.57079632679489661923
 #define DM_QUARTER_PI 0.78539816339744830962
 #define DM_TWO_OVER_PI 0.63661977236758134308
 #define DM_TAN_PI_8 0.41421356237309504880
-#define DM_ATAN_TERMS 22
 
-/* atan(z) for |z| <= tan(pi/8): z * sum_{k<22} (-1)^k z^(2k) / (2k+1), Horner in z^2 */
+/* atan(z) for |z| <= tan(pi/8): z * sum_{k<16} (-1)^k z^(2k) / (2k+1)  (truncation < 2e-14), evaluated as
+ * E(s^2) + s * O(s^2) with s = z^2, both halves by Horner: E holds the even k, O the odd k */
 static double dm_atan_small(double z)
 {
-    const double s = z * z;
-    double p = 1.0 / (2 * (DM_ATAN_TERMS - 1) + 1);
-    if ((DM_ATAN_TERMS - 1) & 1) p = -p;
-    for (int k = DM_ATAN_TERMS - 2; k >= 0; --k) {
-        double c = 1.0 / (double)(2 * k + 1);
-        if (k & 1) c = -c;
-        p = p * s + c;
-    }
-    return z * p;
+    const double s = z * z, s2 = s * s;
+    double e = 1.0 / 29.0, o = -1.0 / 31.0;
+    e = e * s2 + 1.0 / 25.0;  o = o * s2 - 1.0 / 27.0;
+    e = e * s2 + 1.0 / 21.0;  o = o * s2 - 1.0 / 23.0;
+    e = e * s2 + 1.0 / 17.0;  o = o * s2 - 1.0 / 19.0;
+    e = e * s2 + 1.0 / 13.0;  o = o * s2 - 1.0 / 15.0;
+    e = e * s2 + 1.0 / 9.0;   o = o * s2 - 1.0 / 11.0;
+    e = e * s2 + 1.0 / 5.0;   o = o * s2 - 1.0 / 7.0;
+    e = e * s2 + 1.0;         o = o * s2 - 1.0 / 3.0;
+    return z * (e + s * o);
 }
 
+/* one division: atan(num/den) = pi/4 + atan((num - den) / (num + den)) above tan(pi/8) */
 double dm_atan2(double y, double x)
 {
     if (x == 0.0 && y == 0.0) return 0.0;
     const double ax = fabs(x), ay = fabs(y);
     const int swap = ay > ax;
     const double num = swap ? ax : ay, den = swap ? ay : ax;
-    const double a = num / den;
     double r;
-    if (a > DM_TAN_PI_8) r = DM_QUARTER_PI + dm_atan_small((a - 1.0) / (a + 1.0));
-    else r = dm_atan_small(a);
+    if (num > DM_TAN_PI_8 * den) r = DM_QUARTER_PI + dm_atan_small((num - den) / (num + den));
+    else r = dm_atan_small(num / den);
     if (swap) r = DM_HALF_PI - r;
     if (x < 0.0) r = DM_PI - r;
     if (y < 0.0) r = -r;
@@ -125,7 +127,13 @@ void dm_sincos(double a, double *sn, double *cs)
     }
 }
 
-static double dm_mod2pi(double x) { return x - DM_TWO_PI * floor(x / DM_TWO_PI); }
+/* angle into [0, 2 pi); results within 1e-9 of a full turn (rounding of an exact 0) snap to 0 so that no path
+ * carries a spurious extra circle */
+static double dm_mod2pi(double x)
+{
+    const double r = x - DM_TWO_PI * floor(x * DM_INV_TWO_PI);
+    return (r < 0.0 || r > DM_TWO_PI - 1e-9) ? 0.0 : r;
+}
 /* acos through atan2: acos(v) = atan2(sqrt(1 - v^2), v), |v| <= 1 */
 static double dm_acos(double v) { return dm_atan2(sqrt(1.0 - v * v), v); }
 
@@ -144,10 +152,10 @@ static void dubins_setup(int dx, int dy, int h0, int h1, int NH, double rho, dub
     dm_sincos(th1, &s1, &c1);
     dm_sincos((double)(((h0 - h1) % NH + NH) % NH) * dth, &sd, &cd);
     const double D = sqrt((double)((int64_t)dx * dx + (int64_t)dy * dy));
-    g->d = D / rho;
+    g->d = D * (1.0 / rho);
     g->dd = g->d * g->d;
     double cphi = 1.0, sphi = 0.0;
-    if (D > 0.0) { cphi = (double)dx / D; sphi = (double)dy / D; }
+    if (D > 0.0) { const double inv = 1.0 / D; cphi = (double)dx * inv; sphi = (double)dy * inv; }
     const double phi = dm_atan2((double)dy, (double)dx);
     g->alpha = dm_mod2pi(th0 - phi);
     g->beta = dm_mod2pi(th1 - phi);
@@ -190,17 +198,17 @@ static int dubins_word(const dubins_in_t *g, int w, double *ot, double *op, doub
             t = dm_mod2pi(alpha - tmp); q = dm_mod2pi(beta - tmp);
             break;
         case 4: /* RLR */
-            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
+            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sa - sb)) * 0.125;
             if (fabs(tmp) > 1.0) return 0;
             p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
-            t = dm_mod2pi(alpha - dm_atan2(ca - cb, d - sa + sb) + p / 2.0);
+            t = dm_mod2pi(alpha - dm_atan2(ca - cb, d - sa + sb) + p * 0.5);       /* the angle RSR uses */
             q = dm_mod2pi(alpha - beta - t + p);
             break;
         default: /* LRL */
-            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sb - sa)) / 8.0;
+            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sb - sa)) * 0.125;
             if (fabs(tmp) > 1.0) return 0;
             p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
-            t = dm_mod2pi(p / 2.0 - alpha - dm_atan2(ca - cb, d + sa - sb));
+            t = dm_mod2pi(p * 0.5 - alpha + dm_atan2(cb - ca, d + sa - sb));       /* the angle LSL uses */
             q = dm_mod2pi(dm_mod2pi(beta) - alpha - t + p);
             break;
     }
@@ -257,7 +265,7 @@ static void advance(double *x, double *y, double *th, int kind, double len, doub
 void orc2_dubins_point(int x0, int y0, int h0, int NH, double rho, const dubins_t *w, double s, double *ox, double *oy, double *oth)
 {
     double x = (double)x0, y = (double)y0, th = (double)h0 * (DM_TWO_PI / (double)NH);
-    const double u = s / rho;
+    const double u = s * (1.0 / rho);
     const int *k = kSeg[w->word];
     if (u < w->t) {
         advance(&x, &y, &th, k[0], u, rho);

@@ -5,28 +5,33 @@
 // library is compiled with --fmad=false so nothing is contracted.  atan2 / sin / cos are the specification's own
 // polynomials (dm_*), not CUDA's libm, because last-ulp differences would change strict cost comparisons and hence trees.
 #pragma once
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace rrtk {
 
 #define DM_PI 3.14159265358979323846
 #define DM_TWO_PI 6.28318530717958647692
+#define DM_INV_TWO_PI 0.15915494309189533577
 #define DM_HALF_PI 1.57079632679489661923
 #define DM_QUARTER_PI 0.78539816339744830962
 #define DM_TWO_OVER_PI 0.63661977236758134308
 #define DM_TAN_PI_8 0.41421356237309504880
 
-// atan(z), |z| <= tan(pi/8): z * sum_{k<22} (-1)^k z^(2k) / (2k+1), Horner in z^2
+// atan(z), |z| <= tan(pi/8): z * sum_{k<16} (-1)^k z^(2k) / (2k+1) as E(s^2) + s * O(s^2), s = z^2 (two Horner chains)
 __device__ __forceinline__ double dm_atan_small(double z)
 {
-    const double s = z * z;
-    double p = -1.0 / 43.0;
-#pragma unroll
-    for (int k = 20; k >= 0; --k) {
-        const double c = (k & 1) ? -1.0 / (double)(2 * k + 1) : 1.0 / (double)(2 * k + 1);
-        p = p * s + c;
-    }
-    return z * p;
+    const double s = z * z, s2 = s * s;
+    double e = 1.0 / 29.0, o = -1.0 / 31.0;
+    e = e * s2 + 1.0 / 25.0;  o = o * s2 - 1.0 / 27.0;
+    e = e * s2 + 1.0 / 21.0;  o = o * s2 - 1.0 / 23.0;
+    e = e * s2 + 1.0 / 17.0;  o = o * s2 - 1.0 / 19.0;
+    e = e * s2 + 1.0 / 13.0;  o = o * s2 - 1.0 / 15.0;
+    e = e * s2 + 1.0 / 9.0;   o = o * s2 - 1.0 / 11.0;
+    e = e * s2 + 1.0 / 5.0;   o = o * s2 - 1.0 / 7.0;
+    e = e * s2 + 1.0;         o = o * s2 - 1.0 / 3.0;
+    return z * (e + s * o);
 }
 
 __device__ __noinline__ double dm_atan2(double y, double x)
@@ -35,10 +40,10 @@ __device__ __noinline__ double dm_atan2(double y, double x)
     const double ax = fabs(x), ay = fabs(y);
     const bool swap = ay > ax;
     const double num = swap ? ax : ay, den = swap ? ay : ax;
-    const double a = num / den;
-    double r;
-    if (a > DM_TAN_PI_8) r = DM_QUARTER_PI + dm_atan_small((a - 1.0) / (a + 1.0));
-    else r = dm_atan_small(a);
+    const bool hi = num > DM_TAN_PI_8 * den;
+    const double zn = hi ? num - den : num, zd = hi ? num + den : den;
+    double r = dm_atan_small(zn / zd);
+    if (hi) r = DM_QUARTER_PI + r;
     if (swap) r = DM_HALF_PI - r;
     if (x < 0.0) r = DM_PI - r;
     if (y < 0.0) r = -r;
@@ -78,7 +83,12 @@ __device__ __noinline__ void dm_sincos(double a, double &sn, double &cs)
     }
 }
 
-__device__ __forceinline__ double dm_mod2pi(double x) { return x - DM_TWO_PI * floor(x / DM_TWO_PI); }
+// angle into [0, 2 pi); a result within 1e-9 of a full turn (an exact 0 that rounded below) snaps to 0
+__device__ __forceinline__ double dm_mod2pi(double x)
+{
+    const double r = x - DM_TWO_PI * floor(x * DM_INV_TWO_PI);
+    return (r < 0.0 || r > DM_TWO_PI - 1e-9) ? 0.0 : r;
+}
 __device__ __forceinline__ double dm_acos(double v) { return dm_atan2(sqrt(1.0 - v * v), v); }
 
 struct DubinsPath {
@@ -97,10 +107,10 @@ __device__ __forceinline__ void dubins_setup(int dx, int dy, int h0, int h1, int
     int hd = (h0 - h1) % NH;
     if (hd < 0) hd += NH;
     const double D = sqrt((double)((long long)dx * dx + (long long)dy * dy));
-    g.d = D / rho;
+    g.d = D * (1.0 / rho);
     g.dd = g.d * g.d;
     double cphi = 1.0, sphi = 0.0;
-    if (D > 0.0) { cphi = (double)dx / D; sphi = (double)dy / D; }
+    if (D > 0.0) { const double inv = 1.0 / D; cphi = (double)dx * inv; sphi = (double)dy * inv; }
     const double phi = dm_atan2((double)dy, (double)dx);
     g.alpha = dm_mod2pi(th0 - phi);
     g.beta = dm_mod2pi(th1 - phi);
@@ -142,35 +152,89 @@ __device__ __forceinline__ bool dubins_word(const DubinsIn &g, int w, double &t,
             t = dm_mod2pi(alpha - tmp); q = dm_mod2pi(beta - tmp);
             return true;
         case 4:
-            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sa - sb)) / 8.0;
+            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sa - sb)) * 0.125;
             if (fabs(tmp) > 1.0) return false;
             p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
-            t = dm_mod2pi(alpha - dm_atan2(ca - cb, d - sa + sb) + p / 2.0);
+            t = dm_mod2pi(alpha - dm_atan2(ca - cb, d - sa + sb) + p * 0.5);
             q = dm_mod2pi(alpha - beta - t + p);
             return true;
         default:
-            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sb - sa)) / 8.0;
+            tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sb - sa)) * 0.125;
             if (fabs(tmp) > 1.0) return false;
             p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
-            t = dm_mod2pi(p / 2.0 - alpha - dm_atan2(ca - cb, d + sa - sb));
+            t = dm_mod2pi(p * 0.5 - alpha + dm_atan2(cb - ca, d + sa - sb));
             q = dm_mod2pi(dm_mod2pi(beta) - alpha - t + p);
             return true;
     }
 }
 
-// shortest word from (0, 0, h0) to (dx, dy, h1); ties to the first word in the order above
+// shortest word from (0, 0, h0) to (dx, dy, h1); ties to the first word in the order above.  Same operations per word as
+// dubins_word (so the same bits); the two angles that LSL / LRL and RSR / RLR share are evaluated once.
 __device__ __noinline__ void dubins_shortest(int dx, int dy, int h0, int h1, int NH, double rho, const double2 *tab, DubinsPath &out)
 {
     DubinsIn g;
     dubins_setup(dx, dy, h0, h1, NH, rho, tab, g);
+    const double d = g.d, dd = g.dd, alpha = g.alpha, beta = g.beta;
+    const double sa = g.sa, ca = g.ca, sb = g.sb, cb = g.cb, cab = g.cab;
     out.word = -1; out.len = CUDART_INF; out.t = out.p = out.q = 0.0;
-#pragma unroll 1
-    for (int w = 0; w < 6; ++w) {
-        double t, p, q;
-        if (!dubins_word(g, w, t, p, q)) continue;
-        const double len = ((t + p) + q) * rho;
-        if (len < out.len) { out.len = len; out.word = w; out.t = t; out.p = p; out.q = q; }
+    const double a_lsl = dm_atan2(cb - ca, d + sa - sb);
+    const double a_rsr = dm_atan2(ca - cb, d - sa + sb);
+    double t, p, q, tmp, psq, len;
+#define RRTK_DUBINS_TAKE(W)                                                                  \
+    len = ((t + p) + q) * rho;                                                              \
+    if (len < out.len) { out.len = len; out.word = (W); out.t = t; out.p = p; out.q = q; }
+    psq = 2.0 + dd - 2.0 * cab + 2.0 * d * (sa - sb);
+    if (!(psq < 0.0)) {
+        t = dm_mod2pi(a_lsl - alpha); p = sqrt(psq); q = dm_mod2pi(beta - a_lsl);
+        RRTK_DUBINS_TAKE(0)
     }
+    psq = 2.0 + dd - 2.0 * cab + 2.0 * d * (sb - sa);
+    if (!(psq < 0.0)) {
+        t = dm_mod2pi(alpha - a_rsr); p = sqrt(psq); q = dm_mod2pi(a_rsr - beta);
+        RRTK_DUBINS_TAKE(1)
+    }
+    psq = dd - 2.0 + 2.0 * cab + 2.0 * d * (sa + sb);
+    if (!(psq < 0.0)) {
+        p = sqrt(psq);
+        tmp = dm_atan2(-ca - cb, d + sa + sb) - dm_atan2(-2.0, p);
+        t = dm_mod2pi(tmp - alpha); q = dm_mod2pi(tmp - dm_mod2pi(beta));
+        RRTK_DUBINS_TAKE(2)
+    }
+    psq = dd - 2.0 + 2.0 * cab - 2.0 * d * (sa + sb);
+    if (!(psq < 0.0)) {
+        p = sqrt(psq);
+        tmp = dm_atan2(ca + cb, d - sa - sb) - dm_atan2(2.0, p);
+        t = dm_mod2pi(alpha - tmp); q = dm_mod2pi(beta - tmp);
+        RRTK_DUBINS_TAKE(3)
+    }
+    tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sa - sb)) * 0.125;
+    if (!(fabs(tmp) > 1.0)) {
+        p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
+        t = dm_mod2pi(alpha - a_rsr + p * 0.5);
+        q = dm_mod2pi(alpha - beta - t + p);
+        RRTK_DUBINS_TAKE(4)
+    }
+    tmp = (6.0 - dd + 2.0 * cab + 2.0 * d * (sb - sa)) * 0.125;
+    if (!(fabs(tmp) > 1.0)) {
+        p = dm_mod2pi(DM_TWO_PI - dm_acos(tmp));
+        t = dm_mod2pi(p * 0.5 - alpha + a_lsl);
+        q = dm_mod2pi(dm_mod2pi(beta) - alpha - t + p);
+        RRTK_DUBINS_TAKE(5)
+    }
+#undef RRTK_DUBINS_TAKE
+}
+
+// (t, p, q, len) of one given word (the one dubins_shortest chose for the same arguments: identical operations, identical bits)
+__device__ __noinline__ void dubins_rebuild(int dx, int dy, int h0, int h1, int NH, double rho, const double2 *tab, int word, DubinsPath &out)
+{
+    DubinsIn g;
+    dubins_setup(dx, dy, h0, h1, NH, rho, tab, g);
+    out.word = word;
+    out.t = out.p = out.q = 0.0;
+    out.len = CUDART_INF;
+    double t, p, q;
+    if (word >= 0 && dubins_word(g, word, t, p, q)) { out.t = t; out.p = p; out.q = q; out.len = ((t + p) + q) * rho; }
+    else out.word = -1;
 }
 
 // segment kinds of word w, 2 bits each (0 left arc, 1 straight, 2 right arc): LSL RSR LSR RSL RLR LRL
@@ -225,7 +289,7 @@ __device__ __forceinline__ DubinsTrack dubins_track(int x0, int y0, int h0, int 
 // pose at arc length s (cells) from the start
 __device__ __forceinline__ Pose dubins_point(const DubinsTrack &tr, double s)
 {
-    const double u = s / tr.rho;
+    const double u = s * (1.0 / tr.rho);
     if (u < tr.t) return dubins_advance(tr.q0, tr.k0, u, tr.rho);
     const double u2 = u - tr.t;
     if (u2 < tr.p) return dubins_advance(tr.q1, tr.k1, u2, tr.rho);

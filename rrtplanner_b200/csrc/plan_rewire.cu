@@ -91,8 +91,8 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
 
     // ---- shared-memory carve-up -------------------------------------------------------------------
     unsigned char *sp = smem_raw;
-    double *valL = reinterpret_cast<double *>(sp); sp += sizeof(double) * cap;       // edge length per radius-set slot
-    double *valC = reinterpret_cast<double *>(sp); sp += sizeof(double) * cap;       // cost through that edge
+    double *valL1 = reinterpret_cast<double *>(sp); sp += sizeof(double) * cap;      // length member -> sample, per radius-set slot
+    double *valL2 = reinterpret_cast<double *>(sp); sp += sizeof(double) * cap;      // length sample -> member
     double2 *tab = reinterpret_cast<double2 *>(sp); sp += sizeof(double2) * 256;     // (sin, cos) per heading
     uint32_t *spts = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * (size_t)((n + 2) & ~1);
     uint32_t *mask = reinterpret_cast<uint32_t *>(sp); sp += sizeof(uint32_t) * (size_t)(((n + 1 + 31) / 32 + 1) & ~1);
@@ -100,16 +100,17 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
     uint16_t *next = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * (size_t)((n + 4) & ~3);
     uint16_t *ring = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * (size_t)cap;
     uint8_t *flag = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
+    uint8_t *word1 = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;             // Dubins word of the two edges per slot
+    uint8_t *word2 = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
     uint8_t *shead = reinterpret_cast<uint8_t *>(sp);
 
     __shared__ unsigned long long s_wmin[NW];
     __shared__ int s_wcnt[NW];
     __shared__ int s_wdup[NW];
     __shared__ unsigned long long s_best;       // bit pattern of the cheapest free candidate cost
-    __shared__ int s_bestv, s_bestslot;
+    __shared__ int s_bestslot;
     __shared__ int s_accept, s_tail;
-    __shared__ double s_c0, s_l0, s_cbest, s_lbest;
-    __shared__ int s_vbest;
+    __shared__ double s_c0, s_l0;
     __shared__ long long s_stat[10];
 
     const rrtk_plan_desc pd = P.plans[plan];
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
 
     int j = 1;
     long long my_checks = 0, my_lens = 0;      // per-thread counters, reduced at the end
+    const bool both = P.rewire != 0;           // edge lengths in both directions per member
 
     for (int it = 0; it < n; ++it) {
         const short2 sm = samples[it];
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         }
         __syncthreads();
 
-        // ---- B: radius list (ascending) + gate ---------------------------------------------------------
+        // ---- B: ascending radius list; every warp measures the edges of its own members, warp 0 also the gate edge --
         unsigned long long nk = s_wmin[0];
         int m_total = 0, my_off = 0, dup_any = 0;
 #pragma unroll
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         }
         const int vnear = (int)(nk & 0xffffffffu);
         const bool overflow = P.star && m_total > cap;
+        int ntask = 0;
         if (P.star && !overflow) {
             int off = my_off;
             for (int base = v0; base < v1; base += 32) {
@@ -200,21 +203,38 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
                 if ((m >> lane) & 1u) ring[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base + lane);
                 off += __popc(m);
             }
+            ntask = (off - my_off) << (both ? 1 : 0);
+            __syncwarp();
+        }
+        const int extra = warp == 0 ? 1 : 0;                     // task 0 of warp 0 = the edge nearest -> sample
+        DubinsPath w0;
+        w0.word = -1; w0.t = w0.p = w0.q = 0.0; w0.len = 0.0;
+        for (int tsk = lane; tsk < ntask + extra; tsk += 32) {
+            const bool gate = extra && tsk == 0;
+            const int k = tsk - extra;
+            const int slot = gate ? 0 : my_off + (both ? k >> 1 : k);
+            const bool back = both && !gate && (k & 1);          // sample -> member
+            const int vn = gate ? vnear : ring[slot];
+            const uint32_t pv = spts[vn];
+            const int hv = shead[vn];
+            DubinsPath w;
+            const double l = Edge<MODEL>::length(P, tab, back ? pnew : pv, back ? qh : hv, back ? pv : pnew, back ? hv : qh, w);
+            ++my_lens;
+            if (gate) w0 = w, w0.len = l;
+            else if (back) { valL2[slot] = l; word2[slot] = (uint8_t)w.word; }
+            else { valL1[slot] = l; word1[slot] = (uint8_t)w.word; }
         }
         if (warp == 0) {
-            DubinsPath w0;
-            const uint32_t pn = spts[vnear];
-            const int hn = shead[vnear];
-            const double l0 = Edge<MODEL>::length(P, tab, pn, hn, pnew, qh, w0);
-            const bool ok = Edge<MODEL>::is_free(P, bits, pn, hn, pnew, w0, lane);
+            w0.word = __shfl_sync(RRTK_FULL, w0.word, 0);
+            w0.t = __shfl_sync(RRTK_FULL, w0.t, 0); w0.p = __shfl_sync(RRTK_FULL, w0.p, 0);
+            w0.q = __shfl_sync(RRTK_FULL, w0.q, 0); w0.len = __shfl_sync(RRTK_FULL, w0.len, 0);
+            const bool ok = Edge<MODEL>::is_free(P, bits, spts[vnear], shead[vnear], pnew, w0, lane);
             if (lane == 0) {
-                ++my_checks; ++my_lens;
-                const bool acc = ok && !dup_any && j != n && !overflow;
-                s_accept = acc;
+                ++my_checks;
+                s_accept = ok && !dup_any && j != n && !overflow;
                 if (overflow) s_stat[S2_OVERFLOW] = 1;
-                const double c0 = __dadd_rn(cost[vnear], l0);
-                s_c0 = c0; s_l0 = l0;
-                s_best = 0xffffffffffffffffull; s_bestv = 0x7fffffff; s_bestslot = -1;
+                s_c0 = __dadd_rn(cost[vnear], w0.len); s_l0 = w0.len;
+                s_best = 0xffffffffffffffffull; s_bestslot = 0x7fffffff;
             }
         }
         __syncthreads();
@@ -222,35 +242,30 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         const double c0 = s_c0;
         const int m = P.star ? m_total : 0;
 
-        // ---- C: parent candidates -----------------------------------------------------------------------
+        // ---- C: parent candidates (prefilter and cost test of the specification) --------------------------
         for (int i = tid; i < m; i += T) {
             const int vn = ring[i];
             uint8_t f = 0;
             if (vn != vnear) {
-                const uint32_t pv = spts[vn];
                 const double cv = cost[vn];
-                const double D = __dsqrt_rn((double)dist2(pv, qx, qy));
-                if (__dadd_rn(cv, D) < c0) {
-                    DubinsPath w;
-                    const double lc = Edge<MODEL>::length(P, tab, pv, shead[vn], pnew, qh, w);
-                    ++my_lens;
-                    const double cn = __dadd_rn(cv, lc);
-                    if (cn < c0) { valL[i] = lc; valC[i] = cn; f = 1; }
-                }
+                const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
+                if (__dadd_rn(cv, D) < c0 && __dadd_rn(cv, valL1[i]) < c0) f = 1;
             }
             flag[i] = f;
         }
         __syncthreads();
 
-        // ---- D: choose the parent ------------------------------------------------------------------------
+        // ---- D: choose the parent: warps test the candidates' edges, the cheapest free one wins ------------
         for (int i = warp; i < m; i += NW) {
             if (!flag[i]) continue;
-            const double cn = valC[i];
-            if ((unsigned long long)__double_as_longlong(cn) > s_best) continue;    // a cheaper free edge is known
             const int vn = ring[i];
+            const double cn = __dadd_rn(cost[vn], valL1[i]);
+            if ((unsigned long long)__double_as_longlong(cn) > s_best) continue;    // a cheaper free edge is known
             const uint32_t pv = spts[vn];
             DubinsPath w;
-            if (MODEL == RRTK_MODEL_DUBINS) Edge<MODEL>::length(P, tab, pv, shead[vn], pnew, qh, w);
+            w.word = 0;
+            if (MODEL == RRTK_MODEL_DUBINS)
+                dubins_rebuild(px(pnew) - px(pv), py(pnew) - py(pv), shead[vn], qh, P.NH, P.rho, tab, word1[i], w);
             const bool ok = Edge<MODEL>::is_free(P, bits, pv, shead[vn], pnew, w, lane);
             if (lane == 0) {
                 ++my_checks;
@@ -260,19 +275,15 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         __syncthreads();
         if (s_best != 0xffffffffffffffffull) {
             const unsigned long long best = s_best;
-            for (int i = tid; i < m; i += T)
-                if (flag[i] == 2 && (unsigned long long)__double_as_longlong(valC[i]) == best) atomicMin(&s_bestv, (int)ring[i]);
-            __syncthreads();
-            const int bv = s_bestv;
-            for (int i = tid; i < m; i += T)
-                if (ring[i] == bv) s_bestslot = i;
+            for (int i = tid; i < m; i += T)            // ties: the list is ascending, so the lowest slot is the lowest vertex
+                if (flag[i] == 2 && (unsigned long long)__double_as_longlong(__dadd_rn(cost[ring[i]], valL1[i])) == best)
+                    atomicMin(&s_bestslot, i);
             __syncthreads();
         }
         // ---- E: insert vertex j, rewire candidates ---------------------------------------------------------
         int vbest = vnear;
         double cbest = c0, lbest = s_l0;
-        if (s_bestslot >= 0) { vbest = s_bestv; cbest = valC[s_bestslot]; lbest = valL[s_bestslot]; }
-        __syncthreads();                         // valC / valL / flag are rewritten below
+        if (s_bestslot != 0x7fffffff) { vbest = ring[s_bestslot]; lbest = valL1[s_bestslot]; cbest = __dadd_rn(cost[vbest], lbest); }
         if (tid == 0) {
             spts[j] = pnew; shead[j] = (uint8_t)qh;
             o_pts[j] = make_short2((short)qx, (short)qy); o_head[j] = (uint8_t)qh;
@@ -280,21 +291,14 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
             next[j] = first[vbest]; first[vbest] = (uint16_t)j;
             s_stat[S2_ACCEPTED] += 1; s_stat[S2_RING] += m;
         }
-        if (P.rewire) {
+        if (both) {
             for (int i = tid; i < m; i += T) {
                 const int vn = ring[i];
                 uint8_t f = 0;
                 if (vn != vbest) {
-                    const uint32_t pv = spts[vn];
                     const double cv = cost[vn];
-                    const double D = __dsqrt_rn((double)dist2(pv, qx, qy));
-                    if (__dadd_rn(cbest, D) < cv) {
-                        DubinsPath w;
-                        const double lr = Edge<MODEL>::length(P, tab, pnew, qh, pv, shead[vn], w);
-                        ++my_lens;
-                        const double cm = __dadd_rn(cbest, lr);
-                        if (cm < cv) { valL[i] = lr; valC[i] = cm; f = 1; }
-                    }
+                    const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
+                    if (__dadd_rn(cbest, D) < cv && __dadd_rn(cbest, valL2[i]) < cv) f = 1;
                 }
                 flag[i] = f;
             }
@@ -305,7 +309,9 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
                 const int vn = ring[i];
                 const uint32_t pv = spts[vn];
                 DubinsPath w;
-                if (MODEL == RRTK_MODEL_DUBINS) Edge<MODEL>::length(P, tab, pnew, qh, pv, shead[vn], w);
+                w.word = 0;
+                if (MODEL == RRTK_MODEL_DUBINS)
+                    dubins_rebuild(px(pv) - px(pnew), py(pv) - py(pnew), qh, shead[vn], P.NH, P.rho, tab, word2[i], w);
                 const bool ok = Edge<MODEL>::is_free(P, bits, pnew, qh, pv, w, lane);
                 if (lane == 0) { ++my_checks; flag[i] = ok ? 2 : 0; }
             }
@@ -320,7 +326,8 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
                         todo &= todo - 1;
                         const int slot = base + b;
                         const int vn = ring[slot];
-                        const double cm = valC[slot], lr = valL[slot];
+                        const double lr = valL2[slot];
+                        const double cm = __dadd_rn(cbest, lr);
                         const double cv = cost[vn];              // may have been lowered by an earlier rewire of this round
                         const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
                         if (!(__dadd_rn(cbest, D) < cv && cm < cv)) continue;       // warp-uniform
@@ -363,12 +370,13 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
 
     // ---- goal connection (rrt.py:284-332 with this model's edges) ----------------------------------------
     const uint32_t pgoal = pack_xy(pd.goal_x, pd.goal_y);
-    if (tid == 0) { s_best = 0xffffffffffffffffull; s_bestv = 0x7fffffff; }
+    if (tid == 0) { s_best = 0xffffffffffffffffull; s_bestslot = 0x7fffffff; }
     for (int v = tid; v < j; v += T) {
         DubinsPath w;
         const double lg = Edge<MODEL>::length(P, tab, spts[v], shead[v], pgoal, goal_h, w);
         ++my_lens;
         gcost[v] = __dadd_rn(cost[v], lg);
+        first[v] = (uint16_t)(w.word & 0xff);          // the child lists are no longer needed: keep the word per vertex here
     }
     __syncthreads();
     // every vertex whose cost is not already beaten is tested; the shared minimum only prunes
@@ -376,7 +384,9 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         const double cg = gcost[v];
         if ((unsigned long long)__double_as_longlong(cg) > s_best) continue;        // a cheaper free edge is known
         DubinsPath w;
-        if (MODEL == RRTK_MODEL_DUBINS) Edge<MODEL>::length(P, tab, spts[v], shead[v], pgoal, goal_h, w);
+        w.word = 0;
+        if (MODEL == RRTK_MODEL_DUBINS)
+            dubins_rebuild(px(pgoal) - px(spts[v]), py(pgoal) - py(spts[v]), shead[v], goal_h, P.NH, P.rho, tab, (int)(int8_t)first[v], w);
         const bool ok = Edge<MODEL>::is_free(P, bits, spts[v], shead[v], pgoal, w, lane);
         if (lane == 0) {
             ++my_checks;
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         for (int v = tid; v < j; v += T) {
             const unsigned long long b = (unsigned long long)__double_as_longlong(gcost[v]);
             // a vertex with cost == gbest was never pruned (pruning needs cost > best >= gbest), so queue[v] is its verdict
-            if (b == gbest && queue[v] == 1) atomicMin(&s_bestv, v);
+            if (b == gbest && queue[v] == 1) atomicMin(&s_bestslot, v);
         }
     }
     __syncthreads();
@@ -407,7 +417,7 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
     if (tid == 0) {
         int vgoal = 0, found = 0;
         if (gbest != 0xffffffffffffffffull) {
-            const int v = s_bestv;
+            const int v = s_bestslot;
             DubinsPath w;
             const double lg = Edge<MODEL>::length(P, tab, spts[v], shead[v], pgoal, goal_h, w);
             vgoal = j; found = 1;
@@ -430,7 +440,7 @@ static size_t plan2_smem(int n, int cap)
     b += sizeof(uint32_t) * (size_t)(((n + 1 + 31) / 32 + 1) & ~1);
     b += sizeof(uint16_t) * 2 * (size_t)((n + 4) & ~3);
     b += sizeof(uint16_t) * (size_t)cap;
-    b += (size_t)cap;
+    b += (size_t)cap * 3;
     b += (size_t)(n + 1);
     return (b + 15) & ~(size_t)15;
 }
