@@ -9,6 +9,10 @@
 
 #include "common.cuh"
 
+#ifndef RRTK_DM_INLINE
+#define RRTK_DM_INLINE __noinline__
+#endif
+
 namespace rrtk {
 
 #define DM_PI 3.14159265358979323846
@@ -34,7 +38,7 @@ __device__ __forceinline__ double dm_atan_small(double z)
     return z * (e + s * o);
 }
 
-__device__ __noinline__ double dm_atan2(double y, double x)
+__device__ RRTK_DM_INLINE double dm_atan2(double y, double x)
 {
     if (x == 0.0 && y == 0.0) return 0.0;
     const double ax = fabs(x), ay = fabs(y);
@@ -51,7 +55,7 @@ __device__ __noinline__ double dm_atan2(double y, double x)
 }
 
 // quadrant k = floor(a * 2/pi + 1/2), r = a - k * pi/2, Taylor polynomials on |r| <= pi/4
-__device__ __noinline__ void dm_sincos(double a, double &sn, double &cs)
+__device__ RRTK_DM_INLINE void dm_sincos(double a, double &sn, double &cs)
 {
     const double kf = floor(a * DM_TWO_OVER_PI + 0.5);
     const double r = a - kf * DM_HALF_PI;

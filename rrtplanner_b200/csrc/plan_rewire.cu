@@ -19,6 +19,10 @@
 
 #include "dubins.cuh"
 
+#ifndef RRTK_K8_BLOCK_THREADS
+#define RRTK_K8_BLOCK_THREADS 768        // resident threads per SM the register allocation is bounded for
+#endif
+
 namespace rrtk {
 
 enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROPAGATED, S2_RING, S2_LEN_EVALS, S2_OVERFLOW };
@@ -81,7 +85,7 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
 }
 
 template <int MODEL, int T>
-__global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
+__global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kernel(Plan2Params P)
 {
     constexpr int NW = T / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -102,11 +106,14 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
     uint8_t *flag = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
     uint8_t *word1 = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;             // Dubins word of the two edges per slot
     uint8_t *word2 = reinterpret_cast<uint8_t *>(sp); sp += (size_t)cap;
+    uint16_t *tasks2 = reinterpret_cast<uint16_t *>(sp); sp += sizeof(uint16_t) * (size_t)cap;    // slots whose edge sample -> member is wanted
     uint8_t *shead = reinterpret_cast<uint8_t *>(sp);
 
     __shared__ unsigned long long s_wmin[NW];
     __shared__ int s_wcnt[NW];
     __shared__ int s_wdup[NW];
+    __shared__ unsigned long long s_wlb[NW];
+    __shared__ int s_ntask2;
     __shared__ unsigned long long s_best;       // bit pattern of the cheapest free candidate cost
     __shared__ int s_bestslot;
     __shared__ int s_accept, s_tail;
@@ -153,6 +160,9 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
     int j = 1;
     long long my_checks = 0, my_lens = 0;      // per-thread counters, reduced at the end
     const bool both = P.rewire != 0;           // edge lengths in both directions per member
+    // Dubins: a length costs ~1.5 k instructions, so phase B2 first drops the members no new vertex could improve;
+    // Euclid: a length is one square root, so all of them are simply measured
+    const bool prune = both && MODEL == RRTK_MODEL_DUBINS;
 
     for (int it = 0; it < n; ++it) {
         const short2 sm = samples[it];
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         }
         __syncthreads();
 
-        // ---- B: ascending radius list; every warp measures the edges of its own members, warp 0 also the gate edge --
+        // ---- B1: ascending radius list; lower bound on the new vertex's cost ---------------------------------
         unsigned long long nk = s_wmin[0];
         int m_total = 0, my_off = 0, dup_any = 0;
 #pragma unroll
@@ -195,25 +205,65 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         }
         const int vnear = (int)(nk & 0xffffffffu);
         const bool overflow = P.star && m_total > cap;
-        int ntask = 0;
-        if (P.star && !overflow) {
+        const int m = (P.star && !overflow) ? m_total : 0;
+        if (m) {
             int off = my_off;
+            unsigned long long lbk = 0xffffffffffffffffull;
             for (int base = v0; base < v1; base += 32) {
-                const unsigned m = mask[base >> 5];
-                if ((m >> lane) & 1u) ring[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(base + lane);
-                off += __popc(m);
+                const unsigned mk = mask[base >> 5];
+                if ((mk >> lane) & 1u) {
+                    const int v = base + lane;
+                    ring[off + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)v;
+                    if (prune) {
+                        const double c = __dadd_rn(cost[v], __dsqrt_rn((double)dist2(spts[v], qx, qy)));
+                        const unsigned long long k = (unsigned long long)__double_as_longlong(c);
+                        lbk = k < lbk ? k : lbk;
+                    }
+                }
+                off += __popc(mk);
             }
-            ntask = (off - my_off) << (both ? 1 : 0);
-            __syncwarp();
+            if (prune) {
+                lbk = warp_min_u64(lbk);
+                if (lane == 0) s_wlb[warp] = lbk;
+            }
         }
-        const int extra = warp == 0 ? 1 : 0;                     // task 0 of warp 0 = the edge nearest -> sample
+        if (tid == 0) s_ntask2 = 0;
+        __syncthreads();
+
+        // ---- B2: which members need the edge sample -> member: only those a vertex of cost >= lb could improve -------
+        if (prune && m) {
+            unsigned long long lbk = (unsigned long long)__double_as_longlong(
+                __dadd_rn(cost[vnear], __dsqrt_rn((double)(uint32_t)(nk >> 32))));
+#pragma unroll
+            for (int w = 0; w < NW; ++w) lbk = s_wlb[w] < lbk ? s_wlb[w] : lbk;
+            // every edge is at least as long as the straight line up to rounding (and the 1e-9 snap of mod2pi): 1e-6 cells of slack
+            const double lb = __dsub_rn(__longlong_as_double((long long)lbk), 1e-6);
+            for (int base = warp * 32; base < m; base += T) {
+                const int i = base + lane;
+                bool want = false;
+                if (i < m) {
+                    const int vn = ring[i];
+                    want = __dadd_rn(lb, __dsqrt_rn((double)dist2(spts[vn], qx, qy))) < cost[vn];
+                    word2[i] = 0xfe;                              // "not measured": phase E must never need it
+                }
+                const unsigned bal = __ballot_sync(RRTK_FULL, want);
+                int at = 0;
+                if (lane == 0 && bal) at = atomicAdd(&s_ntask2, __popc(bal));
+                at = __shfl_sync(RRTK_FULL, at, 0);
+                if (want) tasks2[at + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+            }
+            __syncthreads();
+        }
+
+        // ---- B3: edge lengths, one task per thread: the gate edge nearest -> sample, member -> sample for every member,
+        //          sample -> member where B2 asked for it --------------------------------------------------------------
+        const int ntask = 1 + m + (prune ? (m ? s_ntask2 : 0) : (both ? m : 0));
         DubinsPath w0;
         w0.word = -1; w0.t = w0.p = w0.q = 0.0; w0.len = 0.0;
-        for (int tsk = lane; tsk < ntask + extra; tsk += 32) {
-            const bool gate = extra && tsk == 0;
-            const int k = tsk - extra;
-            const int slot = gate ? 0 : my_off + (both ? k >> 1 : k);
-            const bool back = both && !gate && (k & 1);          // sample -> member
+        for (int tsk = tid; tsk < ntask; tsk += T) {
+            const bool gate = tsk == 0;
+            const bool back = tsk > m;                           // sample -> member
+            const int slot = gate ? 0 : (back ? (prune ? (int)tasks2[tsk - m - 1] : tsk - m - 1) : tsk - 1);
             const int vn = gate ? vnear : ring[slot];
             const uint32_t pv = spts[vn];
             const int hv = shead[vn];
@@ -240,7 +290,6 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
         __syncthreads();
         if (!s_accept) continue;                 // uniform: every thread reads the same shared flag
         const double c0 = s_c0;
-        const int m = P.star ? m_total : 0;
 
         // ---- C: parent candidates (prefilter and cost test of the specification) --------------------------
         for (int i = tid; i < m; i += T) {
@@ -298,7 +347,10 @@ __global__ void __launch_bounds__(T) plan_rewire_kernel(Plan2Params P)
                 if (vn != vbest) {
                     const double cv = cost[vn];
                     const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
-                    if (__dadd_rn(cbest, D) < cv && __dadd_rn(cbest, valL2[i]) < cv) f = 1;
+                    if (__dadd_rn(cbest, D) < cv) {
+                        if (prune && word2[i] == 0xfe) s_stat[S2_OVERFLOW] = 2;   // the lower bound of B2 was not one: report, never hide
+                        else if (__dadd_rn(cbest, valL2[i]) < cv) f = 1;
+                    }
                 }
                 flag[i] = f;
             }
@@ -440,7 +492,7 @@ static size_t plan2_smem(int n, int cap)
     b += sizeof(uint32_t) * (size_t)(((n + 1 + 31) / 32 + 1) & ~1);
     b += sizeof(uint16_t) * 2 * (size_t)((n + 4) & ~3);
     b += sizeof(uint16_t) * (size_t)cap;
-    b += (size_t)cap * 3;
+    b += (size_t)cap * 5;
     b += (size_t)(n + 1);
     return (b + 15) & ~(size_t)15;
 }
