@@ -492,8 +492,8 @@ def gpu_arm(args):
                "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
                "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8 + 4)),
                "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt / args.steps,
-               "api": "rrtk_ctx_plan_worlds (seed mode, chunks of %d plans on 3 streams) via rrtplanner_b200._lib.Context, "
-                      "pinned host buffers" % (args.e2e_chunk or sms * blocks_per_sm_e2e),
+               "api": "rrtk_ctx_plan_worlds (seed mode, chunks of %d plans on 8 rotating streams) via rrtplanner_b200._lib.Context, "
+                      "pinned host buffers" % (args.e2e_chunk or 2 * sms),
                "matches_device_arm": bool(same)}
         ctx.close()
 

@@ -310,7 +310,7 @@ int rrtk_ctx_plan(rrtk_ctx *ctx, int kind, const rrtk_plan_desc *h_plans, int np
                   int64_t *h_stats, double *h_ell_c);
 
 /* rrtk_ctx_set_grids + rrtk_ctx_plan in one call, pipelined: plans (ordered by world index) are
- * processed in chunks of chunk_plans (0 = one wave of plan blocks: SMs x resident blocks per SM) on rotating streams, so the upload of one chunk's
+ * processed in chunks of chunk_plans (0 = two plan blocks per SM, the first chunk one per SM) on rotating streams, so the upload of one chunk's
  * grids and the download of another's trees overlap the kernels; give pinned host buffers for the
  * copies to be asynchronous.  The worlds are not kept in the context afterwards. */
 int rrtk_ctx_plan_worlds(rrtk_ctx *ctx, int kind, const uint8_t *h_og, int nworlds, int W, int H,

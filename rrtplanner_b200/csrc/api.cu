@@ -121,7 +121,7 @@ struct PipeSlot {
     DevBuf og, bits, rowcum, plans, samples, state, balls, pts, cost, parent, stats, ell;
     std::vector<rrtk_plan_desc> desc;
 };
-constexpr int kPipeSlots = 3;
+constexpr int kPipeSlots = 8;
 
 struct rrtk_ctx {
     cudaStream_t stream = nullptr;
@@ -490,15 +490,19 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
     RRTK_REQUIRE(nworlds >= 1 && nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan_worlds: need nworlds >= 1, nplans >= 0, 1 <= n <= 65534");
     RRTK_TRY(check_grid_dims(W, H, 16384));
     if (nplans == 0) return RRTK_OK;
+    bool ramp = false;
     if (chunk_plans <= 0) {
-        // one chunk = one wave of plan blocks (what the device runs concurrently): smaller chunks leave SMs idle
-        // between kernels, larger ones delay the first download (measured: scripts/e2e_chunks.sh)
+        // Chunks of two plan blocks per SM (a fraction of a wave): the next chunks' uploads, packing and sampler kernel
+        // (one sequential PCG64 thread per plan: ~2.6 ms however few plans) need free SM resources to overlap the running
+        // plan blocks, and a chunk that fills every SM leaves none until its first blocks retire.  Measured on B200, cfg3,
+        // 4096 plans (scripts/e2e_breakdown.py): 222..740 plans per chunk 61.6-64 ms, 1036 (one wave) 75 ms, unpipelined 82 ms.
         DevInfo *di;
         RRTK_TRY(dev_info(&di));
         int smem = 0, per_sm = 0;
-        chunk_plans = 512;
-        if (plan_footprint(kind, W, H, n, 0, di->optin, di->sm_smem, &smem, &per_sm) == RRTK_OK && per_sm > 0)
+        chunk_plans = 2 * di->sms;
+        if (plan_footprint(kind, W, H, n, 0, di->optin, di->sm_smem, &smem, &per_sm) == RRTK_OK && per_sm > 0 && per_sm < 2)
             chunk_plans = di->sms * per_sm;
+        ramp = true;
     }
     for (int p = 0; p < nplans; ++p) {
         const rrtk_plan_desc &d = h_plans[p];
@@ -526,25 +530,50 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
     RRTK_TRY(dev_info(&di));
     const size_t cells = (size_t)W * H, words = grid_words(W, H), rows1 = (size_t)n + 1;
     int status = RRTK_OK;
-    for (int p0 = 0, ci = 0; p0 < nplans && status == RRTK_OK; p0 += chunk_plans, ++ci) {
-        const int m = (nplans - p0 < chunk_plans) ? nplans - p0 : chunk_plans;
-        PipeSlot &s = c->pipe[ci % kPipeSlots];
+    // chunk list, then every slot sized once for the largest chunk (growing a buffer later would free it under the pipeline)
+    std::vector<int> starts;
+    {
+        int sz = ramp ? (di->sms < chunk_plans ? di->sms : chunk_plans) : chunk_plans;
+        for (int p0 = 0; p0 < nplans; p0 += sz, sz = (2 * sz < chunk_plans) ? 2 * sz : chunk_plans) {
+            starts.push_back(p0);
+            if (p0 + sz >= nplans) break;
+        }
+        starts.push_back(nplans);
+    }
+    size_t max_m = 0, max_nw = 0;
+    for (size_t k = 0; k + 1 < starts.size(); ++k) {
+        const size_t m = (size_t)(starts[k + 1] - starts[k]);
+        const size_t nw = (size_t)(h_plans[starts[k + 1] - 1].world - h_plans[starts[k]].world + 1);
+        max_m = m > max_m ? m : max_m;
+        max_nw = nw > max_nw ? nw : max_nw;
+    }
+    const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
+    for (size_t k = 0; k < nslots; ++k) {
+        PipeSlot &s = c->pipe[k];
         if (!s.stream) RRTK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        const bool grow = s.og.cap < cells * max_nw || s.pts.cap < rows1 * max_m * 4 || s.samples.cap < max_m * n * 4 ||
+                          (kind == RRTK_INFORMED && (s.ell.cap < rows1 * max_m * 8 || (h_balls && s.balls.cap < max_m * n * 16)));
+        if (grow) RRTK_CUDA(cudaStreamSynchronize(s.stream));
+        RRTK_TRY(s.og.reserve(cells * max_nw));
+        RRTK_TRY(s.bits.reserve(words * 4 * max_nw));
+        RRTK_TRY(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw));
+        RRTK_TRY(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m));
+        RRTK_TRY(s.samples.reserve(max_m * n * 4));
+        RRTK_TRY(s.state.reserve(max_m * 32));
+        RRTK_TRY(s.pts.reserve(rows1 * max_m * 4));
+        RRTK_TRY(s.cost.reserve(rows1 * max_m * 8));
+        RRTK_TRY(s.parent.reserve(rows1 * max_m * 4));
+        RRTK_TRY(s.stats.reserve(max_m * RRTK_STAT_COUNT * 8));
+        if (kind == RRTK_INFORMED) {
+            RRTK_TRY(s.ell.reserve(rows1 * max_m * 8));
+            if (h_balls) RRTK_TRY(s.balls.reserve(max_m * n * 16));
+        }
+    }
+    for (size_t ci = 0; ci + 1 < starts.size() && status == RRTK_OK; ++ci) {
+        const int p0 = starts[ci], m = starts[ci + 1] - starts[ci];
+        PipeSlot &s = c->pipe[ci % kPipeSlots];
         cudaStream_t st = s.stream;
         const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
-        // buffers of this slot may still be in use by the chunk that last ran on it: stream order covers
-        // the device side; growing a buffer frees it, so drain the stream first in that (first-call) case
-        const bool grow = s.og.cap < cells * nw || s.pts.cap < rows1 * m * 4 || s.samples.cap < (size_t)m * n * 4;
-        if (grow) RRTK_CUDA(cudaStreamSynchronize(st));
-        RRTK_TRY(s.og.reserve(cells * nw));
-        RRTK_TRY(s.bits.reserve(words * 4 * nw));
-        RRTK_TRY(s.rowcum.reserve((size_t)(W + 1) * 4 * nw));
-        RRTK_TRY(s.plans.reserve(sizeof(rrtk_plan_desc) * m));
-        RRTK_TRY(s.samples.reserve((size_t)m * n * 4));
-        RRTK_TRY(s.pts.reserve(rows1 * m * 4));
-        RRTK_TRY(s.cost.reserve(rows1 * m * 8));
-        RRTK_TRY(s.parent.reserve(rows1 * m * 4));
-        RRTK_TRY(s.stats.reserve((size_t)m * RRTK_STAT_COUNT * 8));
         RRTK_CUDA(cudaMemcpyAsync(s.og.p, h_og + cells * w0, cells * nw, cudaMemcpyHostToDevice, st));
         RRTK_TRY(pack_launch(s.og.as<uint8_t>(), nw, W, H, s.bits.as<uint32_t>(), st));
         RRTK_TRY(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st));
@@ -554,18 +583,12 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
         if (h_samples) {
             RRTK_CUDA(cudaMemcpyAsync(s.samples.p, h_samples + (size_t)p0 * n * 2, (size_t)m * n * 4, cudaMemcpyHostToDevice, st));
         } else {
-            RRTK_TRY(s.state.reserve((size_t)m * 32));
             RRTK_CUDA(cudaMemcpyAsync(s.state.p, h_state + (size_t)p0 * 4, (size_t)m * 32, cudaMemcpyHostToDevice, st));
             RRTK_TRY(sample_streams_launch(s.bits.as<uint32_t>(), s.rowcum.as<int32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m,
                                            s.state.as<uint64_t>(), n, s.samples.as<int16_t>(), di->optin, st));
         }
-        if (kind == RRTK_INFORMED) {
-            RRTK_TRY(s.ell.reserve(rows1 * m * 8));
-            if (h_balls) {
-                RRTK_TRY(s.balls.reserve((size_t)m * n * 16));
-                RRTK_CUDA(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st));
-            }
-        }
+        if (kind == RRTK_INFORMED && h_balls)
+            RRTK_CUDA(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st));
         RRTK_TRY(rrtk_plan_batch(kind, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, r_rewire, r_goal,
                                  s.samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? s.balls.as<double>() : nullptr,
                                  s.pts.as<int16_t>(), s.cost.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(),

@@ -80,11 +80,153 @@ __device__ __forceinline__ short2 rank_to_cell(const uint32_t *__restrict__ g, c
     return make_short2((short)lo, (short)y);
 }
 
-// one block per plan: thread 0 runs the (inherently sequential) generator into shared memory,
-// then the block maps ranks to cells in parallel
-__global__ void sample_stream_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ rowcum, int W, int H,
-                                     const rrtk_plan_desc *__restrict__ plans, const unsigned long long *__restrict__ state, int n,
-                                     short2 *__restrict__ samples, unsigned long long *__restrict__ state_out, uint32_t *__restrict__ carry)
+// ---- the generator in parallel ----------------------------------------------------------------------------------
+// PCG64 is a 128-bit LCG, so the state k steps ahead is state * A^k + inc * (A^k - 1) / (A - 1), computable in
+// O(log k) (O'Neill's pcg_advance_lcg_128, restated): every thread jumps to its own slice of the raw 64-bit output
+// sequence.  Lemire's rejection loop then simply drops the raw 32-bit values whose low product half falls below the
+// threshold, i.e. the bounded draws are a stream COMPACTION of the raw values -- one block scan.
+struct U128 { unsigned long long hi, lo; };
+__device__ __forceinline__ U128 mul128(U128 a, U128 b)
+{
+    U128 r;
+    r.lo = a.lo * b.lo;
+    r.hi = __umul64hi(a.lo, b.lo) + a.hi * b.lo + a.lo * b.hi;
+    return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b)
+{
+    U128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+__device__ __forceinline__ void pcg_jump(Pcg64 &g, unsigned long long delta)
+{
+    U128 cur_mult = {0x2360ED051FC65DA4ull, 0x4385DF649FCCF645ull}, cur_plus = {g.inc_hi, g.inc_lo};
+    U128 acc_mult = {0ull, 1ull}, acc_plus = {0ull, 0ull};
+    while (delta) {
+        if (delta & 1ull) {
+            acc_mult = mul128(acc_mult, cur_mult);
+            acc_plus = add128(mul128(acc_plus, cur_mult), cur_plus);
+        }
+        cur_plus = mul128(add128(cur_mult, U128{0ull, 1ull}), cur_plus);
+        cur_mult = mul128(cur_mult, cur_mult);
+        delta >>= 1;
+    }
+    const U128 st = add128(mul128(acc_mult, U128{g.hi, g.lo}), acc_plus);
+    g.hi = st.hi; g.lo = st.lo;
+}
+
+constexpr int kSampleThreads = 128;
+constexpr int kRawSlack = 62;          // raw 32-bit values generated beyond n; more rejections than that -> sequential path
+
+// one block per plan: the generator's raw outputs in parallel slices, Lemire's rejection as a compaction, then
+// ranks -> cells in parallel.  The sequential generator remains as the fallback for a stream with more than kRawSlack
+// rejections (probability ~ (n * nfree / 2^32)^62 / 62!).
+__global__ void __launch_bounds__(kSampleThreads)
+sample_stream_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ rowcum, int W, int H,
+                     const rrtk_plan_desc *__restrict__ plans, const unsigned long long *__restrict__ state, int n,
+                     short2 *__restrict__ samples, unsigned long long *__restrict__ state_out, uint32_t *__restrict__ carry)
+{
+    extern __shared__ uint32_t s_mem[];
+    uint32_t *s_rank = s_mem;                    // n bounded draws
+    uint32_t *s_raw = s_mem + n;                 // raw 32-bit values in the order numpy's next_uint32 hands them out
+    __shared__ int s_warp[kSampleThreads / 32];
+    __shared__ int s_consumed;                   // raw values used up by the n draws (-1: not enough generated)
+    const int plan = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int world = plans[plan].world;
+    const int *rc = rowcum + (size_t)world * (W + 1);
+    const uint32_t nfree = (uint32_t)__ldg(rc + W);
+    Pcg64 g0;
+    g0.hi = state[4 * plan]; g0.lo = state[4 * plan + 1];
+    g0.inc_hi = state[4 * plan + 2]; g0.inc_lo = state[4 * plan + 3];
+    g0.has32 = false; g0.buf32 = 0;
+    if (carry) { g0.has32 = carry[2 * plan] != 0; g0.buf32 = carry[2 * plan + 1]; }   // numpy's has_uint32 / uinteger
+    const int off = g0.has32 ? 1 : 0;
+    if (nfree <= 1u) {                           // numpy returns the single value without touching the generator
+        for (int i = tid; i < n; i += kSampleThreads) s_rank[i] = 0;
+        if (tid == 0) {
+            if (state_out) { state_out[4 * plan] = g0.hi; state_out[4 * plan + 1] = g0.lo; state_out[4 * plan + 2] = g0.inc_hi; state_out[4 * plan + 3] = g0.inc_lo; }
+        }
+        __syncthreads();
+    } else {
+        const int nraw = n + kRawSlack;                                   // raw values wanted: indices 0 .. nraw-1
+        const int n64 = (nraw - off + 1) >> 1;                            // 64-bit outputs that cover them
+        const int per = (n64 + kSampleThreads - 1) / kSampleThreads;      // outputs per thread
+        {
+            Pcg64 g = g0;
+            const int k0 = tid * per;
+            if (k0 < n64) {
+                pcg_jump(g, (unsigned long long)k0);
+                const int k1 = min(n64, k0 + per);
+                for (int k = k0; k < k1; ++k) {
+                    const unsigned long long v = g.next64();
+                    s_raw[off + 2 * k] = (uint32_t)v;
+                    s_raw[off + 2 * k + 1] = (uint32_t)(v >> 32);
+                }
+            }
+            if (tid == 0 && off) s_raw[0] = g0.buf32;
+        }
+        __syncthreads();
+        // compaction: thread t owns raw indices [t * span, (t + 1) * span)
+        const int total = off + 2 * n64;                                  // raw values available (>= nraw)
+        const int span = (total + kSampleThreads - 1) / kSampleThreads;
+        const uint32_t thr = (0xffffffffu - (nfree - 1u)) % nfree;        // Lemire's threshold
+        const int r0 = tid * span, r1 = min(total, r0 + span);
+        int acc = 0;
+        for (int r = r0; r < r1; ++r) acc += ((uint32_t)((unsigned long long)s_raw[r] * nfree) >= thr) ? 1 : 0;
+        int incl = acc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(RRTK_FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        if (tid == 0) s_consumed = -1;
+        __syncthreads();
+        int before = incl - acc;
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        for (int r = r0; r < r1; ++r) {
+            const unsigned long long m = (unsigned long long)s_raw[r] * nfree;
+            if ((uint32_t)m >= thr) {
+                if (before < n) s_rank[before] = (uint32_t)(m >> 32);
+                if (before == n - 1) s_consumed = r + 1;
+                ++before;
+            }
+        }
+        __syncthreads();
+        if (s_consumed < 0) {                    // not enough accepted values in the window: the plain sequential generator
+            if (tid == 0) {
+                Pcg64 g = g0;
+                for (int i = 0; i < n; ++i) s_rank[i] = g.bounded(nfree);
+                if (state_out) { state_out[4 * plan] = g.hi; state_out[4 * plan + 1] = g.lo; state_out[4 * plan + 2] = g.inc_hi; state_out[4 * plan + 3] = g.inc_lo; }
+                if (carry) { carry[2 * plan] = g.has32 ? 1u : 0u; carry[2 * plan + 1] = g.buf32; }
+            }
+        } else if (tid == 0 && (state_out || carry)) {
+            // the generator as the next plan() of the same planner object finds it (rrt.py:85: one rand_gen per object)
+            const int used = s_consumed - off;                            // raw values taken from fresh 64-bit outputs
+            const int out64 = (used + 1) >> 1;
+            Pcg64 g = g0;
+            pcg_jump(g, (unsigned long long)out64);
+            if (state_out) { state_out[4 * plan] = g.hi; state_out[4 * plan + 1] = g.lo; state_out[4 * plan + 2] = g.inc_hi; state_out[4 * plan + 3] = g.inc_lo; }
+            if (carry) {
+                const bool half = used > 0 ? (used & 1) != 0 : g0.has32 && s_consumed == 0;
+                carry[2 * plan] = half ? 1u : 0u;
+                carry[2 * plan + 1] = half ? s_raw[s_consumed] : (used > 0 ? s_raw[s_consumed - 1] : g0.buf32);
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t *g = bits + (size_t)world * grid_words(W, H);
+    const int TY = tiles_y(H);
+    short2 *out = samples + (size_t)plan * n;
+    for (int i = tid; i < n; i += kSampleThreads) out[i] = rank_to_cell(g, rc, W, TY, (int)s_rank[i]);
+}
+
+// n too large for the raw window in shared memory: thread 0 runs the generator sequentially
+__global__ void sample_stream_seq_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ rowcum, int W, int H,
+                                         const rrtk_plan_desc *__restrict__ plans, const unsigned long long *__restrict__ state, int n,
+                                         short2 *__restrict__ samples, unsigned long long *__restrict__ state_out, uint32_t *__restrict__ carry)
 {
     extern __shared__ uint32_t s_rank[];
     const int plan = blockIdx.x;
@@ -96,9 +238,9 @@ __global__ void sample_stream_kernel(const uint32_t *__restrict__ bits, const in
         g.hi = state[4 * plan]; g.lo = state[4 * plan + 1];
         g.inc_hi = state[4 * plan + 2]; g.inc_lo = state[4 * plan + 3];
         g.has32 = false; g.buf32 = 0;
-        if (carry) { g.has32 = carry[2 * plan] != 0; g.buf32 = carry[2 * plan + 1]; }   // numpy's has_uint32 / uinteger
+        if (carry) { g.has32 = carry[2 * plan] != 0; g.buf32 = carry[2 * plan + 1]; }
         for (int i = 0; i < n; ++i) s_rank[i] = nfree ? g.bounded(nfree) : 0;
-        if (state_out) {       // the generator as the next plan() of the same planner object finds it (rrt.py:85: one rand_gen per object)
+        if (state_out) {
             state_out[4 * plan] = g.hi; state_out[4 * plan + 1] = g.lo;
             state_out[4 * plan + 2] = g.inc_hi; state_out[4 * plan + 3] = g.inc_lo;
         }
@@ -116,16 +258,21 @@ int sample_streams_launch(const uint32_t *d_bits, const int32_t *d_rowcum, int W
                           uint64_t *d_state_out, uint32_t *d_carry)
 {
     if (nplans == 0 || n == 0) return RRTK_OK;
-    const size_t smem = (size_t)n * 4;
-    if (smem > (size_t)optin) {
+    const size_t smem = ((size_t)2 * n + kRawSlack + 4) * 4;      // bounded draws + raw 32-bit values
+    const size_t smem_seq = (size_t)n * 4;
+    const unsigned long long *st64 = reinterpret_cast<const unsigned long long *>(d_state);
+    if (smem <= (size_t)optin) {
+        RRTK_CUDA(cudaFuncSetAttribute(sample_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        sample_stream_kernel<<<nplans, kSampleThreads, smem, st>>>(d_bits, d_rowcum, W, H, d_plans, st64, n, reinterpret_cast<short2 *>(d_samples),
+                                                                  reinterpret_cast<unsigned long long *>(d_state_out), d_carry);
+    } else if (smem_seq <= (size_t)optin) {
+        RRTK_CUDA(cudaFuncSetAttribute(sample_stream_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_seq));
+        sample_stream_seq_kernel<<<nplans, 128, smem_seq, st>>>(d_bits, d_rowcum, W, H, d_plans, st64, n, reinterpret_cast<short2 *>(d_samples),
+                                                               reinterpret_cast<unsigned long long *>(d_state_out), d_carry);
+    } else {
         set_error("sample stream of n=%d does not fit shared memory", n);
         return RRTK_ERR_CAPACITY;
     }
-    RRTK_CUDA(cudaFuncSetAttribute(sample_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sample_stream_kernel<<<nplans, 128, smem, st>>>(d_bits, d_rowcum, W, H, d_plans,
-                                                    reinterpret_cast<const unsigned long long *>(d_state), n,
-                                                    reinterpret_cast<short2 *>(d_samples),
-                                                    reinterpret_cast<unsigned long long *>(d_state_out), d_carry);
     RRTK_CUDA(cudaGetLastError());
     return RRTK_OK;
 }

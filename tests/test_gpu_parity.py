@@ -217,6 +217,52 @@ def test_sampler_rejection_path(ctx):
     assert np.array_equal(got[0].astype(np.int64), O.sample_stream(og, 6000, 5))
 
 
+def test_sampler_with_many_rejections(ctx):
+    """nfree = 3700^2: 2^32 mod nfree is large, so one draw in ~430 is rejected -- ~19 rejections at n = 8000 (handled by
+    the parallel compaction) and ~65 at n = 28000 (around the slack of the raw window, so some seeds take the sequential
+    fallback).  Both must reproduce numpy's stream, including the generator state that is carried on."""
+    import torch
+    S = 3700
+    og = np.zeros((S, S), dtype=np.uint8)
+    ctx.set_grids(og[None])
+    seeds = np.arange(70, 78)
+    thr = (1 << 32) % (S * S)
+    for n in (8000, 28000):
+        got = ctx.samples(batch.make_desc(np.zeros(len(seeds), int), np.zeros((len(seeds), 2)), np.zeros((len(seeds), 2))), n,
+                          batch.seed_states(seeds))
+        nrej = []
+        for p, sd in enumerate(seeds):
+            idx = np.random.default_rng(int(sd)).integers(0, S * S, size=n)
+            assert np.array_equal(got[p].astype(np.int64), np.stack([idx // S, idx % S], axis=1)), (n, sd)
+            raw = np.random.default_rng(int(sd)).integers(0, 1 << 32, size=n + 200, dtype=np.uint64)   # raw 32-bit stream
+            nrej.append(int((((raw * np.uint64(S * S)) & np.uint64(0xffffffff)) < thr)[:n].sum()))
+        assert max(nrej) > 5
+        if n == 28000:
+            assert min(nrej) <= 62 < max(nrej)                          # both the compaction and the fallback are exercised
+    # carried generator state across two calls of odd length
+    db = batch.DeviceBatch("standard", S, S, 4001).set_worlds_host(og[None])
+    A = len(seeds)
+    db.set_plans(batch.make_desc(np.zeros(A, int), np.zeros((A, 2)), np.zeros((A, 2))))
+    state = torch.from_numpy(batch.seed_states(seeds).view(np.int64)).cuda()
+    carry = torch.zeros((A, 2), dtype=torch.int32, device="cuda")
+    smp = torch.empty((A, 4001, 2), dtype=torch.int16, device="cuda")
+    gens = [np.random.default_rng(int(sd)) for sd in seeds]
+    for call in range(3):
+        _lib.check(db.L.rrtk_sample_streams_carry(db.bits.data_ptr(), db.rowcum.data_ptr(), S, S, db.desc.data_ptr(), A, state.data_ptr(),
+                                                  carry.data_ptr(), 4001, smp.data_ptr(), torch.cuda.current_stream().cuda_stream), "carry")
+        got = smp.cpu().numpy().astype(np.int64)
+        for a in range(A):
+            idx = gens[a].integers(0, S * S, size=4001)
+            assert np.array_equal(got[a], np.stack([idx // S, idx % S], axis=1)), (call, a)
+        for a in range(A):                                                # generator state equals numpy's
+            stt = gens[a].bit_generator.state
+            want = [stt["state"]["state"] >> 64, stt["state"]["state"] & ((1 << 64) - 1)]
+            have = [int(v) & ((1 << 64) - 1) for v in state[a, :2].cpu().numpy()]
+            assert have == want and int(carry[a, 0]) == stt["has_uint32"]
+            if stt["has_uint32"]:
+                assert (int(carry[a, 1]) & 0xffffffff) == stt["uinteger"]
+
+
 # ---- K7: whole plans ----------------------------------------------------------------------------------
 def run_golden(ctx, g):
     ctx.set_grids(g["og"][None])
