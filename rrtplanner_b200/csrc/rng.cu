@@ -62,20 +62,29 @@ struct Pcg64 {
     }
 };
 
-__device__ __forceinline__ short2 rank_to_cell(const uint32_t *__restrict__ g, const int *__restrict__ rowcum, int W, int TY, int k)
+// rowcum may live in shared memory (the parallel kernel stages it) or in global memory
+__device__ __forceinline__ short2 rank_to_cell(const uint32_t *__restrict__ g, const int *rowcum, int W, int TY, int k)
 {
     int lo = 0, hi = W;                    // largest x with rowcum[x] <= k
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(rowcum + mid) <= k) lo = mid; else hi = mid;
+        if (rowcum[mid] <= k) lo = mid; else hi = mid;
     }
-    int rem = k - __ldg(rowcum + lo);
+    int rem = k - rowcum[lo];
     int y = 0;
-    for (int ty = 0; ty < TY; ++ty) {
-        const uint32_t fr = ~__ldg(g + word_index(lo, ty << 5, TY));
-        const int c = __popc(fr);
-        if (rem < c) { y = (ty << 5) + __fns(fr, 0, rem + 1); break; }
-        rem -= c;
+    const uint32_t *row = g + word_index(lo, 0, TY);        // word of tile (lo >> 5, ty) is row[ty << 5]
+    for (int t0 = 0; t0 < TY; t0 += 4) {                    // four independent loads in flight per step
+        uint32_t fr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fr[u] = (t0 + u < TY) ? ~__ldg(row + ((t0 + u) << 5)) : 0u;
+        bool done = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int c = __popc(fr[u]);
+            if (!done && rem < c) { y = ((t0 + u) << 5) + __fns(fr[u], 0, rem + 1); done = true; }
+            if (!done) rem -= c;
+        }
+        if (done) break;
     }
     return make_short2((short)lo, (short)y);
 }
@@ -131,12 +140,14 @@ sample_stream_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ 
     extern __shared__ uint32_t s_mem[];
     uint32_t *s_rank = s_mem;                    // n bounded draws
     uint32_t *s_raw = s_mem + n;                 // raw 32-bit values in the order numpy's next_uint32 hands them out
+    int *s_rowcum = reinterpret_cast<int *>(s_mem + 2 * n + kRawSlack + 4);      // W + 1 row offsets of this plan's world
     __shared__ int s_warp[kSampleThreads / 32];
     __shared__ int s_consumed;                   // raw values used up by the n draws (-1: not enough generated)
     const int plan = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int world = plans[plan].world;
     const int *rc = rowcum + (size_t)world * (W + 1);
     const uint32_t nfree = (uint32_t)__ldg(rc + W);
+    for (int x = tid; x <= W; x += kSampleThreads) s_rowcum[x] = __ldg(rc + x);    // visible after the barriers below
     Pcg64 g0;
     g0.hi = state[4 * plan]; g0.lo = state[4 * plan + 1];
     g0.inc_hi = state[4 * plan + 2]; g0.inc_lo = state[4 * plan + 3];
@@ -220,7 +231,7 @@ sample_stream_kernel(const uint32_t *__restrict__ bits, const int *__restrict__ 
     const uint32_t *g = bits + (size_t)world * grid_words(W, H);
     const int TY = tiles_y(H);
     short2 *out = samples + (size_t)plan * n;
-    for (int i = tid; i < n; i += kSampleThreads) out[i] = rank_to_cell(g, rc, W, TY, (int)s_rank[i]);
+    for (int i = tid; i < n; i += kSampleThreads) out[i] = rank_to_cell(g, s_rowcum, W, TY, (int)s_rank[i]);
 }
 
 // n too large for the raw window in shared memory: thread 0 runs the generator sequentially
@@ -258,7 +269,7 @@ int sample_streams_launch(const uint32_t *d_bits, const int32_t *d_rowcum, int W
                           uint64_t *d_state_out, uint32_t *d_carry)
 {
     if (nplans == 0 || n == 0) return RRTK_OK;
-    const size_t smem = ((size_t)2 * n + kRawSlack + 4) * 4;      // bounded draws + raw 32-bit values
+    const size_t smem = ((size_t)2 * n + kRawSlack + 4 + W + 1) * 4;      // bounded draws + raw 32-bit values + row offsets
     const size_t smem_seq = (size_t)n * 4;
     const unsigned long long *st64 = reinterpret_cast<const unsigned long long *>(d_state);
     if (smem <= (size_t)optin) {
