@@ -42,7 +42,7 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
     if (n + 1 > 65535) return false;                       // uint16 list entries
     ScanShape s;
     s.K = env_int("RRTK_PLAN_K", 8);
-    if (s.K != 4 && s.K != 8) return false;
+    if (s.K != 4 && s.K != 8 && s.K != 16) return false;
     int T = threads > 0 ? threads : env_int("RRTK_PLAN_T", 0);
     if (T <= 0) T = n < 2048 ? 64 : n < 5120 ? 128 : n < 32768 ? 256 : 512;   // measured: scripts/sweep_tk.sh
     if (T != 64 && T != 128 && T != 160 && T != 256 && T != 512) return false;

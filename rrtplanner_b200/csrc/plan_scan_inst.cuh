@@ -33,6 +33,9 @@ int RRTK_SCAN_FN(const PlanParams &P, int nplans, int T, int K, size_t smem, cud
     switch (K) {
         case 4: return scan_launch_k<4>(P, nplans, T, smem, st);
         case 8: return scan_launch_k<8>(P, nplans, T, smem, st);
+#ifdef RRTK_SCAN_K16
+        case 16: return scan_launch_k<16>(P, nplans, T, smem, st);
+#endif
     }
     set_error("packed-key plan kernel: unsupported samples per round %d", K);
     return RRTK_ERR_INVALID;
