@@ -194,3 +194,83 @@ def test_bad_arguments_raise(ctx):
                   heads=np.full((1, 10), 7, dtype=np.uint8))
     with pytest.raises(ValueError):
         ctx.dubins_collision(np.array([[0, 0, 0, 40, 3, 0]]), 16, 2.0, 1.0)
+
+
+@pytest.mark.parametrize("model", ["dubins", "euclid"])
+def test_full_size_batch_properties(model):
+    """BASELINE cfg5 at full size (1024 plans, 512 x 512 worlds, n = 5000, r = 50): properties that need no oracle.
+    Costs are consistent with the edge lengths after all rewires, the graph is a tree rooted at the start, every edge
+    parent -> child is free when re-tested by the stand-alone kernels (rrtk_dubins_collision / rrtk_collision_segments),
+    stored Dubins lengths equal rrtk_dubins_paths, and the first plans equal the specification bit for bit."""
+    import torch
+    from rrtplanner_b200 import batch
+    W = H = 512
+    n, nh, rho, ds, r, P = 5000, 16, 6.0, 1.0, 50.0, 1024
+    db = batch.DeviceBatch2(model, W, H, n, r_rewire=r, nheadings=nh, rho=rho, ds=ds, device=0)
+    db.gen_worlds([worlds.world_seed(p) for p in range(P)])
+    nfree = db.nfree()
+    rng = np.random.default_rng(3)
+    # start / goal: two free cells per world, taken from the device sampler's own stream
+    pair = batch.DeviceBatch("star", W, H, 2, device=0)
+    pair.bits, pair.rowcum = db.bits, db.rowcum
+    pair.set_plans(batch.make_desc(np.arange(P), np.zeros((P, 2)), np.zeros((P, 2))))
+    pair.seed_samples(5000 + np.arange(P))
+    sg = pair.samples.cpu().numpy().astype(np.int64)
+    hs = rng.integers(0, nh, size=(P, 2))
+    starts = np.concatenate([sg[:, 0], hs[:, :1]], axis=1)
+    goals = np.concatenate([sg[:, 1], hs[:, 1:]], axis=1)
+    db.set_plans(batch.make_desc2(np.arange(P), starts, goals))
+    db.seed_samples(np.arange(P))
+    if model == "dubins":
+        db.seed_heads(9000 + np.arange(P))
+    res = db.run().download()
+    assert (res.stat("overflow") == 0).all() and (nfree > 0).all()
+    j, found = res.stat("j"), res.stat("found")
+    top = j + found
+    rows = np.arange(n + 1)[None, :]
+    live = (rows < top[:, None]) & (rows >= 1)
+    par = np.where(live, res.parent, 0)
+    pc = np.take_along_axis(res.cost, par, axis=1)
+    assert np.array_equal((pc + res.elen)[live].view(np.int64), res.cost[live].view(np.int64))      # cost = parent's cost + edge length
+    assert (res.parent[:, 0] == -1).all() and (res.cost[:, 0] == 0).all()
+    assert ((res.parent[live] >= 0) & (res.parent[live] < np.broadcast_to(j[:, None], live.shape)[live])).all()
+    depth = np.zeros_like(res.parent)                                                                # every vertex reaches the root
+    cur = par.copy()
+    for _ in range(n):
+        nz = cur > 0
+        if not nz.any():
+            break
+        depth += nz
+        cur = np.where(nz, np.take_along_axis(par, cur, axis=1), 0)
+    assert not (cur > 0).any()
+    assert np.median(res.stat("rewires")) > 1000
+    # every edge re-tested by the stand-alone kernels, parent -> child
+    pi, vi = np.nonzero(live)
+    ctx = _lib.Context()
+    try:
+        for lo in range(0, P, 128):
+            sel = (pi >= lo) & (pi < lo + 128)
+            p_, v_ = pi[sel], vi[sel]
+            u_ = res.parent[p_, v_]
+            ctx.set_grids(db.og[lo: lo + 128].cpu().numpy())
+            for q in range(lo, min(lo + 128, P)):                          # the host-buffer forms take one world per call
+                m = p_ == q
+                if model == "dubins":
+                    qq = np.stack([res.pts[q, u_[m], 0], res.pts[q, u_[m], 1], res.head[q, u_[m]], res.pts[q, v_[m], 0],
+                                   res.pts[q, v_[m], 1], res.head[q, v_[m]]], axis=1).astype(np.int32)
+                    assert ctx.dubins_collision(qq, nh, rho, ds, world=q - lo).all()
+                    if q % 64 == 0:
+                        assert np.array_equal(ctx.dubins_paths(qq, nh, rho)[2].view(np.int64), res.elen[q, v_[m]].view(np.int64))
+                else:
+                    seg = np.concatenate([res.pts[q, u_[m]], res.pts[q, v_[m]]], axis=1).astype(np.int32)
+                    assert ctx.collision(seg, world=q - lo).all()
+    finally:
+        ctx.close()
+    smp = db.samples.cpu().numpy().astype(np.int64)
+    hd = db.heads.cpu().numpy().astype(np.int64) if model == "dubins" else np.zeros((P, n), dtype=np.int64)
+    ogs = db.og[:3].cpu().numpy()
+    for p in range(3):
+        want = R.plan(model, ogs[p], n, starts[p], goals[p], np.concatenate([smp[p], hd[p][:, None]], axis=1), star=True, rewire=True,
+                      r_rewire=r, nh=nh, rho=rho, ds=ds)
+        _compare((res.pts[p], res.head[p], res.cost[p], res.elen[p], res.parent[p],
+                  dict(zip(_lib.STAT2_NAMES, (int(v) for v in res.stats[p])))), want, model)
