@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             if (MODEL == RRTK_MODEL_DUBINS)
                 dubins_rebuild(px(pnew) - px(pv), py(pnew) - py(pv), shead[vn], qh, P.NH, P.rho, tab, word1[i], w);
             const bool ok = Edge<MODEL>::is_free(P, bits, pv, shead[vn], pnew, w, lane);
+            __syncwarp();                            // every lane has read flag[i] before lane 0 rewrites it
             if (lane == 0) {
                 ++my_checks;
                 if (ok) { flag[i] = 2; atomicMin(&s_best, (unsigned long long)__double_as_longlong(cn)); }
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 if (MODEL == RRTK_MODEL_DUBINS)
                     dubins_rebuild(px(pv) - px(pnew), py(pv) - py(pnew), qh, shead[vn], P.NH, P.rho, tab, word2[i], w);
                 const bool ok = Edge<MODEL>::is_free(P, bits, pnew, qh, pv, w, lane);
+                __syncwarp();                        // every lane has read flag[i] before lane 0 rewrites it
                 if (lane == 0) { ++my_checks; flag[i] = ok ? 2 : 0; }
             }
             __syncthreads();
