@@ -329,6 +329,23 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
                "edge_length_evals_per_s": float(st[:, 8].sum()) / (ms / 1e3), "edge_tests_per_s": float(st[:, 3].sum()) / (ms / 1e3),
                "smem_bytes_per_block": smem, "blocks_per_sm": blocks, "overflow": int(st[:, 9].sum()),
                "kernel": "rrtk::plan_rewire_kernel<%s, T=%d>" % (model.upper(), threads or 256)}
+        # end to end through the host-buffer C ABI: grids, descriptors, PCG64 states and headings up, every tree down
+        ctx = _lib.Context()
+        og_host = db.og.cpu().numpy()
+        desc_h = batch.make_desc2(np.arange(plans), np.concatenate([starts, hs[:, :1]], axis=1), np.concatenate([goals, hs[:, 1:]], axis=1))
+        heads_h = db.heads.cpu().numpy() if model == "dubins" else None
+        t_best = None
+        for rep in range(2):
+            t0 = time.perf_counter()
+            ctx.set_grids(og_host)
+            r_host = ctx.plan2(db.cfg, desc_h, N_ITER, states=batch.seed_states(np.arange(plans)), heads=heads_h)
+            dt = time.perf_counter() - t0
+            t_best = dt if t_best is None else min(t_best, dt)
+        ctx.close()
+        rec["e2e"] = {"value": plans / t_best, "unit": "plans/s", "api": "rrtk_ctx_set_grids + rrtk_ctx_plan2 (seed mode), host buffers, not pipelined",
+                      "h2d_bytes_per_step": int(plans * (W * H + 64 + 32 + (N_ITER if model == "dubins" else 0))),
+                      "d2h_bytes_per_step": int(plans * ((N_ITER + 1) * 25 + _lib.STAT_COUNT * 8)),
+                      "matches_device_arm": bool(np.array_equal(r_host[4], db.out["parent"].cpu().numpy()))}
         out["dubins_rrtstar" if model == "dubins" else "euclid_rrtstar_with_rewire"] = rec
         keep[model] = (db, starts, goals, hs)
     if cpu:
