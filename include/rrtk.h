@@ -243,6 +243,10 @@ typedef struct {
     double r_rewire;
     double rho;              /* DUBINS: turning radius in cells, > 0 */
     double ds;               /* DUBINS: arc-length step of the collision samples in cells, > 0 */
+    const void *dubins_table; /* DUBINS, optional (NULL = none): DEVICE memo made by rrtk_dubins_table_build for the same
+                                nheadings and rho; edges whose |dx|, |dy| <= table_radius are looked up instead of evaluated */
+    int32_t table_radius;
+    int32_t reserved;
 } rrtk_plan2_cfg;
 
 /* statistics slots rrtk_plan2_batch writes (RRTK_STAT_COUNT int64 per plan; J / VGOAL / FOUND / CHECKS as above) */
@@ -273,6 +277,13 @@ int rrtk_plan2_batch(const rrtk_plan2_cfg *cfg, const uint32_t *d_bits, int W, i
                      double *d_cost, double *d_elen, int32_t *d_parent, int64_t *d_stats, void *d_scratch, int threads,
                      void *stream);
 int rrtk_plan2_footprint(int n, int threads, int *smem_bytes, int *blocks_per_sm);
+
+/* Memo of the Dubins primitive: with integer cells and indexed headings the shortest path depends only on
+ * (dx, dy, h0, h1), so all of them with |dx|, |dy| <= radius fit a table (radius 50, 16 headings: 2.6 M entries, 86 MB,
+ * the 21 MB of lengths stay L2-resident) that every plan of a batch shares; the entries are what rrtk_dubins_paths
+ * returns, bit for bit.  rrtk_ctx_plan2 builds and caches one on its own. */
+size_t rrtk_dubins_table_bytes(int radius, int nheadings);
+int rrtk_dubins_table_build(int radius, int nheadings, double rho, void *d_table, void *stream);
 
 /* Dubins primitive, batched.  d_q: nq x (x0, y0, h0, x1, y1, h1) int32.  Outputs (each optional): d_word 0..5 =
  * LSL RSR LSR RSL RLR LRL, d_tpq nq x 3 segment lengths in units of rho, d_len path length in cells. */

@@ -22,10 +22,10 @@ MODEL_EUCLID, MODEL_DUBINS = 0, 1
 STAT2_NAMES = ("j", "vgoal", "found", "checks", "accepted", "rewires", "propagated", "ring_members", "len_evals", "overflow",
                "reserved0", "reserved1")
 DUBINS_WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
-# numpy mirror of rrtk_plan2_cfg (40 bytes)
+# numpy mirror of rrtk_plan2_cfg (56 bytes)
 PLAN2_CFG = np.dtype([("model", "<i4"), ("star", "<i4"), ("rewire", "<i4"), ("nheadings", "<i4"), ("r_rewire", "<f8"),
-                      ("rho", "<f8"), ("ds", "<f8")], align=True)
-assert PLAN2_CFG.itemsize == 40
+                      ("rho", "<f8"), ("ds", "<f8"), ("dubins_table", "<u8"), ("table_radius", "<i4"), ("reserved", "<i4")], align=True)
+assert PLAN2_CFG.itemsize == 56
 
 
 def plan2_cfg(model, star, rewire, r_rewire=0.0, nheadings=1, rho=1.0, ds=1.0) -> np.ndarray:
@@ -90,6 +90,8 @@ SIGNATURES = {
     "rrtk_ctx_within_f64": (_i, [_vp, _vp, _i, _vp, _i, _d, _i, _vp, _vp]),
     "rrtk_ctx_near_order": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "rrtk_ctx_near_order_f64": (_i, [_vp, _vp, _i, _d, _d, _vp]),
+    "rrtk_dubins_table_bytes": (_sz, [_i, _i]),
+    "rrtk_dubins_table_build": (_i, [_i, _i, _d, _vp, _vp]),
     "rrtk_plan2_scratch_bytes": (_sz, [_i, _i]),
     "rrtk_plan2_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rrtk_plan2_footprint": (_i, [_i, _i, _vp, _vp]),

@@ -345,13 +345,24 @@ class DeviceBatch2(DeviceBatch):
     """HBM-resident batch of K8 plans (RRT* with a firing rewire, Dubins RRT / RRT*; include/rrtk.h rrtk_plan2_batch)."""
 
     def __init__(self, model, W: int, H: int, n: int, r_rewire=0.0, star=True, rewire=True, nheadings=16, rho=6.0, ds=1.0,
-                 device=None, threads: int = 0):
+                 device=None, threads: int = 0, use_table: bool = True):
         super().__init__("star" if star else "standard", W, H, n, r_rewire=r_rewire, device=device, threads=threads)
         m = {"euclid": _lib.MODEL_EUCLID, "dubins": _lib.MODEL_DUBINS}[model] if isinstance(model, str) else int(model)
         self.cfg = _lib.plan2_cfg(m, star, rewire, r_rewire, nheadings if m == _lib.MODEL_DUBINS else 1, rho, ds)
         self.nheadings = int(self.cfg["nheadings"][0])
         self.heads = None
         self.scratch = None
+        self.table = None
+        if use_table and m == _lib.MODEL_DUBINS and star and 1.0 <= float(r_rewire) <= 1024.0:
+            # memo of the Dubins primitive over the rewire radius, shared by every plan of the batch
+            R = int(np.ceil(float(r_rewire)))
+            nbytes = int(self.L.rrtk_dubins_table_bytes(R, self.nheadings))
+            if 0 < nbytes <= (256 << 20):
+                self.table = self._empty((nbytes,), self.torch.uint8)
+                with self.torch.cuda.device(self.dev):
+                    _lib.check(self.L.rrtk_dubins_table_build(R, self.nheadings, float(rho), self._p(self.table), self._stream()),
+                               "dubins_table_build")
+                self.cfg["dubins_table"], self.cfg["table_radius"] = self.table.data_ptr(), R
 
     def set_plans(self, desc: np.ndarray):
         t = self.torch

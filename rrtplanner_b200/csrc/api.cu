@@ -53,6 +53,8 @@ int plan2_launch(const rrtk_plan2_cfg &, const uint32_t *, int, int, const rrtk_
 size_t plan2_scratch_bytes(int, int);
 int plan2_footprint(int, int, int, int, int *, int *);
 int dubins_paths_launch(const int32_t *, int64_t, int, double, int32_t *, double *, double *, cudaStream_t);
+size_t dubins_table_bytes(int, int);
+int dubins_table_launch(int, int, double, void *, int, cudaStream_t);
 int dubins_walk_launch(const uint32_t *, int, int, const int32_t *, const int32_t *, int64_t, int, double, double, uint8_t *, int,
                        double *, int32_t *, cudaStream_t);
 
@@ -131,6 +133,9 @@ struct rrtk_ctx {
     DevBuf pts, cost, parent, stats, ell;       // plan outputs
     DevBuf a, b, c, d, e;                       // query scratch
     DevBuf heads, head_out, elen, scratch2;     // K8 (rrtk_ctx_plan2)
+    DevBuf dtable;                              // memo of the Dubins primitive, valid for (dt_R, dt_NH, dt_rho)
+    int dt_R = 0, dt_NH = 0;
+    double dt_rho = 0.0;
     PipeSlot pipe[kPipeSlots];
 };
 
@@ -356,7 +361,7 @@ int rrtk_destroy(rrtk_ctx *c)
     if (!c) return RRTK_OK;
     DevBuf *all[] = {&c->og, &c->bits, &c->rowcum, &c->plans, &c->samples, &c->state, &c->balls, &c->pts,
                      &c->cost, &c->parent, &c->stats, &c->ell, &c->a, &c->b, &c->c, &c->d, &c->e,
-                     &c->heads, &c->head_out, &c->elen, &c->scratch2};
+                     &c->heads, &c->head_out, &c->elen, &c->scratch2, &c->dtable};
     for (DevBuf *b : all) b->release();
     for (PipeSlot &p : c->pipe) {
         DevBuf *pb[] = {&p.og, &p.bits, &p.rowcum, &p.plans, &p.samples, &p.state, &p.balls, &p.pts, &p.cost, &p.parent, &p.stats, &p.ell};
@@ -758,6 +763,7 @@ static int check_plan2_cfg(const rrtk_plan2_cfg *cfg)
     RRTK_REQUIRE(cfg, "rrtk_plan2: null configuration");
     RRTK_REQUIRE(cfg->model == RRTK_MODEL_EUCLID || cfg->model == RRTK_MODEL_DUBINS, "rrtk_plan2: unknown model");
     RRTK_REQUIRE(cfg->r_rewire == cfg->r_rewire, "rrtk_plan2: NaN radius");
+    RRTK_REQUIRE(!cfg->dubins_table || (cfg->table_radius >= 1 && cfg->table_radius <= 1024), "rrtk_plan2: table_radius out of range");
     if (cfg->model == RRTK_MODEL_DUBINS) {
         RRTK_REQUIRE(cfg->nheadings >= 1 && cfg->nheadings <= 255, "rrtk_plan2: need 1 <= nheadings <= 255");
         RRTK_REQUIRE(cfg->rho > 0.0 && cfg->ds > 0.0 && cfg->rho < 1e9 && cfg->ds < 1e9, "rrtk_plan2: need rho > 0 and ds > 0");
@@ -770,6 +776,20 @@ static int check_dubins_args(int nheadings, double rho, double ds)
     RRTK_REQUIRE(nheadings >= 1 && nheadings <= 255, "dubins: need 1 <= nheadings <= 255");
     RRTK_REQUIRE(rho > 0.0 && rho < 1e9 && ds > 0.0 && ds < 1e9, "dubins: need rho > 0 and ds > 0");
     return RRTK_OK;
+}
+
+size_t rrtk_dubins_table_bytes(int radius, int nheadings)
+{
+    return (radius < 1 || radius > 1024 || nheadings < 1 || nheadings > 255) ? 0 : dubins_table_bytes(radius, nheadings);
+}
+
+int rrtk_dubins_table_build(int radius, int nheadings, double rho, void *d_table, void *stream)
+{
+    RRTK_REQUIRE(d_table && radius >= 1 && radius <= 1024, "rrtk_dubins_table_build: need a table and 1 <= radius <= 1024");
+    RRTK_TRY(check_dubins_args(nheadings, rho, 1.0));
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return dubins_table_launch(radius, nheadings, rho, d_table, d->sms, (cudaStream_t)stream);
 }
 
 size_t rrtk_plan2_scratch_bytes(int nplans, int n) { return (nplans < 0 || n < 1) ? 0 : plan2_scratch_bytes(nplans, n); }
@@ -890,6 +910,23 @@ int rrtk_ctx_plan2(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc 
                                        nplans, c->state.as<uint64_t>(), n, c->samples.as<int16_t>(), d->optin, st));
     }
     if (h_heads) RRTK_CUDA(cudaMemcpyAsync(c->heads.p, h_heads, total, cudaMemcpyHostToDevice, st));
+    rrtk_plan2_cfg use = *cfg;
+    if (dub && cfg->star && !cfg->dubins_table && cfg->r_rewire >= 1.0 && cfg->r_rewire <= 1024.0) {
+        // memo of the primitive over the rewire radius, kept in the context while (radius, headings, rho) stay the same
+        const int R = (int)ceil(cfg->r_rewire);
+        const size_t bytes = dubins_table_bytes(R, cfg->nheadings);
+        if (bytes <= ((size_t)256 << 20)) {
+            if (c->dt_R != R || c->dt_NH != cfg->nheadings || c->dt_rho != cfg->rho || !c->dtable.p) {
+                RRTK_CUDA(cudaStreamSynchronize(st));
+                RRTK_TRY(c->dtable.reserve(bytes));
+                RRTK_TRY(rrtk_dubins_table_build(R, cfg->nheadings, cfg->rho, c->dtable.p, st));
+                c->dt_R = R; c->dt_NH = cfg->nheadings; c->dt_rho = cfg->rho;
+            }
+            use.dubins_table = c->dtable.p;
+            use.table_radius = R;
+        }
+    }
+    cfg = &use;
     RRTK_TRY(rrtk_plan2_batch(cfg, c->bits.as<uint32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(), nplans, n, c->samples.as<int16_t>(),
                               h_heads ? c->heads.as<uint8_t>() : nullptr, c->pts.as<int16_t>(), c->head_out.as<uint8_t>(),
                               c->cost.as<double>(), c->elen.as<double>(), c->parent.as<int32_t>(), c->stats.as<int64_t>(),

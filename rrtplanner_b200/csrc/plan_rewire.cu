@@ -47,13 +47,25 @@ struct Plan2Params {
     double *gcost;          // scratch: (n + 1) doubles per plan
     uint16_t *queue;        // scratch: (n + 1) vertex ids per plan
     int ring_cap;
+    // optional memo of the Dubins primitive (rrtk_dubins_table_build): shortest path for every displacement in
+    // [-tR, tR]^2 and every heading pair, entry ((dx + tR) * (2 tR + 1) + dy + tR) * NH * NH + h0 * NH + h1
+    const double *tlen;     // length
+    const double *ttpq;     // (t, p, q)
+    const uint8_t *tword;   // word
+    int tR;
 };
+
+__host__ __device__ __forceinline__ size_t dubins_table_entries(int R, int NH) { return (size_t)(2 * R + 1) * (2 * R + 1) * NH * NH; }
+__device__ __forceinline__ size_t dubins_table_index(int dx, int dy, int h0, int h1, int R, int NH)
+{
+    return ((size_t)((dx + R) * (2 * R + 1) + dy + R) * NH + h0) * NH + h1;
+}
 
 constexpr uint16_t kNil = 0xffffu;
 
 template <int MODEL>
 struct Edge {
-    // length of a -> b
+    // length of a -> b (Dubins: w.word and w.len are set; t, p, q only when the path was computed, see path())
     static __device__ __forceinline__ double length(const Plan2Params &P, const double2 *tab, uint32_t pa, int ha, uint32_t pb, int hb,
                                                     DubinsPath &w)
     {
@@ -61,10 +73,33 @@ struct Edge {
             w.word = 0;
             return __dsqrt_rn((double)dist2(pa, px(pb), py(pb)));
         }
-        dubins_shortest(px(pb) - px(pa), py(pb) - py(pa), ha, hb, P.NH, P.rho, tab, w);
+        const int dx = px(pb) - px(pa), dy = py(pb) - py(pa);
+        if (P.tlen && abs(dx) <= P.tR && abs(dy) <= P.tR) {           // memoised: one L2-resident load instead of ~1.5 k FP64 operations
+            const size_t i = dubins_table_index(dx, dy, ha, hb, P.tR, P.NH);
+            w.word = (int)__ldg(P.tword + i);
+            w.len = __ldg(P.tlen + i);
+            w.t = w.p = w.q = CUDART_NAN;
+            return w.len;
+        }
+        dubins_shortest(dx, dy, ha, hb, P.NH, P.rho, tab, w);
         return w.len;
     }
-    // warp-cooperative: is a -> b free (w = the path length() returned for the same pair)
+    // (t, p, q) of the word length() chose for the same pair (same bits either way: the table was filled by dubins_shortest)
+    static __device__ __forceinline__ void path(const Plan2Params &P, const double2 *tab, uint32_t pa, int ha, uint32_t pb, int hb, int word,
+                                                DubinsPath &w)
+    {
+        if (MODEL == RRTK_MODEL_EUCLID) { w.word = 0; return; }
+        const int dx = px(pb) - px(pa), dy = py(pb) - py(pa);
+        if (P.tlen && abs(dx) <= P.tR && abs(dy) <= P.tR) {
+            const size_t i = dubins_table_index(dx, dy, ha, hb, P.tR, P.NH);
+            w.word = word;
+            w.len = __ldg(P.tlen + i);
+            w.t = __ldg(P.ttpq + 3 * i); w.p = __ldg(P.ttpq + 3 * i + 1); w.q = __ldg(P.ttpq + 3 * i + 2);
+            return;
+        }
+        dubins_rebuild(dx, dy, ha, hb, P.NH, P.rho, tab, word, w);
+    }
+    // warp-cooperative: is a -> b free (w = the path of path() for the same pair)
     static __device__ __forceinline__ bool is_free(const Plan2Params &P, const uint32_t *bits, uint32_t pa, int ha, uint32_t pb,
                                                    const DubinsPath &w, int lane)
     {
@@ -278,6 +313,8 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             w0.word = __shfl_sync(RRTK_FULL, w0.word, 0);
             w0.t = __shfl_sync(RRTK_FULL, w0.t, 0); w0.p = __shfl_sync(RRTK_FULL, w0.p, 0);
             w0.q = __shfl_sync(RRTK_FULL, w0.q, 0); w0.len = __shfl_sync(RRTK_FULL, w0.len, 0);
+            if (MODEL == RRTK_MODEL_DUBINS && w0.t != w0.t)      // length came from the memo: fetch the path's (t, p, q)
+                Edge<MODEL>::path(P, tab, spts[vnear], shead[vnear], pnew, qh, w0.word, w0);
             const bool ok = Edge<MODEL>::is_free(P, bits, spts[vnear], shead[vnear], pnew, w0, lane);
             if (lane == 0) {
                 ++my_checks;
@@ -313,8 +350,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             const uint32_t pv = spts[vn];
             DubinsPath w;
             w.word = 0;
-            if (MODEL == RRTK_MODEL_DUBINS)
-                dubins_rebuild(px(pnew) - px(pv), py(pnew) - py(pv), shead[vn], qh, P.NH, P.rho, tab, word1[i], w);
+            Edge<MODEL>::path(P, tab, pv, shead[vn], pnew, qh, word1[i], w);
             const bool ok = Edge<MODEL>::is_free(P, bits, pv, shead[vn], pnew, w, lane);
             __syncwarp();                            // every lane has read flag[i] before lane 0 rewrites it
             if (lane == 0) {
@@ -363,8 +399,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 const uint32_t pv = spts[vn];
                 DubinsPath w;
                 w.word = 0;
-                if (MODEL == RRTK_MODEL_DUBINS)
-                    dubins_rebuild(px(pv) - px(pnew), py(pv) - py(pnew), qh, shead[vn], P.NH, P.rho, tab, word2[i], w);
+                Edge<MODEL>::path(P, tab, pnew, qh, pv, shead[vn], word2[i], w);
                 const bool ok = Edge<MODEL>::is_free(P, bits, pnew, qh, pv, w, lane);
                 __syncwarp();                        // every lane has read flag[i] before lane 0 rewrites it
                 if (lane == 0) { ++my_checks; flag[i] = ok ? 2 : 0; }
@@ -439,8 +474,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
         if ((unsigned long long)__double_as_longlong(cg) > s_best) continue;        // a cheaper free edge is known
         DubinsPath w;
         w.word = 0;
-        if (MODEL == RRTK_MODEL_DUBINS)
-            dubins_rebuild(px(pgoal) - px(spts[v]), py(pgoal) - py(spts[v]), shead[v], goal_h, P.NH, P.rho, tab, (int)(int8_t)first[v], w);
+        Edge<MODEL>::path(P, tab, spts[v], shead[v], pgoal, goal_h, (int)(int8_t)first[v], w);
         const bool ok = Edge<MODEL>::is_free(P, bits, spts[v], shead[v], pgoal, w, lane);
         if (lane == 0) {
             ++my_checks;
@@ -554,6 +588,14 @@ int plan2_launch(const rrtk_plan2_cfg &cfg, const uint32_t *d_bits, int W, int H
     uintptr_t s = (reinterpret_cast<uintptr_t>(d_scratch) + 15) & ~(uintptr_t)15;
     P.gcost = reinterpret_cast<double *>(s);
     P.queue = reinterpret_cast<uint16_t *>(P.gcost + (size_t)nplans * (n + 1));
+    P.tlen = nullptr; P.ttpq = nullptr; P.tword = nullptr; P.tR = 0;
+    if (cfg.model == RRTK_MODEL_DUBINS && cfg.dubins_table && cfg.table_radius > 0) {
+        const size_t N = dubins_table_entries(cfg.table_radius, cfg.nheadings);
+        P.tlen = reinterpret_cast<const double *>(cfg.dubins_table);
+        P.ttpq = P.tlen + N;
+        P.tword = reinterpret_cast<const uint8_t *>(P.ttpq + 3 * N);
+        P.tR = cfg.table_radius;
+    }
     P.ring_cap = plan2_ring_cap(n);
     const size_t smem = plan2_smem(n, P.ring_cap);
     if (smem + 1024 > (size_t)optin) {
@@ -624,6 +666,45 @@ __global__ void dubins_walk_kernel(const uint32_t *bits, size_t words_per_grid, 
         }
         if (lane == 0) count[i] = (int)(ns + 1);
     }
+}
+
+// memo of the primitive: one thread per (displacement, heading pair)
+__global__ void dubins_table_kernel(int R, int NH, double rho, double *tlen, double *ttpq, uint8_t *tword)
+{
+    __shared__ double2 tab[256];
+    const double dth = DM_TWO_PI / (double)NH;
+    for (int h = threadIdx.x; h < NH; h += blockDim.x) {
+        double s, c;
+        dm_sincos((double)h * dth, s, c);
+        tab[h] = make_double2(s, c);
+    }
+    __syncthreads();
+    const size_t N = dubins_table_entries(R, NH);
+    const int side = 2 * R + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+        const int h1 = (int)(i % NH), h0 = (int)((i / NH) % NH);
+        const size_t cell = i / ((size_t)NH * NH);
+        const int dy = (int)(cell % side) - R, dx = (int)(cell / side) - R;
+        DubinsPath w;
+        dubins_shortest(dx, dy, h0, h1, NH, rho, tab, w);
+        tlen[i] = w.len; tword[i] = (uint8_t)w.word;
+        ttpq[3 * i] = w.t; ttpq[3 * i + 1] = w.p; ttpq[3 * i + 2] = w.q;
+    }
+}
+
+size_t dubins_table_bytes(int R, int NH) { return dubins_table_entries(R, NH) * (4 * sizeof(double) + 1) + 16; }
+
+int dubins_table_launch(int R, int NH, double rho, void *d_table, int sm_count, cudaStream_t st)
+{
+    const size_t N = dubins_table_entries(R, NH);
+    double *tlen = reinterpret_cast<double *>(d_table);
+    double *ttpq = tlen + N;
+    uint8_t *tword = reinterpret_cast<uint8_t *>(ttpq + 3 * N);
+    size_t blocks = (N + 127) / 128;
+    const size_t cap = (size_t)(sm_count > 0 ? sm_count : 148) * 64;
+    dubins_table_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 128, 0, st>>>(R, NH, rho, tlen, ttpq, tword);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
 }
 
 int dubins_paths_launch(const int32_t *d_q, int64_t nq, int NH, double rho, int32_t *d_word, double *d_tpq, double *d_len, cudaStream_t st)

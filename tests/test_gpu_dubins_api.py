@@ -131,11 +131,36 @@ def test_radius_set_overflow_is_reported_not_hidden():
         p.plan(np.array([1, 1]), np.array([60, 60]))
 
 
-@pytest.mark.parametrize("threads", [0, 128])
-def test_device_batch2_matches_the_host_buffer_call(threads):
+def test_dubins_memo_table_equals_the_primitive():
+    import torch
+    L = _lib.lib()
+    R_, nh, rho = 12, 8, 3.5
+    nbytes = int(L.rrtk_dubins_table_bytes(R_, nh))
+    N = (2 * R_ + 1) ** 2 * nh * nh
+    assert nbytes >= N * 33
+    tab = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
+    _lib.check(L.rrtk_dubins_table_build(R_, nh, rho, tab.data_ptr(), torch.cuda.current_stream().cuda_stream), "table")
+    torch.cuda.synchronize()
+    raw = tab.cpu().numpy()
+    tlen = raw[: 8 * N].view(np.float64)
+    ttpq = raw[8 * N: 32 * N].view(np.float64).reshape(N, 3)
+    tword = raw[32 * N: 33 * N]
+    side = 2 * R_ + 1
+    idx = np.arange(N)
+    h1, h0, cell = idx % nh, (idx // nh) % nh, idx // (nh * nh)
+    q = np.stack([np.zeros(N, int), np.zeros(N, int), h0, cell // side - R_, cell % side - R_, h1], axis=1)
+    word, tpq, ln = O2.dubins(q, nh, rho)
+    assert np.array_equal(tword.astype(np.int32), word)
+    assert np.array_equal(tlen.view(np.int64), ln.view(np.int64)) and np.array_equal(ttpq.view(np.int64), tpq.view(np.int64))
+    assert L.rrtk_dubins_table_bytes(0, nh) == 0 and L.rrtk_dubins_table_build(5, 300, 1.0, tab.data_ptr(), None) == -1
+
+
+@pytest.mark.parametrize("threads,use_table", [(0, True), (128, True), (0, False)])
+def test_device_batch2_matches_the_host_buffer_call(threads, use_table):
     W = H = 128
     n, nh, P = 500, 16, 5
-    db = batch.DeviceBatch2("dubins", W, H, n, r_rewire=25.0, nheadings=nh, rho=4.0, ds=1.0, device=0, threads=threads)
+    db = batch.DeviceBatch2("dubins", W, H, n, r_rewire=25.0, nheadings=nh, rho=4.0, ds=1.0, device=0, threads=threads, use_table=use_table)
+    assert (db.table is not None) == use_table
     db.gen_worlds([worlds.world_seed(w) for w in range(P)])
     ogs = db.og.cpu().numpy()
     starts = np.array([[*np.argwhere(ogs[p] == 0)[7], p % nh] for p in range(P)])
