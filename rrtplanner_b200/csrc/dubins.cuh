@@ -55,8 +55,11 @@ __device__ RRTK_DM_INLINE double dm_atan2(double y, double x)
 }
 
 // quadrant k = floor(a * 2/pi + 1/2), r = a - k * pi/2, Taylor polynomials on |r| <= pi/4
-__device__ RRTK_DM_INLINE void dm_sincos(double a, double &sn, double &cs)
+// (sin, cos) returned by value: a non-inlined function hands 16 bytes back in registers, while reference outputs would
+// go through local memory (which misses the small L1 left beside the plan blocks' shared memory)
+__device__ RRTK_DM_INLINE double2 dm_sincos2(double a)
 {
+    double sn, cs;
     const double kf = floor(a * DM_TWO_OVER_PI + 0.5);
     const double r = a - kf * DM_HALF_PI;
     const double s = r * r;
@@ -85,6 +88,12 @@ __device__ RRTK_DM_INLINE void dm_sincos(double a, double &sn, double &cs)
         case 2: sn = -ps; cs = -pc; break;
         default: sn = -pc; cs = ps; break;
     }
+    return make_double2(sn, cs);
+}
+__device__ __forceinline__ void dm_sincos(double a, double &sn, double &cs)
+{
+    const double2 r = dm_sincos2(a);
+    sn = r.x; cs = r.y;
 }
 
 // angle into [0, 2 pi); a result within 1e-9 of a full turn (an exact 0 that rounded below) snaps to 0
@@ -241,63 +250,68 @@ __device__ __noinline__ void dubins_rebuild(int dx, int dy, int h0, int h1, int 
     else out.word = -1;
 }
 
-// segment kinds of word w, 2 bits each (0 left arc, 1 straight, 2 right arc): LSL RSR LSR RSL RLR LRL
+// segment kinds of word w (0 left arc, 1 straight, 2 right arc) for LSL RSR LSR RSL RLR LRL: three 2-bit fields per word,
+// six words packed in one constant (a lookup array would live in local memory)
 __device__ __forceinline__ int dubins_seg(int word, int i)
 {
-    const unsigned codes[6] = {0u | 1u << 2 | 0u << 4, 2u | 1u << 2 | 2u << 4, 0u | 1u << 2 | 2u << 4,
-                               2u | 1u << 2 | 0u << 4, 2u | 0u << 2 | 2u << 4, 0u | 2u << 2 | 0u << 4};
-    return (int)((codes[word] >> (2 * i)) & 3u);
+    constexpr unsigned long long kCodes = (4ull << 0) | (38ull << 6) | (36ull << 12) | (6ull << 18) | (34ull << 24) | (8ull << 30);
+    return (int)((kCodes >> (6 * word + 2 * i)) & 3ull);
 }
 
 struct Pose { double x, y, th; };
 
-__device__ __forceinline__ Pose dubins_advance(Pose a, int kind, double len, double rho)
+// one segment from pose a, whose heading's (sin, cos) = (sa, ca) the caller already has; returns the end pose and,
+// through (se, ce), the (sin, cos) of its heading.  Same operations as the specification's advance().
+__device__ __forceinline__ Pose dubins_advance(Pose a, double sa, double ca, int kind, double len, double rho, double &se, double &ce)
 {
-    double s0, c0, s1, c1;
-    dm_sincos(a.th, s0, c0);
     if (kind == 1) {
-        a.x = a.x + rho * len * c0;
-        a.y = a.y + rho * len * s0;
+        a.x = a.x + rho * len * ca;
+        a.y = a.y + rho * len * sa;
+        se = sa; ce = ca;
     } else if (kind == 0) {
-        dm_sincos(a.th + len, s1, c1);
-        a.x = a.x + rho * (s1 - s0);
-        a.y = a.y + rho * (c0 - c1);
+        dm_sincos(a.th + len, se, ce);
+        a.x = a.x + rho * (se - sa);
+        a.y = a.y + rho * (ca - ce);
         a.th = a.th + len;
     } else {
-        dm_sincos(a.th - len, s1, c1);
-        a.x = a.x + rho * (s0 - s1);
-        a.y = a.y + rho * (c1 - c0);
+        dm_sincos(a.th - len, se, ce);
+        a.x = a.x + rho * (sa - se);
+        a.y = a.y + rho * (ce - ca);
         a.th = a.th - len;
     }
     return a;
 }
 
-// the path cut at its two junctions: q0 start, q1 after the first segment, q2 after the second
+// the path cut at its two junctions: q0 start, q1 after the first segment, q2 after the second, each with the
+// (sin, cos) of its heading (the specification recomputes them per point; the values are the same)
 struct DubinsTrack {
     Pose q0, q1, q2;
+    double s0, c0, s1, c1, s2, c2;
     int k0, k1, k2;
-    double t, p, rho;
+    double t, p, rho, inv_rho;
 };
 
 __device__ __forceinline__ DubinsTrack dubins_track(int x0, int y0, int h0, int NH, double rho, const DubinsPath &w)
 {
     DubinsTrack tr;
     tr.k0 = dubins_seg(w.word, 0); tr.k1 = dubins_seg(w.word, 1); tr.k2 = dubins_seg(w.word, 2);
-    tr.t = w.t; tr.p = w.p; tr.rho = rho;
+    tr.t = w.t; tr.p = w.p; tr.rho = rho; tr.inv_rho = 1.0 / rho;
     tr.q0.x = (double)x0; tr.q0.y = (double)y0; tr.q0.th = (double)h0 * (DM_TWO_PI / (double)NH);
-    tr.q1 = dubins_advance(tr.q0, tr.k0, w.t, rho);
-    tr.q2 = dubins_advance(tr.q1, tr.k1, w.p, rho);
+    dm_sincos(tr.q0.th, tr.s0, tr.c0);
+    tr.q1 = dubins_advance(tr.q0, tr.s0, tr.c0, tr.k0, w.t, rho, tr.s1, tr.c1);
+    tr.q2 = dubins_advance(tr.q1, tr.s1, tr.c1, tr.k1, w.p, rho, tr.s2, tr.c2);
     return tr;
 }
 
 // pose at arc length s (cells) from the start
 __device__ __forceinline__ Pose dubins_point(const DubinsTrack &tr, double s)
 {
-    const double u = s * (1.0 / tr.rho);
-    if (u < tr.t) return dubins_advance(tr.q0, tr.k0, u, tr.rho);
+    const double u = s * tr.inv_rho;
+    double se, ce;
+    if (u < tr.t) return dubins_advance(tr.q0, tr.s0, tr.c0, tr.k0, u, tr.rho, se, ce);
     const double u2 = u - tr.t;
-    if (u2 < tr.p) return dubins_advance(tr.q1, tr.k1, u2, tr.rho);
-    return dubins_advance(tr.q2, tr.k2, u2 - tr.p, tr.rho);
+    if (u2 < tr.p) return dubins_advance(tr.q1, tr.s1, tr.c1, tr.k1, u2, tr.rho, se, ce);
+    return dubins_advance(tr.q2, tr.s2, tr.c2, tr.k2, u2 - tr.p, tr.rho, se, ce);
 }
 
 __device__ __forceinline__ bool cell_blocked(const uint32_t *bits, int W, int H, int TY, double x, double y)
@@ -309,19 +323,24 @@ __device__ __forceinline__ bool cell_blocked(const uint32_t *bits, int W, int H,
 }
 
 // warp-cooperative sampled collision test of the path w from (x0, y0, h0) to cell (x1, y1): points at arc length
-// k * ds, k = 0 .. floor(len / ds), one per lane and round, plus the target cell.  All lanes must pass the same path.
+// k * ds, k = 0 .. floor(len / ds), one per lane, two rounds of 32 in flight together (their grid reads overlap),
+// plus the target cell.  All lanes must pass the same path.
 __device__ __forceinline__ bool dubins_free_warp(const uint32_t *bits, int W, int H, int TY, int x0, int y0, int h0, int x1, int y1,
                                                  int NH, double rho, double ds, const DubinsPath &w, int lane)
 {
     if (w.word < 0) return false;
     const DubinsTrack tr = dubins_track(x0, y0, h0, NH, rho, w);
     const long long ns = (long long)floor(w.len / ds);
-    for (long long base = 0; base <= ns; base += 32) {
-        const long long k = base + lane;
+    for (long long base = 0; base <= ns; base += 64) {
+        const long long ka = base + lane, kb = base + 32 + lane;
         bool hit = false;
-        if (k <= ns) {
-            const Pose a = dubins_point(tr, (double)k * ds);
+        if (ka <= ns) {
+            const Pose a = dubins_point(tr, (double)ka * ds);
             hit = cell_blocked(bits, W, H, TY, a.x, a.y);
+        }
+        if (kb <= ns) {
+            const Pose b = dubins_point(tr, (double)kb * ds);
+            hit |= cell_blocked(bits, W, H, TY, b.x, b.y);
         }
         if (__any_sync(RRTK_FULL, hit)) return false;
     }

@@ -16,6 +16,7 @@
 //                subtree's costs are recomputed breadth-first over child lists kept in shared memory
 // The goal connection evaluates every vertex, prunes with a shared 64-bit minimum and breaks ties by index.
 #include <math_constants.h>
+#include <cstdio>
 
 #include "dubins.cuh"
 
@@ -81,7 +82,9 @@ struct Edge {
             w.t = w.p = w.q = CUDART_NAN;
             return w.len;
         }
-        dubins_shortest(dx, dy, ha, hb, P.NH, P.rho, tab, w);
+        DubinsPath tmp;                           // only this copy has its address taken: w itself can stay in registers
+        dubins_shortest(dx, dy, ha, hb, P.NH, P.rho, tab, tmp);
+        w = tmp;
         return w.len;
     }
     // (t, p, q) of the word length() chose for the same pair (same bits either way: the table was filled by dubins_shortest)
@@ -97,7 +100,9 @@ struct Edge {
             w.t = __ldg(P.ttpq + 3 * i); w.p = __ldg(P.ttpq + 3 * i + 1); w.q = __ldg(P.ttpq + 3 * i + 2);
             return;
         }
-        dubins_rebuild(dx, dy, ha, hb, P.NH, P.rho, tab, word, w);
+        DubinsPath tmp;
+        dubins_rebuild(dx, dy, ha, hb, P.NH, P.rho, tab, word, tmp);
+        w = tmp;
     }
     // warp-cooperative: is a -> b free (w = the path of path() for the same pair)
     static __device__ __forceinline__ bool is_free(const Plan2Params &P, const uint32_t *bits, uint32_t pa, int ha, uint32_t pb,
@@ -123,6 +128,7 @@ template <int MODEL, int T>
 __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kernel(Plan2Params P)
 {
     constexpr int NW = T / 32;
+    constexpr int KS = 1024 / T;                 // radius-set slots per thread (the list holds at most 1024)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = P.n, cap = P.ring_cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,8 +155,9 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
     __shared__ int s_wdup[NW];
     __shared__ unsigned long long s_wlb[NW];
     __shared__ int s_ntask2;
-    __shared__ unsigned long long s_best;       // bit pattern of the cheapest free candidate cost
+    __shared__ unsigned long long s_best;       // goal connection: bit pattern of the cheapest free cost
     __shared__ int s_bestslot;
+    __shared__ int s_bestrank, s_ncand;         // choose-parent: lowest free rank, number of ranked candidates
     __shared__ int s_accept, s_tail;
     __shared__ double s_c0, s_l0;
     __shared__ long long s_stat[10];
@@ -194,6 +201,18 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
 
     int j = 1;
     long long my_checks = 0, my_lens = 0;      // per-thread counters, reduced at the end
+    // -DRRTK_K8_CLOCKS (experiment builds): cycles thread 0 spends up to the barrier that ends each phase, printed for plan 0
+#ifdef RRTK_K8_CLOCKS
+    long long clk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, clk_last = clock64(), clk_rounds = 0;
+    long long clk_sub[4] = {0, 0, 0, 0}, clk_t0 = 0;
+#define K8_SUB0() do { if (tid == 0) clk_t0 = clock64(); } while (0)
+#define K8_SUB(i) do { if (tid == 0) { const long long now_ = clock64(); clk_sub[i] += now_ - clk_t0; clk_t0 = now_; } } while (0)
+#define K8_CLK(i) do { if (tid == 0) { const long long now_ = clock64(); clk_acc[i] += now_ - clk_last; clk_last = now_; } } while (0)
+#else
+#define K8_CLK(i) do { } while (0)
+#define K8_SUB0() do { } while (0)
+#define K8_SUB(i) do { } while (0)
+#endif
     const bool both = P.rewire != 0;           // edge lengths in both directions per member
     // Dubins: a length costs ~1.5 k instructions, so phase B2 first drops the members no new vertex could improve;
     // Euclid: a length is one square root, so all of them are simply measured
@@ -227,6 +246,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             if (lane == 0) { s_wmin[warp] = key; s_wcnt[warp] = cnt; s_wdup[warp] = anydup; }
         }
         __syncthreads();
+        K8_CLK(0);
 
         // ---- B1: ascending radius list; lower bound on the new vertex's cost ---------------------------------
         unsigned long long nk = s_wmin[0];
@@ -264,6 +284,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
         }
         if (tid == 0) s_ntask2 = 0;
         __syncthreads();
+        K8_CLK(1);
 
         // ---- B2: which members need the edge sample -> member: only those a vertex of cost >= lb could improve -------
         if (prune && m) {
@@ -288,11 +309,13 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 if (want) tasks2[at + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
             }
             __syncthreads();
+        K8_CLK(2);
         }
 
         // ---- B3: edge lengths, one task per thread: the gate edge nearest -> sample, member -> sample for every member,
         //          sample -> member where B2 asked for it --------------------------------------------------------------
         const int ntask = 1 + m + (prune ? (m ? s_ntask2 : 0) : (both ? m : 0));
+        K8_SUB0();
         DubinsPath w0;
         w0.word = -1; w0.t = w0.p = w0.q = 0.0; w0.len = 0.0;
         for (int tsk = tid; tsk < ntask; tsk += T) {
@@ -309,71 +332,104 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             else if (back) { valL2[slot] = l; word2[slot] = (uint8_t)w.word; }
             else { valL1[slot] = l; word1[slot] = (uint8_t)w.word; }
         }
+        K8_SUB(0);
         if (warp == 0) {
             w0.word = __shfl_sync(RRTK_FULL, w0.word, 0);
             w0.t = __shfl_sync(RRTK_FULL, w0.t, 0); w0.p = __shfl_sync(RRTK_FULL, w0.p, 0);
             w0.q = __shfl_sync(RRTK_FULL, w0.q, 0); w0.len = __shfl_sync(RRTK_FULL, w0.len, 0);
             if (MODEL == RRTK_MODEL_DUBINS && w0.t != w0.t)      // length came from the memo: fetch the path's (t, p, q)
                 Edge<MODEL>::path(P, tab, spts[vnear], shead[vnear], pnew, qh, w0.word, w0);
+            K8_SUB(1);
+#ifdef RRTK_K8_NOGATE
+            const bool ok = w0.len < 1e30;
+#else
             const bool ok = Edge<MODEL>::is_free(P, bits, spts[vnear], shead[vnear], pnew, w0, lane);
+#endif
+            K8_SUB(2);
             if (lane == 0) {
                 ++my_checks;
                 s_accept = ok && !dup_any && j != n && !overflow;
                 if (overflow) s_stat[S2_OVERFLOW] = 1;
                 s_c0 = __dadd_rn(cost[vnear], w0.len); s_l0 = w0.len;
-                s_best = 0xffffffffffffffffull; s_bestslot = 0x7fffffff;
+                s_bestrank = 0x7fffffff; s_ncand = 0;
             }
         }
         __syncthreads();
+        K8_CLK(3);
         if (!s_accept) continue;                 // uniform: every thread reads the same shared flag
         const double c0 = s_c0;
 
-        // ---- C: parent candidates (prefilter and cost test of the specification) --------------------------
-        for (int i = tid; i < m; i += T) {
-            const int vn = ring[i];
-            uint8_t f = 0;
-            if (vn != vnear) {
-                const double cv = cost[vn];
-                const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
-                if (__dadd_rn(cv, D) < c0 && __dadd_rn(cv, valL1[i]) < c0) f = 1;
+        // ---- C: parent candidates (prefilter and cost test of the specification); a candidate's slot of valL1 now holds
+        //         its cost through that edge, the edge length stays in a register of the thread that owns the slot --------
+        double myL[KS];
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+            const int i = tid + k * T;
+            myL[k] = 0.0;
+            if (i < m) {
+                const int vn = ring[i];
+                uint8_t f = 0;
+                if (vn != vnear) {
+                    const double cv = cost[vn];
+                    const double D = __dsqrt_rn((double)dist2(spts[vn], qx, qy));
+                    const double L = valL1[i];
+                    const double cn = __dadd_rn(cv, L);
+                    if (__dadd_rn(cv, D) < c0 && cn < c0) { f = 1; myL[k] = L; valL1[i] = cn; }
+                }
+                flag[i] = f;
             }
-            flag[i] = f;
         }
         __syncthreads();
-
-        // ---- D: choose the parent: warps test the candidates' edges, the cheapest free one wins ------------
-        for (int i = warp; i < m; i += NW) {
+        K8_CLK(4);
+        // ---- C2: rank the candidates by (cost, vertex) -- the order the specification breaks ties in -- so that the edge
+        //          tests below run cheapest first and the first free one in that order is the parent ----------------------
+        for (int i = tid; i < m; i += T) {
             if (!flag[i]) continue;
+            const double cn = valL1[i];
+            int rank = 0;
+            for (int t = 0; t < m; ++t) {
+                if (!flag[t]) continue;
+                const double ct = valL1[t];
+                rank += (ct < cn || (ct == cn && t < i)) ? 1 : 0;
+            }
+            tasks2[rank] = (uint16_t)i;              // tasks2 is free again: rank -> slot
+            atomicAdd(&s_ncand, 1);
+        }
+        __syncthreads();
+        K8_CLK(5);
+
+        // ---- D: choose the parent: warps test the candidates' edges in rank order, the lowest free rank wins -----------
+        for (int r = warp; r < s_ncand; r += NW) {
+            if (r > s_bestrank) break;                // a cheaper free edge is known
+            const int i = tasks2[r];
             const int vn = ring[i];
-            const double cn = __dadd_rn(cost[vn], valL1[i]);
-            if ((unsigned long long)__double_as_longlong(cn) > s_best) continue;    // a cheaper free edge is known
             const uint32_t pv = spts[vn];
             DubinsPath w;
             w.word = 0;
             Edge<MODEL>::path(P, tab, pv, shead[vn], pnew, qh, word1[i], w);
             const bool ok = Edge<MODEL>::is_free(P, bits, pv, shead[vn], pnew, w, lane);
-            __syncwarp();                            // every lane has read flag[i] before lane 0 rewrites it
             if (lane == 0) {
                 ++my_checks;
-                if (ok) { flag[i] = 2; atomicMin(&s_best, (unsigned long long)__double_as_longlong(cn)); }
+                if (ok) atomicMin(&s_bestrank, r);
             }
         }
         __syncthreads();
-        if (s_best != 0xffffffffffffffffull) {
-            const unsigned long long best = s_best;
-            for (int i = tid; i < m; i += T)            // ties: the list is ascending, so the lowest slot is the lowest vertex
-                if (flag[i] == 2 && (unsigned long long)__double_as_longlong(__dadd_rn(cost[ring[i]], valL1[i])) == best)
-                    atomicMin(&s_bestslot, i);
-            __syncthreads();
-        }
+        K8_CLK(6);
         // ---- E: insert vertex j, rewire candidates ---------------------------------------------------------
-        int vbest = vnear;
-        double cbest = c0, lbest = s_l0;
-        if (s_bestslot != 0x7fffffff) { vbest = ring[s_bestslot]; lbest = valL1[s_bestslot]; cbest = __dadd_rn(cost[vbest], lbest); }
+        int vbest = vnear, wslot = -1;
+        double cbest = c0;
+        if (s_bestrank != 0x7fffffff) { wslot = tasks2[s_bestrank]; vbest = ring[wslot]; cbest = valL1[wslot]; }
+        if (wslot >= 0 && tid == (wslot % T)) {       // the owner of the winning slot still holds the edge length
+            double lb = 0.0;
+#pragma unroll
+            for (int k = 0; k < KS; ++k) lb = (wslot / T == k) ? myL[k] : lb;
+            elen[j] = lb;
+        }
         if (tid == 0) {
             spts[j] = pnew; shead[j] = (uint8_t)qh;
             o_pts[j] = make_short2((short)qx, (short)qy); o_head[j] = (uint8_t)qh;
-            cost[j] = cbest; elen[j] = lbest; parent[j] = vbest;
+            cost[j] = cbest; parent[j] = vbest;
+            if (wslot < 0) elen[j] = s_l0;
             next[j] = first[vbest]; first[vbest] = (uint16_t)j;
             s_stat[S2_ACCEPTED] += 1; s_stat[S2_RING] += m;
         }
@@ -392,6 +448,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 flag[i] = f;
             }
             __syncthreads();
+        K8_CLK(7);
             // ---- F: test the rewire edges sample -> member -------------------------------------------------
             for (int i = warp; i < m; i += NW) {
                 if (!flag[i]) continue;
@@ -405,6 +462,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 if (lane == 0) { ++my_checks; flag[i] = ok ? 2 : 0; }
             }
             __syncthreads();
+        K8_CLK(8);
             // ---- G: apply in ascending vertex order ----------------------------------------------------------
             if (warp == 0) {
                 for (int base = 0; base < m; base += 32) {
@@ -455,8 +513,15 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
         }
         ++j;
         __syncthreads();
+        K8_CLK(9);
     }
 
+#ifdef RRTK_K8_CLOCKS
+    if (tid == 0 && plan == 0)
+        printf("K8 clocks plan0 j=%d: A %lld B1 %lld B2 %lld B3 %lld C %lld D %lld Dres %lld E %lld F %lld G %lld\n", j, clk_acc[0], clk_acc[1],
+               clk_acc[2], clk_acc[3], clk_acc[4], clk_acc[5], clk_acc[6], clk_acc[7], clk_acc[8], clk_acc[9]);
+    if (tid == 0 && plan == 0) printf("K8 B3 split: tasks %lld path %lld gate-test %lld\n", clk_sub[0], clk_sub[1], clk_sub[2]);
+#endif
     // ---- goal connection (rrt.py:284-332 with this model's edges) ----------------------------------------
     const uint32_t pgoal = pack_xy(pd.goal_x, pd.goal_y);
     if (tid == 0) { s_best = 0xffffffffffffffffull; s_bestslot = 0x7fffffff; }
