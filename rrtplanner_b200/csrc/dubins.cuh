@@ -325,12 +325,19 @@ __device__ __forceinline__ bool cell_blocked(const uint32_t *bits, int W, int H,
 // warp-cooperative sampled collision test of the path w from (x0, y0, h0) to cell (x1, y1): points at arc length
 // k * ds, k = 0 .. floor(len / ds), one per lane, two rounds of 32 in flight together (their grid reads overlap),
 // plus the target cell.  All lanes must pass the same path.
-__device__ __forceinline__ bool dubins_free_warp(const uint32_t *bits, int W, int H, int TY, int x0, int y0, int h0, int x1, int y1,
-                                                 int NH, double rho, double ds, const DubinsPath &w, int lane)
+#ifndef RRTK_FREE_INLINE
+#define RRTK_FREE_INLINE __forceinline__
+#endif
+// Inlined by default; as a real call (-DRRTK_FREE_INLINE=__noinline__, measured: -4 %) it would have the register budget to
+// itself but pays for saving the plan loop's state around every test.
+__device__ RRTK_FREE_INLINE bool dubins_free_path(const uint32_t *bits, int W, int H, int TY, int x0, int y0, int h0, int x1, int y1,
+                                                 int NH, double rho, double ds, int word, double t, double p, double len, int lane)
 {
-    if (w.word < 0) return false;
+    if (word < 0) return false;
+    DubinsPath w;
+    w.word = word; w.t = t; w.p = p; w.q = 0.0; w.len = len;
     const DubinsTrack tr = dubins_track(x0, y0, h0, NH, rho, w);
-    const long long ns = (long long)floor(w.len / ds);
+    const long long ns = (long long)floor(len / ds);
     for (long long base = 0; base <= ns; base += 64) {
         const long long ka = base + lane, kb = base + 32 + lane;
         bool hit = false;
@@ -345,6 +352,12 @@ __device__ __forceinline__ bool dubins_free_warp(const uint32_t *bits, int W, in
         if (__any_sync(RRTK_FULL, hit)) return false;
     }
     return !((__ldg(bits + word_index(x1, y1, TY)) >> (y1 & 31)) & 1u);
+}
+
+__device__ __forceinline__ bool dubins_free_warp(const uint32_t *bits, int W, int H, int TY, int x0, int y0, int h0, int x1, int y1,
+                                                 int NH, double rho, double ds, const DubinsPath &w, int lane)
+{
+    return dubins_free_path(bits, W, H, TY, x0, y0, h0, x1, y1, NH, rho, ds, w.word, w.t, w.p, w.len, lane);
 }
 
 }  // namespace rrtk

@@ -328,6 +328,8 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             DubinsPath w;
             const double l = Edge<MODEL>::length(P, tab, back ? pnew : pv, back ? qh : hv, back ? pv : pnew, back ? hv : qh, w);
             ++my_lens;
+            if (gate && MODEL == RRTK_MODEL_DUBINS && w.t != w.t)   // memoised length: fetch (t, p, q) in the same round trip
+                Edge<MODEL>::path(P, tab, pv, hv, pnew, qh, w.word, w);
             if (gate) w0 = w, w0.len = l;
             else if (back) { valL2[slot] = l; word2[slot] = (uint8_t)w.word; }
             else { valL1[slot] = l; word1[slot] = (uint8_t)w.word; }
