@@ -248,112 +248,107 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
         __syncthreads();
         K8_CLK(0);
 
-        // ---- B1: ascending radius list; lower bound on the new vertex's cost ---------------------------------
+        // ---- B: the last warp tests the gate edge nearest -> sample (a path lookup, then up to ~90 sampled cells: the longest
+        //         single job of a round) while the other warps build the radius list and measure its edges; the workers
+        //         synchronise among themselves on named barrier 1, everybody meets again at the block barrier below ------
         unsigned long long nk = s_wmin[0];
-        int m_total = 0, my_off = 0, dup_any = 0;
+        int m_total = 0, my_off = 0, dup_any = 0, last_off = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
             nk = s_wmin[w] < nk ? s_wmin[w] : nk;
             if (w < warp) my_off += s_wcnt[w];
+            if (w < NW - 1) last_off += s_wcnt[w];
             m_total += s_wcnt[w];
             dup_any |= s_wdup[w];
         }
         const int vnear = (int)(nk & 0xffffffffu);
         const bool overflow = P.star && m_total > cap;
         const int m = (P.star && !overflow) ? m_total : 0;
-        if (m) {
-            int off = my_off;
-            unsigned long long lbk = 0xffffffffffffffffull;
-            for (int base = v0; base < v1; base += 32) {
-                const unsigned mk = mask[base >> 5];
-                if ((mk >> lane) & 1u) {
-                    const int v = base + lane;
-                    ring[off + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)v;
-                    if (prune) {
-                        const double c = __dadd_rn(cost[v], __dsqrt_rn((double)dist2(spts[v], qx, qy)));
-                        const unsigned long long k = (unsigned long long)__double_as_longlong(c);
-                        lbk = k < lbk ? k : lbk;
-                    }
-                }
-                off += __popc(mk);
-            }
-            if (prune) {
-                lbk = warp_min_u64(lbk);
-                if (lane == 0) s_wlb[warp] = lbk;
-            }
-        }
-        if (tid == 0) s_ntask2 = 0;
-        __syncthreads();
-        K8_CLK(1);
-
-        // ---- B2: which members need the edge sample -> member: only those a vertex of cost >= lb could improve -------
-        if (prune && m) {
-            unsigned long long lbk = (unsigned long long)__double_as_longlong(
-                __dadd_rn(cost[vnear], __dsqrt_rn((double)(uint32_t)(nk >> 32))));
-#pragma unroll
-            for (int w = 0; w < NW; ++w) lbk = s_wlb[w] < lbk ? s_wlb[w] : lbk;
-            // every edge is at least as long as the straight line up to rounding (and the 1e-9 snap of mod2pi): 1e-6 cells of slack
-            const double lb = __dsub_rn(__longlong_as_double((long long)lbk), 1e-6);
-            for (int base = warp * 32; base < m; base += T) {
-                const int i = base + lane;
-                bool want = false;
-                if (i < m) {
-                    const int vn = ring[i];
-                    want = __dadd_rn(lb, __dsqrt_rn((double)dist2(spts[vn], qx, qy))) < cost[vn];
-                    word2[i] = 0xfe;                              // "not measured": phase E must never need it
-                }
-                const unsigned bal = __ballot_sync(RRTK_FULL, want);
-                int at = 0;
-                if (lane == 0 && bal) at = atomicAdd(&s_ntask2, __popc(bal));
-                at = __shfl_sync(RRTK_FULL, at, 0);
-                if (want) tasks2[at + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
-            }
-            __syncthreads();
-        K8_CLK(2);
-        }
-
-        // ---- B3: edge lengths, one task per thread: the gate edge nearest -> sample, member -> sample for every member,
-        //          sample -> member where B2 asked for it --------------------------------------------------------------
-        const int ntask = 1 + m + (prune ? (m ? s_ntask2 : 0) : (both ? m : 0));
-        K8_SUB0();
-        DubinsPath w0;
-        w0.word = -1; w0.t = w0.p = w0.q = 0.0; w0.len = 0.0;
-        for (int tsk = tid; tsk < ntask; tsk += T) {
-            const bool gate = tsk == 0;
-            const bool back = tsk > m;                           // sample -> member
-            const int slot = gate ? 0 : (back ? (prune ? (int)tasks2[tsk - m - 1] : tsk - m - 1) : tsk - 1);
-            const int vn = gate ? vnear : ring[slot];
-            const uint32_t pv = spts[vn];
-            const int hv = shead[vn];
-            DubinsPath w;
-            const double l = Edge<MODEL>::length(P, tab, back ? pnew : pv, back ? qh : hv, back ? pv : pnew, back ? hv : qh, w);
-            ++my_lens;
-            if (gate && MODEL == RRTK_MODEL_DUBINS && w.t != w.t)   // memoised length: fetch (t, p, q) in the same round trip
-                Edge<MODEL>::path(P, tab, pv, hv, pnew, qh, w.word, w);
-            if (gate) w0 = w, w0.len = l;
-            else if (back) { valL2[slot] = l; word2[slot] = (uint8_t)w.word; }
-            else { valL1[slot] = l; word1[slot] = (uint8_t)w.word; }
-        }
-        K8_SUB(0);
-        if (warp == 0) {
-            w0.word = __shfl_sync(RRTK_FULL, w0.word, 0);
-            w0.t = __shfl_sync(RRTK_FULL, w0.t, 0); w0.p = __shfl_sync(RRTK_FULL, w0.p, 0);
-            w0.q = __shfl_sync(RRTK_FULL, w0.q, 0); w0.len = __shfl_sync(RRTK_FULL, w0.len, 0);
-            if (MODEL == RRTK_MODEL_DUBINS && w0.t != w0.t)      // length came from the memo: fetch the path's (t, p, q)
-                Edge<MODEL>::path(P, tab, spts[vnear], shead[vnear], pnew, qh, w0.word, w0);
-            K8_SUB(1);
-#ifdef RRTK_K8_NOGATE
-            const bool ok = w0.len < 1e30;
-#else
-            const bool ok = Edge<MODEL>::is_free(P, bits, spts[vnear], shead[vnear], pnew, w0, lane);
-#endif
-            K8_SUB(2);
+        if (warp == NW - 1) {
+            // ---- gate warp ---------------------------------------------------------------------------------------
+            const uint32_t pn = spts[vnear];
+            const int hn = shead[vnear];
+            DubinsPath w0;
+            const double l0 = Edge<MODEL>::length(P, tab, pn, hn, pnew, qh, w0);
+            if (MODEL == RRTK_MODEL_DUBINS && w0.t != w0.t)      // memoised length: fetch the path's (t, p, q)
+                Edge<MODEL>::path(P, tab, pn, hn, pnew, qh, w0.word, w0);
+            w0.len = l0;
+            const bool ok = Edge<MODEL>::is_free(P, bits, pn, hn, pnew, w0, lane);
             if (lane == 0) {
-                ++my_checks;
+                ++my_checks; ++my_lens;
                 s_accept = ok && !dup_any && j != n && !overflow;
                 if (overflow) s_stat[S2_OVERFLOW] = 1;
-                s_c0 = __dadd_rn(cost[vnear], w0.len); s_l0 = w0.len;
+                s_c0 = __dadd_rn(cost[vnear], l0); s_l0 = l0;
                 s_bestrank = 0x7fffffff; s_ncand = 0;
+            }
+        } else {
+            // ---- worker warps: B1 ascending radius list; lower bound on the new vertex's cost ---------------------
+            constexpr int TW = T - 32;                            // worker threads
+            if (m) {
+                unsigned long long lbk = 0xffffffffffffffffull;
+                // own slice of the tree, and warp 0 also takes the gate warp's slice
+                for (int part = 0; part < (warp == 0 ? 2 : 1); ++part) {
+                    const int c0v = part ? (NW - 1) * chunk : v0, c1v = part ? min(j, c0v + chunk) : v1;
+                    int off = part ? last_off : my_off;
+                    for (int base = c0v; base < c1v; base += 32) {
+                        const unsigned mk = mask[base >> 5];
+                        if ((mk >> lane) & 1u) {
+                            const int v = base + lane;
+                            ring[off + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)v;
+                            if (prune) {
+                                const double c = __dadd_rn(cost[v], __dsqrt_rn((double)dist2(spts[v], qx, qy)));
+                                const unsigned long long k = (unsigned long long)__double_as_longlong(c);
+                                lbk = k < lbk ? k : lbk;
+                            }
+                        }
+                        off += __popc(mk);
+                    }
+                }
+                if (prune) {
+                    lbk = warp_min_u64(lbk);
+                    if (lane == 0) s_wlb[warp] = lbk;
+                }
+            }
+            if (tid == 0) s_ntask2 = 0;
+            asm volatile("bar.sync 1, %0;" ::"r"(TW) : "memory");
+            // ---- B2: which members need the edge sample -> member: only those a vertex of cost >= lb could improve ---
+            if (prune && m) {
+                unsigned long long lbk = (unsigned long long)__double_as_longlong(
+                    __dadd_rn(cost[vnear], __dsqrt_rn((double)(uint32_t)(nk >> 32))));
+#pragma unroll
+                for (int w = 0; w < NW - 1; ++w) lbk = s_wlb[w] < lbk ? s_wlb[w] : lbk;
+                // every edge is at least as long as the straight line up to rounding (and the 1e-9 snap of mod2pi): 1e-6 cells of slack
+                const double lb = __dsub_rn(__longlong_as_double((long long)lbk), 1e-6);
+                for (int base = warp * 32; base < m; base += TW) {
+                    const int i = base + lane;
+                    bool want = false;
+                    if (i < m) {
+                        const int vn = ring[i];
+                        want = __dadd_rn(lb, __dsqrt_rn((double)dist2(spts[vn], qx, qy))) < cost[vn];
+                        word2[i] = 0xfe;                              // "not measured": phase E must never need it
+                    }
+                    const unsigned bal = __ballot_sync(RRTK_FULL, want);
+                    int at = 0;
+                    if (lane == 0 && bal) at = atomicAdd(&s_ntask2, __popc(bal));
+                    at = __shfl_sync(RRTK_FULL, at, 0);
+                    if (want) tasks2[at + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+                }
+                asm volatile("bar.sync 1, %0;" ::"r"(TW) : "memory");
+            }
+            // ---- B3: edge lengths, one task per worker thread: member -> sample for every member, sample -> member
+            //          where B2 asked for it (Euclid: everywhere) ------------------------------------------------------
+            const int ntask = m + (prune ? (m ? s_ntask2 : 0) : (both ? m : 0));
+            for (int tsk = tid; tsk < ntask; tsk += TW) {
+                const bool back = tsk >= m;                          // sample -> member
+                const int slot = back ? (prune ? (int)tasks2[tsk - m] : tsk - m) : tsk;
+                const int vn = ring[slot];
+                const uint32_t pv = spts[vn];
+                const int hv = shead[vn];
+                DubinsPath w;
+                const double l = Edge<MODEL>::length(P, tab, back ? pnew : pv, back ? qh : hv, back ? pv : pnew, back ? hv : qh, w);
+                ++my_lens;
+                if (back) { valL2[slot] = l; word2[slot] = (uint8_t)w.word; }
+                else { valL1[slot] = l; word1[slot] = (uint8_t)w.word; }
             }
         }
         __syncthreads();
