@@ -7,11 +7,14 @@
 // the K-samples-per-round replay of plan_scan.cuh does not apply).  Per round:
 //   A  scan      each warp owns a contiguous slice of the tree: nearest vertex (lowest index on ties), duplicate test,
 //                membership of the rewire radius as one ballot word per 32 vertices
-//   B  gate      ascending radius list from the ballot words; warp 0 builds the edge nearest -> sample and tests it
-//   C  parents   one thread per radius-set member: Euclidean prefilter, edge length (Dubins: shortest of six words)
-//   D  choose    warps test the candidates' edges, cheapest free one wins (cost, then vertex index)
-//   E  insert    vertex j; one thread per member: rewire prefilter + edge length sample -> member
-//   F  test      warps test the rewire candidates' edges
+//   B  gate ||   the LAST warp measures and tests the gate edge nearest -> sample; meanwhile the other warps (named
+//      lists     barrier 1 among themselves) build the ascending radius list, bound the new vertex's cost from below to
+//                drop hopeless rewire candidates, and measure one edge per thread (Dubins: a lookup in the memo of the
+//                primitive when the batch has one, else the shortest of six words)
+//   C  rank      candidates (Euclidean prefilter and cost test of the specification) ranked by (cost, vertex)
+//   D  choose    warps test the candidates' edges in rank order; the lowest free rank is the parent
+//   E  insert    vertex j; rewire candidates flagged against the new vertex's cost
+//   F  test      warps test the rewire edges sample -> member
 //   G  apply     warp 0, ascending vertex order, re-testing against costs already lowered this round; the rewired
 //                subtree's costs are recomputed breadth-first over child lists kept in shared memory
 // The goal connection evaluates every vertex, prunes with a shared 64-bit minimum and breaks ties by index.
