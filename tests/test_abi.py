@@ -81,3 +81,35 @@ def test_pcg_state_words():
     w = _lib.pcg64_state_words(np.random.default_rng(0))
     st = np.random.default_rng(0).bit_generator.state["state"]
     assert (int(w[0]) << 64) | int(w[1]) == st["state"] and (int(w[2]) << 64) | int(w[3]) == st["inc"]
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The numpy mirrors of the ABI structs (rrtk_plan_desc, rrtk_plan2_cfg) have the sizes and field offsets a C compiler
+    gives the declarations of include/rrtk.h."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "rrtk.h"
+#define F(T, f) printf(#T "." #f " %zu\n", offsetof(T, f))
+int main(void) {
+    printf("rrtk_plan_desc %zu\n", sizeof(rrtk_plan_desc));
+    F(rrtk_plan_desc, world); F(rrtk_plan_desc, start_x); F(rrtk_plan_desc, start_y); F(rrtk_plan_desc, goal_x);
+    F(rrtk_plan_desc, goal_y); F(rrtk_plan_desc, reserved); F(rrtk_plan_desc, rot);
+    printf("rrtk_plan2_cfg %zu\n", sizeof(rrtk_plan2_cfg));
+    F(rrtk_plan2_cfg, model); F(rrtk_plan2_cfg, star); F(rrtk_plan2_cfg, rewire); F(rrtk_plan2_cfg, nheadings);
+    F(rrtk_plan2_cfg, r_rewire); F(rrtk_plan2_cfg, rho); F(rrtk_plan2_cfg, ds); F(rrtk_plan2_cfg, dubins_table);
+    F(rrtk_plan2_cfg, table_radius); F(rrtk_plan2_cfg, reserved);
+    printf("RRTK_STAT_COUNT %d\n", (int)RRTK_STAT_COUNT);
+    return 0;
+}
+''')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(line.rsplit(" ", 1) for line in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+    assert int(got["rrtk_plan_desc"]) == _lib.PLAN_DESC.itemsize and int(got["rrtk_plan2_cfg"]) == _lib.PLAN2_CFG.itemsize
+    for struct, dt in (("rrtk_plan_desc", _lib.PLAN_DESC), ("rrtk_plan2_cfg", _lib.PLAN2_CFG)):
+        for name in dt.names:
+            assert int(got[f"{struct}.{name}"]) == dt.fields[name][1], (struct, name)
+    assert int(got["RRTK_STAT_COUNT"]) == _lib.STAT_COUNT == len(_lib.STAT2_NAMES)
