@@ -66,6 +66,24 @@ def test_no_silent_cpu_fallback(lib):
         R.RRT(og, 10).plan(np.array([1, 1]), np.array([2, 2]))
     with pytest.raises(NotImplementedError):
         R.RRTStar(og, 10, 5, costfn=lambda *a: 0.0)
+    # the planners the reference only advertises behave the same way: no GPU, no result
+    with pytest.raises(RuntimeError):
+        R.RRTStar(og, 10, 5, pbar=False, rewire="rrtstar").plan(np.array([1, 1]), np.array([9, 9]))
+    with pytest.raises(RuntimeError):
+        R.RRTStarDubins(og, 10, 5.0, 2.0, pbar=False).plan(np.array([1, 1, 0]), np.array([9, 9, 3]))
+    with pytest.raises(RuntimeError):
+        R.dubins_path([1, 1, 0], [9, 9, 3], 2.0)
+
+
+def test_k8_argument_checks_need_no_gpu(lib):
+    cfg = _lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 16, 2.0, 1.0)
+    assert lib.rrtk_plan2_batch(_lib.ptr(cfg), None, 8, 8, None, 1, 10, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    bad = _lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 0, 2.0, 1.0)           # zero headings
+    assert lib.rrtk_plan2_batch(_lib.ptr(bad), None, 8, 8, None, 1, 10, None, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert b"nheadings" in lib.rrtk_last_error()
+    assert lib.rrtk_plan2_scratch_bytes(4, 100) >= 4 * 101 * 10 and lib.rrtk_plan2_scratch_bytes(-1, 100) == 0
+    assert lib.rrtk_dubins_table_bytes(50, 16) == (101 * 101 * 256) * 33 + 16
+    assert lib.rrtk_dubins_paths(None, 5, 16, 2.0, None, None, None, None) == -1
 
 
 def test_product_never_imports_the_oracle():

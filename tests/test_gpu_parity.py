@@ -217,6 +217,16 @@ def test_sampler_rejection_path(ctx):
     assert np.array_equal(got[0].astype(np.int64), O.sample_stream(og, 6000, 5))
 
 
+def test_sample_stream_large_n_takes_the_sequential_kernel(ctx):
+    """Above ~29 000 draws the raw window of the parallel generator no longer fits shared memory and the launcher falls back to
+    the one-thread generator; both must give numpy's stream."""
+    og = worlds.perlin_occupancygrid(96, 80, seed=3).astype(np.uint8)
+    ctx.set_grids(og[None])
+    for n in (28000, 40000):
+        got = ctx.samples(batch.make_desc([0], [[0, 0]], [[0, 0]]), n, batch.seed_states([77]))
+        assert np.array_equal(got[0].astype(np.int64), O.sample_stream(og, n, 77))
+
+
 def test_sampler_with_many_rejections(ctx):
     """nfree = 3700^2: 2^32 mod nfree is large, so one draw in ~430 is rejected -- ~19 rejections at n = 8000 (handled by
     the parallel compaction) and ~65 at n = 28000 (around the slack of the raw window, so some seeds take the sequential
