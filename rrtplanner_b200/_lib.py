@@ -255,17 +255,23 @@ class Context:
         return out
 
     # -- K8: rewire / Dubins planners, Dubins primitive ---------------------------------------
-    def plan2(self, cfg, desc, n, samples=None, states=None, heads=None):
-        """rrtk_ctx_plan2: returns (pts, head, cost, elen, parent, stats); desc["reserved"][:, :2] = start / goal heading."""
+    def plan2(self, cfg, desc, n, samples=None, states=None, heads=None, out=None):
+        """rrtk_ctx_plan2: returns (pts, head, cost, elen, parent, stats); desc["reserved"][:, :2] = start / goal heading.
+        ``out``: optional preallocated host arrays in that order (e.g. pinned)."""
         nplans = desc.shape[0]
         desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
         cfg = np.ascontiguousarray(cfg, dtype=PLAN2_CFG)
-        pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
-        head = np.empty((nplans, n + 1), dtype=np.uint8)
-        cost = np.empty((nplans, n + 1), dtype=np.float64)
-        elen = np.empty((nplans, n + 1), dtype=np.float64)
-        parent = np.empty((nplans, n + 1), dtype=np.int32)
-        stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
+        if out is not None:
+            pts, head, cost, elen, parent, stats = out
+            assert pts.shape == (nplans, n + 1, 2) and pts.dtype == np.int16 and head.dtype == np.uint8
+            assert cost.shape == elen.shape == (nplans, n + 1) and parent.dtype == np.int32 and stats.shape == (nplans, STAT_COUNT)
+        else:
+            pts = np.empty((nplans, n + 1, 2), dtype=np.int16)
+            head = np.empty((nplans, n + 1), dtype=np.uint8)
+            cost = np.empty((nplans, n + 1), dtype=np.float64)
+            elen = np.empty((nplans, n + 1), dtype=np.float64)
+            parent = np.empty((nplans, n + 1), dtype=np.int32)
+            stats = np.empty((nplans, STAT_COUNT), dtype=np.int64)
         if samples is not None:
             samples = np.ascontiguousarray(samples, dtype=np.int16)
             assert samples.shape == (nplans, n, 2), samples.shape
