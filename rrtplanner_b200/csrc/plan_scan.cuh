@@ -77,6 +77,9 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     static_assert(T % 32 == 0 && K <= 16 && K >= 1, "block shape");
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int2 s_near[K][NW];                    // [sample][warp] (min key >> sbits, vertex)
+#ifdef RRTK_SPEC_SCAN
+    __shared__ int2 s_near2[K][NW];                   // the same from the speculative scan of the tree's full quads (see the commit phase)
+#endif
     __shared__ SampleRec s_rec[K];
     __shared__ RoundSummary s_sum;
     __shared__ short2 s_q[K];                         // samples of the round
@@ -140,6 +143,18 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 
     // block-uniform state, replicated in every thread (refreshed from s_sum after each round)
     int j = 1, it0 = 0;
+#ifdef RRTK_SPEC_SCAN
+    bool spec_ok = false;               // the quads [0, spec_quads) of this round's scan were done during the last commit phase
+    int spec_quads = 0;
+    int cw = 0, cw_prev = 0;            // the warp that commits this round / committed the last one: the duty rotates, because
+                                        // warp w of every block sits on scheduler w mod 4 and the committing warp's columns are
+                                        // scanned by its neighbours -- a fixed choice would overload one scheduler of the SM
+    __shared__ unsigned long long s_cnt[4];   // commit-phase counters of all warps, summed at the end
+    if (tid < 4) s_cnt[tid] = 0ull;
+#define RRTK_COMMIT_WARP cw
+#else
+#define RRTK_COMMIT_WARP 0
+#endif
     bool have_sol = false;              // INFORMED: running least_cost over vsoln (rrt.py:627-633)
     int vsol = 0;
     double csol = 0.0;
@@ -169,6 +184,78 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         const int rows = (j + T - 1) / T;
         const int steps = (rows + 3) >> 2;
         const int nwords = (steps + 7) >> 3;
+        // One column (the vertices v = row * T + col) over the quads [qa, qb): membership bits appended to the column's words,
+        // running minima in best[].  A word that an earlier call left incomplete (stored unshifted) is continued; `finish`
+        // stores the last word in its final, left-aligned form even when it is incomplete (and even if qa == qb).
+        auto scan_quads = [&](int col, int qa, int qb, bool mask_last, bool finish, const int (&ax)[K], const int (&ay)[K],
+                              const int (&thr)[K], int (&best)[K]) {
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts) + col;
+            auto step = [&](int s, uint32_t (&h)[K], auto masked_c) {
+                constexpr bool masked = decltype(masked_c)::value;
+                const uint4 q = q4[s * T];
+                const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; e += 2) {
+                    int vx[2], vy[2], nvs[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        vx[u] = px(wv[e + u]); vy[u] = py(wv[e + u]);
+                        const int row = 4 * s + e + u;
+                        nvs[u] = (vx[u] * vx[u] + vy[u] * vy[u]) * S + row;
+                        if (masked && row * T + col >= j) { vx[u] = 0; vy[u] = 0; nvs[u] = kKeyDead; }
+                    }
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const int d0 = vx[0] * ax[k] + (vy[0] * ay[k] + nvs[0]) - thr[k];
+                        const int d1 = vx[1] * ax[k] + (vy[1] * ay[k] + nvs[1]) - thr[k];
+                        if (KIND != RRTK_STANDARD) {
+                            h[k] = __funnelshift_l((uint32_t)d0, h[k], 1);
+                            h[k] = __funnelshift_l((uint32_t)d1, h[k], 1);
+                        }
+                        best[k] = min(best[k], min(d0, d1));
+                    }
+                }
+            };
+            int s = qa;
+            if (qa == qb) {
+                if (finish && (qa & 7) && KIND != RRTK_STANDARD) {       // nothing new, but the word the range would continue must be finalised
+                    const int w = qa >> 3, fill = 32 - 4 * (qa & 7);
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + col] <<= fill;
+                }
+                return;
+            }
+            while (s < qb) {
+                const int w = s >> 3;
+                const int s_end = min(qb, 8 * w + 8);
+                uint32_t h[K];
+                const bool resume = (s & 7) != 0;                          // an earlier call stored this word unshifted
+#pragma unroll
+                for (int k = 0; k < K; ++k) h[k] = (resume && KIND != RRTK_STANDARD) ? s_hits[(w * K + k) * T + col] : 0u;
+                const int s_full = mask_last ? min(s_end, qb - 1) : s_end;
+                for (; s < s_full; ++s) step(s, h, std::false_type{});
+                if (s < s_end) { step(s, h, std::true_type{}); ++s; }
+                if (KIND != RRTK_STANDARD) {
+                    const int done = s - 8 * w;
+                    const int fill = (done == 8 || (finish && s == qb)) ? 32 - 4 * done : 0;   // processed slot p  <->  bit 31 - p
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + col] = fill < 32 ? h[k] << fill : 0u;
+                }
+            }
+        };
+        // fold the running minima of a warp into (distance key, vertex) per sample; col = the column each lane scanned
+        auto fold_near = [&](int col, const int (&thr)[K], const int (&best)[K], int2 (*dst)[NW]) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {   // warp minimum, lowest index among equals
+                const bool any = best[k] != 0x7fffffff;
+                const int key = best[k] + thr[k];
+                const int dp = any ? (key >> sbits) : 0x7fffffff;
+                const int v = (key & (S - 1)) * T + col;
+                const int wd = __reduce_min_sync(RRTK_FULL, dp);
+                const unsigned wi = __reduce_min_sync(RRTK_FULL, (any && dp == wd) ? (unsigned)v : 0xffffffffu);
+                if (lane == 0) dst[k][warp] = make_int2(wd, (int)wi);
+            }
+        };
         {
             int ax[K], ay[K], thr[K], best[K];
 #pragma unroll
@@ -177,58 +264,13 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 ax[k] = c.x; ay[k] = c.y; thr[k] = c.z;
                 best[k] = 0x7fffffff;
             }
-            const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts) + tid;
-            for (int w = 0; w < nwords; ++w) {
-                uint32_t h[K];
-#pragma unroll
-                for (int k = 0; k < K; ++k) h[k] = 0;
-                const int s_end = min(steps, 8 * w + 8);
-                auto step = [&](int s, auto masked_c) {
-                    constexpr bool masked = decltype(masked_c)::value;
-                    const uint4 q = q4[s * T];
-                    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                    for (int e = 0; e < 4; e += 2) {
-                        int vx[2], vy[2], nvs[2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            vx[u] = px(wv[e + u]); vy[u] = py(wv[e + u]);
-                            const int row = 4 * s + e + u;
-                            nvs[u] = (vx[u] * vx[u] + vy[u] * vy[u]) * S + row;
-                            if (masked && row * T + tid >= j) { vx[u] = 0; vy[u] = 0; nvs[u] = kKeyDead; }
-                        }
-#pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const int d0 = vx[0] * ax[k] + (vy[0] * ay[k] + nvs[0]) - thr[k];
-                            const int d1 = vx[1] * ax[k] + (vy[1] * ay[k] + nvs[1]) - thr[k];
-                            if (KIND != RRTK_STANDARD) {
-                                h[k] = __funnelshift_l((uint32_t)d0, h[k], 1);
-                                h[k] = __funnelshift_l((uint32_t)d1, h[k], 1);
-                            }
-                            best[k] = min(best[k], min(d0, d1));
-                        }
-                    }
-                };
-                int s = 8 * w;
-                const int s_full = min(s_end, steps - 1);
-                for (; s < s_full; ++s) step(s, std::false_type{});
-                if (s < s_end) { step(s, std::true_type{}); ++s; }
-                if (KIND != RRTK_STANDARD) {
-                    const int fill = 32 - 4 * (s - 8 * w);                    // processed slot p  <->  bit 31 - p
-#pragma unroll
-                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + tid] = fill < 32 ? h[k] << fill : 0u;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < K; ++k) {   // warp minimum, lowest index among equals
-                const bool any = best[k] != 0x7fffffff;
-                const int key = best[k] + thr[k];
-                const int dp = any ? (key >> sbits) : 0x7fffffff;
-                const int v = (key & (S - 1)) * T + tid;
-                const int wd = __reduce_min_sync(RRTK_FULL, dp);
-                const unsigned wi = __reduce_min_sync(RRTK_FULL, (any && dp == wd) ? (unsigned)v : 0xffffffffu);
-                if (lane == 0) s_near[k][warp] = make_int2(wd, (int)wi);
-            }
+#ifdef RRTK_SPEC_SCAN
+            const int q_first = spec_ok ? spec_quads : 0;                 // those quads were scanned during the last commit phase
+#else
+            const int q_first = 0;
+#endif
+            scan_quads(tid, q_first, steps, true, true, ax, ay, thr, best);
+            fold_near(tid, thr, best, s_near);
         }
         __syncthreads();                                                   // ---- barrier: scan results visible
         PHASE_T(t_1);
@@ -248,7 +290,13 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             uint32_t bd;
             int vnear;
             {
+#ifdef RRTK_SPEC_SCAN
+                const int2 e = lane < NW ? s_near[k][lane]
+                                         : ((spec_ok && lane >= NW && lane < 2 * NW && lane - NW != cw_prev) ? s_near2[k][lane - NW]
+                                                                                                              : make_int2(0x7fffffff, 0x7fffffff));
+#else
                 const int2 e = lane < NW ? s_near[k][lane] : make_int2(0x7fffffff, 0x7fffffff);
+#endif
                 const int md = __reduce_min_sync(RRTK_FULL, e.x);
                 vnear = (int)__reduce_min_sync(RRTK_FULL, e.x == md ? (unsigned)e.y : 0xffffffffu);
                 bd = (uint32_t)(md + x * x + y * y);
@@ -410,7 +458,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 
         // ---- commit phase: warp 0 replays the results in sample order; lane m holds the m-th vertex
         //      accepted in this round ----------------------------------------------------------------
-        if (warp == 0) {
+        if (warp == RRTK_COMMIT_WARP) {
             // the stream samples the next round can start with (it0 + consumed + k, consumed <= kact <= K)
             short2 ahead = make_short2(0, 0);
             if (lane < 2 * K) ahead = samples[min(it0 + lane, n - 1)];
@@ -520,6 +568,47 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             }
             (void)cut;
         }
+#ifdef RRTK_SPEC_SCAN
+        // While warp 0 commits, the other warps scan the NEXT round's samples -- assuming this round consumes all of its kact
+        // samples, which the commit warp confirms or refutes in the summary -- against the quads of the tree that are full at
+        // the start of this round (new vertices land in later quads); warp 0's columns are shared out by membership word.
+        int spec_try = 0;
+        if (KIND != RRTK_INFORMED && it0 + kact + 1 < n) spec_try = j / (4 * T);
+        if (warp != cw && spec_try > 0) {
+            int ax[K], ay[K], thr[K], best[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int4 c = scan_consts(samples[min(it0 + kact + k, n - 1)], true);
+                ax[k] = c.x; ay[k] = c.y; thr[k] = c.z;
+                best[k] = 0x7fffffff;
+            }
+            scan_quads(tid, 0, spec_try, false, false, ax, ay, thr, best);
+            fold_near(tid, thr, best, s_near2);
+#pragma unroll
+            for (int k = 0; k < K; ++k) best[k] = 0x7fffffff;
+            bool more = false;
+            // the committing warp's columns, one membership word at a time, shared out among the others
+            for (int w0 = (warp - cw - 1 + NW) % NW; 8 * w0 < spec_try; w0 += NW - 1) {
+                scan_quads(cw * 32 + lane, 8 * w0, min(spec_try, 8 * w0 + 8), false, false, ax, ay, thr, best);
+                more = true;
+            }
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const bool any = best[k] != 0x7fffffff;
+                    const int key = best[k] + thr[k];
+                    const int dp = any ? (key >> sbits) : 0x7fffffff;
+                    const int v = (key & (S - 1)) * T + cw * 32 + lane;
+                    const int wd = __reduce_min_sync(RRTK_FULL, dp);
+                    const unsigned wi = __reduce_min_sync(RRTK_FULL, (any && dp == wd) ? (unsigned)v : 0xffffffffu);
+                    if (lane == 0) {
+                        const int2 cur = s_near2[k][warp];
+                        if (wd < cur.x || (wd == cur.x && (int)wi < cur.y)) s_near2[k][warp] = make_int2(wd, (int)wi);
+                    }
+                }
+            }
+        }
+#endif
         __syncthreads();                                                   // ---- barrier: tree updated
         PHASE_T(t_3);
         PHASE_ADD(clk_scan, t_0, t_1); PHASE_ADD(clk_owner, t_1, t_2); PHASE_ADD(clk_commit, t_2, t_3); PHASE_ADD(clk_ownwork, t_1, t_1b);
@@ -528,6 +617,12 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 #endif
         {
             const RoundSummary s = s_sum;
+#ifdef RRTK_SPEC_SCAN
+            spec_ok = spec_try > 0 && s.consumed == kact && !(s.flags & 2);
+            spec_quads = spec_try;
+            cw_prev = cw;
+            cw = (cw + 1) % NW;
+#endif
             j = s.j;
             it0 += s.consumed;
             have_sol = s.flags & 1;
@@ -601,6 +696,14 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         opts[v] = o;
         if (v >= top) { cost[v] = CUDART_INF; parent[v] = -1; }
     }
+#ifdef RRTK_SPEC_SCAN
+    if (lane == 0) {      // every warp has committed some rounds: add the counters up
+        atomicAdd(&s_cnt[0], (unsigned long long)ell_iters); atomicAdd(&s_cnt[1], (unsigned long long)nn_pairs);
+        atomicAdd(&s_cnt[2], (unsigned long long)ring_members); atomicAdd(&s_cnt[3], (unsigned long long)accepted);
+    }
+    __syncthreads();
+    ell_iters = (long long)s_cnt[0]; nn_pairs = (long long)s_cnt[1]; ring_members = (long long)s_cnt[2]; accepted = (long long)s_cnt[3];
+#endif
     if (tid == 0) {      // warp 0 carries the commit-phase counters
         if (found) { cost[j] = __longlong_as_double((long long)cstar_bits); parent[j] = vparent; }
         long long *st = P.stats + (size_t)plan * RRTK_STAT_COUNT;
