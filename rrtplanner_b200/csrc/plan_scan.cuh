@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 
     // -DRRTK_PHASE_CLOCKS (experiment builds, scripts/phase_clocks.py): cycles per phase in spare stats slots
 #ifdef RRTK_PHASE_CLOCKS
-    long long clk_scan = 0, clk_owner = 0, clk_commit = 0, clk_ownwork = 0, rounds = 0;
+    long long clk_scan = 0, clk_owner = 0, clk_commit = 0, clk_ownwork = 0, rounds = 0, spec_hits = 0;
 #define PHASE_T(var) const long long var = clock64()
 #define PHASE_ADD(acc, a, b) acc += (b) - (a)
 #else
@@ -622,6 +622,9 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             spec_quads = spec_try;
             cw_prev = cw;
             cw = (cw + 1) % NW;
+#ifdef RRTK_PHASE_CLOCKS
+            if (spec_ok) ++spec_hits;
+#endif
 #endif
             j = s.j;
             it0 += s.consumed;
@@ -725,6 +728,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         st[RRTK_STAT_ELL_ITERS] = clk_commit;
         st[RRTK_STAT_FIRST_SOL_ITER] = clk_ownwork;
         st[RRTK_STAT_RING_MEMBERS] = rounds;
+        st[RRTK_STAT_NN_PAIRS] = spec_hits;
 #endif
     }
 #undef WALK
