@@ -241,8 +241,8 @@ typedef struct {
     int32_t rewire;          /* 0: none (what the reference computes)   1: rewire as specified above (needs star) */
     int32_t nheadings;       /* DUBINS: 1 .. 255 heading values */
     double r_rewire;
-    double rho;              /* DUBINS: turning radius in cells, > 0 */
-    double ds;               /* DUBINS: arc-length step of the collision samples in cells, > 0 */
+    double rho;              /* DUBINS: turning radius in cells, 0 < rho <= 16384 */
+    double ds;               /* DUBINS: arc-length step of the collision samples in cells, 0.05 <= ds <= 16384 */
     const void *dubins_table; /* DUBINS, optional (NULL = none): DEVICE memo made by rrtk_dubins_table_build for the same
                                 nheadings and rho; edges whose |dx|, |dy| <= table_radius are looked up instead of evaluated */
     int32_t table_radius;

@@ -766,7 +766,8 @@ static int check_plan2_cfg(const rrtk_plan2_cfg *cfg)
     RRTK_REQUIRE(!cfg->dubins_table || (cfg->table_radius >= 1 && cfg->table_radius <= 1024), "rrtk_plan2: table_radius out of range");
     if (cfg->model == RRTK_MODEL_DUBINS) {
         RRTK_REQUIRE(cfg->nheadings >= 1 && cfg->nheadings <= 255, "rrtk_plan2: need 1 <= nheadings <= 255");
-        RRTK_REQUIRE(cfg->rho > 0.0 && cfg->ds > 0.0 && cfg->rho < 1e9 && cfg->ds < 1e9, "rrtk_plan2: need rho > 0 and ds > 0");
+        RRTK_REQUIRE(cfg->rho > 0.0 && cfg->rho <= 16384.0 && cfg->ds >= 0.05 && cfg->ds <= 16384.0,
+                     "rrtk_plan2: need 0 < rho <= 16384 and 0.05 <= ds <= 16384 (cells)");
     }
     return RRTK_OK;
 }
@@ -774,7 +775,8 @@ static int check_plan2_cfg(const rrtk_plan2_cfg *cfg)
 static int check_dubins_args(int nheadings, double rho, double ds)
 {
     RRTK_REQUIRE(nheadings >= 1 && nheadings <= 255, "dubins: need 1 <= nheadings <= 255");
-    RRTK_REQUIRE(rho > 0.0 && rho < 1e9 && ds > 0.0 && ds < 1e9, "dubins: need rho > 0 and ds > 0");
+    // bounds keep the number of sampled points per path finite and sane (a path is at most ~ W + H + 19 rho long)
+    RRTK_REQUIRE(rho > 0.0 && rho <= 16384.0 && ds >= 0.05 && ds <= 16384.0, "dubins: need 0 < rho <= 16384 and 0.05 <= ds <= 16384 (cells)");
     return RRTK_OK;
 }
 

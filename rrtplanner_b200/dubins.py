@@ -87,8 +87,8 @@ class RRTDubins(RRT):
     def __init__(self, og: np.ndarray, n: int, rho: float, nheadings: int = 16, ds: float = 1.0, costfn: callable = None,
                  pbar: bool = True, seed: int = 0):
         super().__init__(og, n, costfn=costfn, pbar=pbar, seed=seed)
-        if not (rho > 0 and ds > 0):
-            raise ValueError("rho and ds must be positive")
+        if not (0 < rho <= 16384 and 0.05 <= ds <= 16384):
+            raise ValueError("need 0 < rho <= 16384 and 0.05 <= ds <= 16384 (cells)")
         if not (1 <= int(nheadings) <= 255):
             raise ValueError("nheadings must be in [1, 255]")
         self.rho, self.nheadings, self.ds = float(rho), int(nheadings), float(ds)

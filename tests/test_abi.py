@@ -81,6 +81,8 @@ def test_k8_argument_checks_need_no_gpu(lib):
     bad = _lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 0, 2.0, 1.0)           # zero headings
     assert lib.rrtk_plan2_batch(_lib.ptr(bad), None, 8, 8, None, 1, 10, None, None, None, None, None, None, None, None, None, 0, None) == -1
     assert b"nheadings" in lib.rrtk_last_error()
+    tiny = _lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 5.0, 16, 2.0, 1e-9)        # a step that would sample ~1e10 points per path
+    assert lib.rrtk_plan2_batch(_lib.ptr(tiny), None, 8, 8, None, 1, 10, None, None, None, None, None, None, None, None, None, 0, None) == -1
     assert lib.rrtk_plan2_scratch_bytes(4, 100) >= 4 * 101 * 10 and lib.rrtk_plan2_scratch_bytes(-1, 100) == 0
     assert lib.rrtk_dubins_table_bytes(50, 16) == (101 * 101 * 256) * 33 + 16
     assert lib.rrtk_dubins_paths(None, 5, 16, 2.0, None, None, None, None) == -1
