@@ -274,3 +274,30 @@ def test_full_size_batch_properties(model):
                       r_rewire=r, nh=nh, rho=rho, ds=ds)
         _compare((res.pts[p], res.head[p], res.cost[p], res.elen[p], res.parent[p],
                   dict(zip(_lib.STAT2_NAMES, (int(v) for v in res.stats[p])))), want, model)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_sweep_against_the_specification(ctx, seed):
+    """Random shapes, radii, turning radii, heading counts, steps and flag combinations (seeded): every result bit-exact."""
+    rng = np.random.default_rng(1000 + seed)
+    model = "dubins" if seed % 3 else "euclid"
+    W, H = int(rng.integers(40, 200)), int(rng.integers(40, 200))
+    n = int(rng.integers(50, 900))
+    star = bool(rng.integers(0, 4))                       # mostly RRT*
+    rewire = star and bool(rng.integers(0, 3))
+    r = float(rng.uniform(5.0, 60.0)) if star else 0.0
+    nh = int(rng.choice([1, 4, 16, 64])) if model == "dubins" else 1
+    rho = float(rng.uniform(0.5, 12.0))
+    ds = float(rng.choice([0.5, 1.0, 2.0]))
+    og = worlds.perlin_occupancygrid(W, H, seed=int(rng.integers(0, 10000))).astype(np.uint8)
+    free = np.argwhere(og == 0)
+    if len(free) < 10:
+        pytest.skip("world without free space")
+    smp = np.concatenate([free[rng.integers(0, len(free), n)], rng.integers(0, nh, (n, 1))], axis=1)
+    start = [*free[rng.integers(0, len(free))], int(rng.integers(0, nh))]
+    goal = [*free[rng.integers(0, len(free))], int(rng.integers(0, nh))]
+    want = R.plan(model, og, n, start, goal, smp, star=star, rewire=rewire, r_rewire=r, nh=nh, rho=rho, ds=ds)
+    if want["stats"]["ring_members"] and r * r * np.pi > 1024 and n > 1024:
+        pytest.skip("radius set may exceed the kernel's list")
+    got = _run(ctx, model, og, n, start, goal, smp, star, rewire, r, nh, rho, ds)
+    _compare(got, want, model)
