@@ -288,36 +288,37 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             // ---- worker warps: B1 ascending radius list; lower bound on the new vertex's cost ---------------------
             constexpr int TW = T - 32;                            // worker threads
             if (m) {
-                unsigned long long lbk = 0xffffffffffffffffull;
                 // own slice of the tree, and warp 0 also takes the gate warp's slice
                 for (int part = 0; part < (warp == 0 ? 2 : 1); ++part) {
                     const int c0v = part ? (NW - 1) * chunk : v0, c1v = part ? min(j, c0v + chunk) : v1;
                     int off = part ? last_off : my_off;
                     for (int base = c0v; base < c1v; base += 32) {
                         const unsigned mk = mask[base >> 5];
-                        if ((mk >> lane) & 1u) {
-                            const int v = base + lane;
-                            ring[off + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)v;
-                            if (prune) {
-                                const double c = __dadd_rn(cost[v], __dsqrt_rn((double)dist2(spts[v], qx, qy)));
-                                const unsigned long long k = (unsigned long long)__double_as_longlong(c);
-                                lbk = k < lbk ? k : lbk;
-                            }
-                        }
+                        if ((mk >> lane) & 1u) ring[off + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)(base + lane);
                         off += __popc(mk);
                     }
-                }
-                if (prune) {
-                    lbk = warp_min_u64(lbk);
-                    if (lane == 0) s_wlb[warp] = lbk;
                 }
             }
             if (tid == 0) s_ntask2 = 0;
             asm volatile("bar.sync 1, %0;" ::"r"(TW) : "memory");
             // ---- B2: which members need the edge sample -> member: only those a vertex of cost >= lb could improve ---
             if (prune && m) {
-                unsigned long long lbk = (unsigned long long)__double_as_longlong(
-                    __dadd_rn(cost[vnear], __dsqrt_rn((double)(uint32_t)(nk >> 32))));
+                // lower bound on the new vertex's cost, min over the members of cost + straight-line distance, taken over the
+                // dense list (in the sparse ballot loop above it ran with one or two active lanes per step)
+                unsigned long long lbk = 0xffffffffffffffffull;
+                for (int base = warp * 32; base < m; base += TW) {
+                    const int i = base + lane;
+                    if (i < m) {
+                        const int vn = ring[i];
+                        const double c = __dadd_rn(cost[vn], __dsqrt_rn((double)dist2(spts[vn], qx, qy)));
+                        const unsigned long long k = (unsigned long long)__double_as_longlong(c);
+                        lbk = k < lbk ? k : lbk;
+                    }
+                }
+                lbk = warp_min_u64(lbk);
+                if (lane == 0) s_wlb[warp] = lbk;
+                asm volatile("bar.sync 1, %0;" ::"r"(TW) : "memory");
+                lbk = (unsigned long long)__double_as_longlong(__dadd_rn(cost[vnear], __dsqrt_rn((double)(uint32_t)(nk >> 32))));
 #pragma unroll
                 for (int w = 0; w < NW - 1; ++w) lbk = s_wlb[w] < lbk ? s_wlb[w] : lbk;
                 // every edge is at least as long as the straight line up to rounding (and the 1e-9 snap of mod2pi): 1e-6 cells of slack
