@@ -82,6 +82,15 @@ int rrtk_set_device(int device);
 /* SM count and opt-in shared memory per block of the current device */
 int rrtk_device_info(int *sm_count, int *smem_optin_bytes);
 
+/* Roofline denominators measured on the device at hand (bench.py; SURVEY.md section 8(d) bounds the nearest / radius
+ * scan of rrt.py:131-181 by shared-memory bandwidth and the collision walk of rrt.py:183-229 by L2 bandwidth, and
+ * MEASURED_PEAKS.json holds neither).  Each call launches one read sweep on `stream` and reports the bytes it reads;
+ * the caller times it with events.  rrtk_peak_l2_read: `passes` sweeps over d_buf (choose `bytes` between the L1 and
+ * the L2 size; warm L2 with one untimed call).  rrtk_peak_smem_read: one block per SM reads its shared memory `iters`
+ * times with conflict-free 16-byte loads (smem_bytes <= 0: as much as a block may have). */
+int rrtk_peak_l2_read(const void *d_buf, size_t bytes, int passes, uint32_t *d_sink, int64_t *bytes_read, void *stream);
+int rrtk_peak_smem_read(int smem_bytes, int iters, uint32_t *d_sink, int64_t *bytes_read, void *stream);
+
 /* ---- occupancy grids ------------------------------------------------------------------------- */
 /* uint32 words of one tiled bit grid */
 size_t rrtk_grid_words(int W, int H);
@@ -215,6 +224,15 @@ int rrtk_plan_footprint(int kind, int W, int H, int n, int threads, int *smem_by
  * to cap vertex ids per plan, root first; d_len the path length (0 if vgoal has no parent chain) */
 int rrtk_extract_paths(const int32_t *d_parent, const int64_t *d_stats, int nplans, int n, int cap,
                        int32_t *d_path, int32_t *d_len, void *stream);
+
+/* The same walk, returning what a caller of the reference ends up holding for a plan (rrt.py:87-129): vertex ids
+ * root -> goal (route2gv), their points (the sequence vertices_as_ndarray pairs up into segments) and the path cost
+ * (vcosts[vgoal]; 0 with a one-vertex path when the goal was not connected).  Rows are padded to cap entries with
+ * -1 / (-32768, -32768); d_len may exceed cap, in which case that plan's row is left unwritten.  This fixed-size
+ * record is what a multi-GPU run gathers (rrtplanner_b200/multigpu.py). */
+int rrtk_extract_paths_xy(const int32_t *d_parent, const int16_t *d_pts, const double *d_cost, const int64_t *d_stats,
+                          int nplans, int n, int cap, int32_t *d_path, int16_t *d_xy, int32_t *d_len,
+                          double *d_path_cost, void *stream);
 
 /* ---- K8: planners the reference advertises but does not ship ---------------------------------------- */
 /*

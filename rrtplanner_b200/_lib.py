@@ -54,6 +54,8 @@ SIGNATURES = {
     "rrtk_device_count": (_i, []),
     "rrtk_set_device": (_i, [_i]),
     "rrtk_device_info": (_i, [_vp, _vp]),
+    "rrtk_peak_l2_read": (_i, [_vp, _sz, _i, _vp, _vp, _vp]),
+    "rrtk_peak_smem_read": (_i, [_i, _i, _vp, _vp, _vp]),
     "rrtk_grid_words": (_sz, [_i, _i]),
     "rrtk_pack_grid": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "rrtk_unpack_grid": (_i, [_vp, _i, _i, _i, _vp, _vp]),
@@ -76,6 +78,7 @@ SIGNATURES = {
     "rrtk_plan_batch": (_i, [_i, _vp, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "rrtk_plan_footprint": (_i, [_i, _i, _i, _i, _i, _vp, _vp]),
     "rrtk_extract_paths": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rrtk_extract_paths_xy": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "rrtk_create": (_i, [_vp]),
     "rrtk_destroy": (_i, [_vp]),
     "rrtk_ctx_set_grids": (_i, [_vp, _vp, _i, _i, _i, _vp]),

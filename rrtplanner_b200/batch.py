@@ -148,9 +148,19 @@ def plan_batch(kind, ogs, n, starts, goals, world_ids=None, r_rewire=0.0, r_goal
     """End-to-end batched plan() from host arrays through ``rrtk_ctx_plan_worlds``.
 
     ogs: (nworlds, W, H) array, non-zero = obstacle.  Either ``samples`` (P, n, 2) -- the explicit
-    sample streams -- or ``seeds`` (P,) -- plan p draws what a planner built with seed=seeds[p] would.
+    sample streams -- or ``seeds`` (P,) -- plan p's free-space stream is what a planner built with
+    seed=seeds[p] draws (``default_rng(seed).integers(0, nfree, n)``, rrt.py:85,240).
+
+    Informed plans take their ellipse phase from pre-generated streams: ``balls`` (P, n, 2), the unit-disc
+    point iteration i would use (rrt.py:579-587), and ``rots`` (P, 2, 2), ``rotation_to_world_frame`` of each
+    pair (rrt.py:601-613).  Both are required: without ``balls`` the kernel runs as a probe that stops at the
+    first solution vertex, and without ``rots`` every ellipse sample collapses onto the centre, so neither is
+    accepted silently.  (RRTStarInformed.plan() composes the two launches that reproduce the reference's single
+    interleaved generator; a batch has no such generator.)
     """
     k = KINDS[kind] if isinstance(kind, str) else int(kind)
+    if k == _lib.KIND_INFORMED and (balls is None or rots is None):
+        raise ValueError("plan_batch('informed', ...) needs both balls (P, n, 2) and rots (P, 2, 2); see the docstring")
     ogs = np.asarray(ogs)
     if ogs.ndim == 2:
         ogs = ogs[None]
@@ -302,6 +312,20 @@ class DeviceBatch:
             _lib.check(self.L.rrtk_extract_paths(self._p(self.out["parent"]), self._p(self.out["stats"]), self.nplans, self.n, cap,
                                                  self._p(path), self._p(ln), self._stream()), "extract_paths")
         return path, ln
+
+    def path_records(self, cap: int = 256):
+        """Fixed-size per-plan records on the device -- what a caller of the reference keeps of a plan (rrt.py:87-129):
+        path vertex ids, their points, path length, path cost -- plus the statistics row.  Dict of torch tensors with
+        leading dimension nplans; the unit multigpu.gather_tensors moves."""
+        t = self.torch
+        P = self.nplans
+        rec = dict(path=self._empty((P, cap), t.int32), xy=self._empty((P, cap, 2), t.int16), len=self._empty((P,), t.int32),
+                   path_cost=self._empty((P,), t.float64), stats=self.out["stats"])
+        with t.cuda.device(self.dev):
+            _lib.check(self.L.rrtk_extract_paths_xy(self._p(self.out["parent"]), self._p(self.out["pts"]), self._p(self.out["cost"]),
+                                                    self._p(self.out["stats"]), P, self.n, cap, self._p(rec["path"]), self._p(rec["xy"]),
+                                                    self._p(rec["len"]), self._p(rec["path_cost"]), self._stream()), "extract_paths_xy")
+        return rec
 
     def footprint(self):
         import ctypes as C

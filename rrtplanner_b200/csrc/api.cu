@@ -48,6 +48,8 @@ int plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, in
                 const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int plan_footprint(int, int, int, int, int, int, int, int *, int *);
 int paths_launch(const int32_t *, const int64_t *, int, int, int, int32_t *, int32_t *, cudaStream_t);
+int paths_xy_launch(const int32_t *, const int16_t *, const double *, const int64_t *, int, int, int, int32_t *, int16_t *, int32_t *,
+                    double *, cudaStream_t);
 int plan2_launch(const rrtk_plan2_cfg &, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, const int16_t *, const uint8_t *,
                  int16_t *, uint8_t *, double *, double *, int32_t *, int64_t *, void *, int, int, cudaStream_t);
 size_t plan2_scratch_bytes(int, int);
@@ -55,6 +57,8 @@ int plan2_footprint(int, int, int, int, int *, int *);
 int dubins_paths_launch(const int32_t *, int64_t, int, double, int32_t *, double *, double *, cudaStream_t);
 size_t dubins_table_bytes(int, int);
 int dubins_table_launch(int, int, double, void *, int, cudaStream_t);
+int l2_read_launch(const void *, size_t, int, int, uint32_t *, cudaStream_t);
+int smem_read_launch(int, int, int, uint32_t *, cudaStream_t);
 int dubins_walk_launch(const uint32_t *, int, int, const int32_t *, const int32_t *, int64_t, int, double, double, uint8_t *, int,
                        double *, int32_t *, cudaStream_t);
 
@@ -338,6 +342,38 @@ int rrtk_extract_paths(const int32_t *d_parent, const int64_t *d_stats, int npla
     RRTK_REQUIRE(d_parent && d_stats && d_path && d_len && nplans >= 0 && n >= 1 && cap >= 1, "rrtk_extract_paths: bad argument");
     if (nplans == 0) return RRTK_OK;
     return paths_launch(d_parent, d_stats, nplans, n, cap, d_path, d_len, (cudaStream_t)stream);
+}
+
+int rrtk_extract_paths_xy(const int32_t *d_parent, const int16_t *d_pts, const double *d_cost, const int64_t *d_stats, int nplans,
+                          int n, int cap, int32_t *d_path, int16_t *d_xy, int32_t *d_len, double *d_path_cost, void *stream)
+{
+    RRTK_REQUIRE(d_parent && d_pts && d_cost && d_stats && d_path && d_xy && d_len && d_path_cost && nplans >= 0 && n >= 1 && cap >= 1,
+                 "rrtk_extract_paths_xy: bad argument");
+    if (nplans == 0) return RRTK_OK;
+    return paths_xy_launch(d_parent, d_pts, d_cost, d_stats, nplans, n, cap, d_path, d_xy, d_len, d_path_cost, (cudaStream_t)stream);
+}
+
+// ---- measured roofline denominators (csrc/peaks.cu) ---------------------------------------------------
+int rrtk_peak_l2_read(const void *d_buf, size_t bytes, int passes, uint32_t *d_sink, int64_t *bytes_read, void *stream)
+{
+    RRTK_REQUIRE(d_buf && d_sink && bytes >= 4096 && passes >= 1, "rrtk_peak_l2_read: bad argument");
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    if (bytes_read) *bytes_read = (int64_t)(bytes / 16 * 16) * passes;
+    return l2_read_launch(d_buf, bytes, passes, d->sms, d_sink, (cudaStream_t)stream);
+}
+
+int rrtk_peak_smem_read(int smem_bytes, int iters, uint32_t *d_sink, int64_t *bytes_read, void *stream)
+{
+    RRTK_REQUIRE(d_sink && iters >= 1, "rrtk_peak_smem_read: bad argument");
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    if (smem_bytes <= 0 || smem_bytes > d->optin) smem_bytes = d->optin;
+    int words16 = smem_bytes / 16;
+    words16 -= words16 % (1024 * 8);
+    RRTK_REQUIRE(words16 > 0, "rrtk_peak_smem_read: need at least 128 KB of shared memory per block");
+    if (bytes_read) *bytes_read = (int64_t)words16 * 16 * iters * d->sms;
+    return smem_read_launch(words16 * 16, iters, d->sms, d_sink, (cudaStream_t)stream);
 }
 
 // ---- host-buffer context ---------------------------------------------------------------------------

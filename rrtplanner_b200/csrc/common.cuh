@@ -40,16 +40,23 @@ struct GlobalGrid {
     __device__ __forceinline__ uint32_t load(uint32_t i) const { return __ldg(w + i); }
 };
 
-// floor(num / den) for 0 <= num < 2^24, 0 < den < 2^24 and a quotient <= 64, via one approximate
-// fp32 reciprocal and a +-1 fix-up (the estimate is within 1e-5 of the true quotient).
+// floor(num / den) for 0 <= num < 2^23, 0 < den <= 2^15 and a quotient <= 64, via one approximate fp32 reciprocal.
+// (num + 1/2) / den lies at least 1 / (2 den) >= 1.5e-5 away from every integer, and the computed value is within
+// 64 * 3 * 2^-24 = 1.2e-5 of it (one ulp for the reciprocal estimate, half an ulp each for the two roundings), so
+// truncation gives the exact quotient without a fix-up.  -DRRTK_DIV_FIXUP: the earlier estimate with a +-1 correction.
 __device__ __forceinline__ int small_div(int num, int den, int &rem)
 {
     float inv;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__int2float_rn(den)));      // one MUFU; the fix-up absorbs its error
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__int2float_rn(den)));      // one MUFU
+#ifdef RRTK_DIV_FIXUP
     int q = __float2int_rz(__int2float_rn(num) * inv);
     int r = num - q * den;
     if (r < 0) { r += den; --q; }
     if (r >= den) { r -= den; ++q; }
+#else
+    const int q = __float2int_rz((__int2float_rn(num) + 0.5f) * inv);
+    const int r = num - q * den;
+#endif
     rem = r;
     return q;
 }

@@ -61,7 +61,7 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
     if (kind != RRTK_STANDARD) s.smem += (size_t)4 * s.hit_words * s.K * T + (size_t)2 * (T / 32) * s.list_cap;   // one list per warp
     s.smem = (s.smem + 15) & ~(size_t)15;
     if (s.smem > (size_t)optin - 2048) return false;
-    int by_smem = (int)((size_t)sm_smem / (s.smem + 896 + 1024));        // + static + per-block reservation
+    int by_smem = (int)((size_t)sm_smem / (s.smem + 1600 + 1024));       // + static (upper bound) + per-block reservation
     int by_threads = 2048 / T;
     int b = by_smem < by_threads ? by_smem : by_threads;
     const int by_regs = 65536 / (T * (65536 / (T * scan_min_blocks(T)) / 8 * 8));
@@ -136,6 +136,41 @@ __global__ void paths_kernel(const int *parent, const long long *stats, int npla
     if (L > cap) return;
     int u = v;
     for (int k = L - 1; k >= 0; --k) { out[k] = u; u = u > 0 ? par[u] : 0; }
+}
+
+// the same walk, also emitting what a caller of the reference ends up holding for a plan: the path's points
+// (vertices_as_ndarray, rrt.py:109-129, as the point sequence) and its cost (vcosts[vgoal])
+__global__ void paths_xy_kernel(const int *parent, const short2 *pts, const double *cost, const long long *stats, int nplans, int n,
+                                int cap, int *path, short2 *xy, int *len, double *pcost)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nplans) return;
+    const size_t row = (size_t)p * (n + 1);
+    const int *par = parent + row;
+    int v = (int)stats[(size_t)p * RRTK_STAT_COUNT + RRTK_STAT_VGOAL];
+    int depth = 0;
+    for (int u = v; u > 0 && depth <= n; u = par[u]) ++depth;
+    const int L = depth + 1;
+    len[p] = L;
+    pcost[p] = cost[row + v];
+    if (L > cap) return;
+    int u = v;
+    for (int k = L - 1; k >= 0; --k) {
+        path[(size_t)p * cap + k] = u;
+        xy[(size_t)p * cap + k] = pts[row + u];
+        u = u > 0 ? par[u] : 0;
+    }
+    for (int k = L; k < cap; ++k) { path[(size_t)p * cap + k] = -1; xy[(size_t)p * cap + k] = make_short2(-32768, -32768); }
+}
+
+int paths_xy_launch(const int32_t *d_parent, const int16_t *d_pts, const double *d_cost, const int64_t *d_stats, int nplans, int n, int cap,
+                    int32_t *d_path, int16_t *d_xy, int32_t *d_len, double *d_pcost, cudaStream_t st)
+{
+    paths_xy_kernel<<<(nplans + 127) / 128, 128, 0, st>>>(d_parent, reinterpret_cast<const short2 *>(d_pts), d_cost,
+                                                         reinterpret_cast<const long long *>(d_stats), nplans, n, cap, d_path,
+                                                         reinterpret_cast<short2 *>(d_xy), d_len, d_pcost);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
 }
 
 int paths_launch(const int32_t *d_parent, const int64_t *d_stats, int nplans, int n, int cap, int32_t *d_path,

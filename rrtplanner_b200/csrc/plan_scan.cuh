@@ -29,10 +29,10 @@
 //            (rrt.py:424/506/706; its first grid word and the nearest vertex's cost are requested
 //            before the radius set is compacted), FP64 cost via the nearest vertex, compaction of
 //            the membership words into a dense list, choose-parent (rrt.py:510-521) cheapest first:
-//            three members per lane are costed together, the cheapest one of the warp that beats
+//            up to three members per lane are costed together, the cheapest one of the warp that beats
 //            the nearest vertex is walked, and the first free one wins (ties: lowest index).
 //   barrier
-//   commit   warp 0 replays the K results in sample order against the vertices accepted earlier in
+//   commit   one warp (the duty rotates, see cw) replays the K results in sample order against the vertices accepted earlier in
 //            the same round (one per lane): equal cell -> duplicate; inside the radius -> extra
 //            candidate (cost, walk); strictly nearer than the recorded nearest vertex, or a change
 //            of the informed sampler's state -> the round is cut there and the remaining samples
@@ -64,10 +64,13 @@ __device__ __forceinline__ int tree_slot(int v)
 #ifndef RRTK_MINB128
 #define RRTK_MINB128 7
 #endif
+#ifndef RRTK_MINB256
+#define RRTK_MINB256 3
+#endif
 template <int KIND, int K, int T>
 struct ScanCfg {
     // resident blocks per SM the register allocation aims for
-    static constexpr int kMinBlocks = (T <= 64) ? 12 : (T <= 128) ? RRTK_MINB128 : (T <= 160) ? 5 : (T <= 256) ? 3 : 1;
+    static constexpr int kMinBlocks = (T <= 64) ? 12 : (T <= 128) ? RRTK_MINB128 : (T <= 160) ? 5 : (T <= 256) ? RRTK_MINB256 : 1;
 };
 
 template <int KIND, int K, int T>
@@ -77,9 +80,6 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
     static_assert(T % 32 == 0 && K <= 16 && K >= 1, "block shape");
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ int2 s_near[K][NW];                    // [sample][warp] (min key >> sbits, vertex)
-#ifdef RRTK_SPEC_SCAN
-    __shared__ int2 s_near2[K][NW];                   // the same from the speculative scan of the tree's full quads (see the commit phase)
-#endif
     __shared__ SampleRec s_rec[K];
     __shared__ RoundSummary s_sum;
     __shared__ short2 s_q[K];                         // samples of the round
@@ -143,29 +143,22 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 
     // block-uniform state, replicated in every thread (refreshed from s_sum after each round)
     int j = 1, it0 = 0;
-#ifdef RRTK_SPEC_SCAN
-    bool spec_ok = false;               // the quads [0, spec_quads) of this round's scan were done during the last commit phase
-    int spec_quads = 0;
-    int cw = 0, cw_prev = 0;            // the warp that commits this round / committed the last one: the duty rotates, because
-                                        // warp w of every block sits on scheduler w mod 4 and the committing warp's columns are
-                                        // scanned by its neighbours -- a fixed choice would overload one scheduler of the SM
-    __shared__ unsigned long long s_cnt[4];   // commit-phase counters of all warps, summed at the end
+    // The commit duty rotates over the warps: warp w of every resident block sits on scheduler w mod 4 of the SM, so a
+    // fixed commit warp would load one scheduler with all the serial work of every block (-DRRTK_FIXED_COMMIT: warp 0).
+    int cw = 0;
+    __shared__ unsigned long long s_cnt[4];           // commit-phase counters of all warps, summed at the end
     if (tid < 4) s_cnt[tid] = 0ull;
-#define RRTK_COMMIT_WARP cw
-#else
-#define RRTK_COMMIT_WARP 0
-#endif
     bool have_sol = false;              // INFORMED: running least_cost over vsoln (rrt.py:627-633)
     int vsol = 0;
     double csol = 0.0;
     long long first_sol = -1;
-    // counters kept by warp 0 (commit phase) / per warp (walks)
+    // counters kept by the committing warp (every warp takes its turn) / per warp (walks)
     long long ell_iters = 0, nn_pairs = 0, ring_members = 0, accepted = 0;
     unsigned my_checks = 0, my_cells = 0;
 
     // -DRRTK_PHASE_CLOCKS (experiment builds, scripts/phase_clocks.py): cycles per phase in spare stats slots
 #ifdef RRTK_PHASE_CLOCKS
-    long long clk_scan = 0, clk_owner = 0, clk_commit = 0, clk_ownwork = 0, rounds = 0, spec_hits = 0;
+    long long clk_scan = 0, clk_owner = 0, clk_commit = 0, clk_ownwork = 0, rounds = 0;
 #define PHASE_T(var) const long long var = clock64()
 #define PHASE_ADD(acc, a, b) acc += (b) - (a)
 #else
@@ -184,65 +177,6 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         const int rows = (j + T - 1) / T;
         const int steps = (rows + 3) >> 2;
         const int nwords = (steps + 7) >> 3;
-        // One column (the vertices v = row * T + col) over the quads [qa, qb): membership bits appended to the column's words,
-        // running minima in best[].  A word that an earlier call left incomplete (stored unshifted) is continued; `finish`
-        // stores the last word in its final, left-aligned form even when it is incomplete (and even if qa == qb).
-        auto scan_quads = [&](int col, int qa, int qb, bool mask_last, bool finish, const int (&ax)[K], const int (&ay)[K],
-                              const int (&thr)[K], int (&best)[K]) {
-            const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts) + col;
-            auto step = [&](int s, uint32_t (&h)[K], auto masked_c) {
-                constexpr bool masked = decltype(masked_c)::value;
-                const uint4 q = q4[s * T];
-                const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int e = 0; e < 4; e += 2) {
-                    int vx[2], vy[2], nvs[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        vx[u] = px(wv[e + u]); vy[u] = py(wv[e + u]);
-                        const int row = 4 * s + e + u;
-                        nvs[u] = (vx[u] * vx[u] + vy[u] * vy[u]) * S + row;
-                        if (masked && row * T + col >= j) { vx[u] = 0; vy[u] = 0; nvs[u] = kKeyDead; }
-                    }
-#pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int d0 = vx[0] * ax[k] + (vy[0] * ay[k] + nvs[0]) - thr[k];
-                        const int d1 = vx[1] * ax[k] + (vy[1] * ay[k] + nvs[1]) - thr[k];
-                        if (KIND != RRTK_STANDARD) {
-                            h[k] = __funnelshift_l((uint32_t)d0, h[k], 1);
-                            h[k] = __funnelshift_l((uint32_t)d1, h[k], 1);
-                        }
-                        best[k] = min(best[k], min(d0, d1));
-                    }
-                }
-            };
-            int s = qa;
-            if (qa == qb) {
-                if (finish && (qa & 7) && KIND != RRTK_STANDARD) {       // nothing new, but the word the range would continue must be finalised
-                    const int w = qa >> 3, fill = 32 - 4 * (qa & 7);
-#pragma unroll
-                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + col] <<= fill;
-                }
-                return;
-            }
-            while (s < qb) {
-                const int w = s >> 3;
-                const int s_end = min(qb, 8 * w + 8);
-                uint32_t h[K];
-                const bool resume = (s & 7) != 0;                          // an earlier call stored this word unshifted
-#pragma unroll
-                for (int k = 0; k < K; ++k) h[k] = (resume && KIND != RRTK_STANDARD) ? s_hits[(w * K + k) * T + col] : 0u;
-                const int s_full = mask_last ? min(s_end, qb - 1) : s_end;
-                for (; s < s_full; ++s) step(s, h, std::false_type{});
-                if (s < s_end) { step(s, h, std::true_type{}); ++s; }
-                if (KIND != RRTK_STANDARD) {
-                    const int done = s - 8 * w;
-                    const int fill = (done == 8 || (finish && s == qb)) ? 32 - 4 * done : 0;   // processed slot p  <->  bit 31 - p
-#pragma unroll
-                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + col] = fill < 32 ? h[k] << fill : 0u;
-                }
-            }
-        };
         // fold the running minima of a warp into (distance key, vertex) per sample; col = the column each lane scanned
         auto fold_near = [&](int col, const int (&thr)[K], const int (&best)[K], int2 (*dst)[NW]) {
 #pragma unroll
@@ -264,12 +198,54 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 ax[k] = c.x; ay[k] = c.y; thr[k] = c.z;
                 best[k] = 0x7fffffff;
             }
-#ifdef RRTK_SPEC_SCAN
-            const int q_first = spec_ok ? spec_quads : 0;                 // those quads were scanned during the last commit phase
-#else
-            const int q_first = 0;
-#endif
-            scan_quads(tid, q_first, steps, true, true, ax, ay, thr, best);
+            // column tid of the tree, one quad (LDS.128 = rows 4s .. 4s+3) per step; the last, partly empty quad is masked
+            // and done in halves (rows 4s, 4s+1 always; 4s+2, 4s+3 only if the tree reaches them)
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(s_pts) + tid;
+            auto pair_step = [&](const uint32_t w0, const uint32_t w1, int row0, uint32_t (&h)[K], auto masked_c) {
+                constexpr bool masked = decltype(masked_c)::value;
+                int vx[2], vy[2], nvs[2];
+                const uint32_t wv[2] = {w0, w1};
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    vx[u] = px(wv[u]); vy[u] = py(wv[u]);
+                    nvs[u] = (vx[u] * vx[u] + vy[u] * vy[u]) * S + (row0 + u);
+                    if (masked && (row0 + u) * T + tid >= j) { vx[u] = 0; vy[u] = 0; nvs[u] = kKeyDead; }
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int d0 = vx[0] * ax[k] + (vy[0] * ay[k] + nvs[0]) - thr[k];
+                    const int d1 = vx[1] * ax[k] + (vy[1] * ay[k] + nvs[1]) - thr[k];
+                    if (KIND != RRTK_STANDARD) {
+                        h[k] = __funnelshift_l((uint32_t)d0, h[k], 1);
+                        h[k] = __funnelshift_l((uint32_t)d1, h[k], 1);
+                    }
+                    best[k] = min(best[k], min(d0, d1));
+                }
+            };
+            for (int w = 0; w < nwords; ++w) {          // one membership word = 32 rows = 8 quads; row r of the word -> bit 31 - r
+                uint32_t h[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) h[k] = 0u;
+                const int s_end = min(steps, 8 * w + 8);
+                const int s_full = (s_end == steps) ? s_end - 1 : s_end;
+                int s = 8 * w;
+                for (; s < s_full; ++s) {
+                    const uint4 q = q4[s * T];
+                    pair_step(q.x, q.y, 4 * s, h, std::false_type{});
+                    pair_step(q.z, q.w, 4 * s + 2, h, std::false_type{});
+                }
+                int nrow = 4 * (s - 8 * w);
+                if (s < s_end) {
+                    const uint4 q = q4[s * T];
+                    pair_step(q.x, q.y, 4 * s, h, std::true_type{});
+                    nrow += 2;
+                    if (rows > 4 * s + 2) { pair_step(q.z, q.w, 4 * s + 2, h, std::true_type{}); nrow += 2; }
+                }
+                if (KIND != RRTK_STANDARD) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + tid] = h[k] << (32 - nrow);   // 2 <= nrow <= 32
+                }
+            }
             fold_near(tid, thr, best, s_near);
         }
         __syncthreads();                                                   // ---- barrier: scan results visible
@@ -290,13 +266,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             uint32_t bd;
             int vnear;
             {
-#ifdef RRTK_SPEC_SCAN
-                const int2 e = lane < NW ? s_near[k][lane]
-                                         : ((spec_ok && lane >= NW && lane < 2 * NW && lane - NW != cw_prev) ? s_near2[k][lane - NW]
-                                                                                                              : make_int2(0x7fffffff, 0x7fffffff));
-#else
                 const int2 e = lane < NW ? s_near[k][lane] : make_int2(0x7fffffff, 0x7fffffff);
-#endif
                 const int md = __reduce_min_sync(RRTK_FULL, e.x);
                 vnear = (int)__reduce_min_sync(RRTK_FULL, e.x == md ? (unsigned)e.y : 0xffffffffu);
                 bd = (uint32_t)(md + x * x + y * y);
@@ -358,7 +328,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                     if (KIND != RRTK_STANDARD) {
                         ring = total;
                         if (total <= cap) {
-                            // choose-parent (rrt.py:510-521), cheapest first: three candidates per lane have their costs
+                            // choose-parent (rrt.py:510-521), cheapest first: up to three candidates per lane have their costs
                             // loaded and evaluated together; the cheapest live one of the warp is walked, and the first
                             // free one is the minimum over (cost, index) of everything that beats the nearest vertex.
                             // (the list is in lane order, not index order: every tie is resolved on the vertex index)
@@ -367,19 +337,25 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                                 uint32_t cp[3];
                                 unsigned long long ck[3];                     // cost bits; ~0 = not a candidate
                                 double ccv[3];
+                                const int left = total - base;                // slots u with 32 u >= left are empty for every lane
 #pragma unroll
                                 for (int u = 0; u < 3; ++u) {
-                                    const int idx = base + 32 * u + lane;
-                                    const bool has = idx < total;
-                                    cv[u] = has ? (int)list[idx] : 0;
-                                    cp[u] = s_pts[tree_slot<T>(cv[u])];
-                                    ccv[u] = has ? cost[cv[u]] : CUDART_INF;
+                                    ck[u] = ~0ull; cv[u] = 0; cp[u] = 0u; ccv[u] = CUDART_INF;
+                                    if (32 * u < left) {
+                                        const int idx = base + 32 * u + lane;
+                                        const bool has = idx < total;
+                                        cv[u] = has ? (int)list[idx] : 0;
+                                        cp[u] = s_pts[tree_slot<T>(cv[u])];
+                                        if (has) ccv[u] = cost[cv[u]];
+                                    }
                                 }
 #pragma unroll
                                 for (int u = 0; u < 3; ++u) {
-                                    const double cn = reach_cost(ccv[u], dist2(cp[u], x, y));
-                                    const bool live = cn < c0 && (cn < wc || (cn == wc && cv[u] < wv));
-                                    ck[u] = live ? (unsigned long long)__double_as_longlong(cn) : ~0ull;   // positive doubles order like their bits
+                                    if (32 * u < left) {
+                                        const double cn = reach_cost(ccv[u], dist2(cp[u], x, y));
+                                        const bool live = cn < c0 && (cn < wc || (cn == wc && cv[u] < wv));
+                                        if (live) ck[u] = (unsigned long long)__double_as_longlong(cn);   // positive doubles order like their bits
+                                    }
                                 }
                                 for (;;) {
                                     // this lane's cheapest live candidate, lowest vertex index among equal costs
@@ -458,7 +434,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 
         // ---- commit phase: warp 0 replays the results in sample order; lane m holds the m-th vertex
         //      accepted in this round ----------------------------------------------------------------
-        if (warp == RRTK_COMMIT_WARP) {
+        if (warp == cw) {
             // the stream samples the next round can start with (it0 + consumed + k, consumed <= kact <= K)
             short2 ahead = make_short2(0, 0);
             if (lane < 2 * K) ahead = samples[min(it0 + lane, n - 1)];
@@ -568,47 +544,6 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             }
             (void)cut;
         }
-#ifdef RRTK_SPEC_SCAN
-        // While warp 0 commits, the other warps scan the NEXT round's samples -- assuming this round consumes all of its kact
-        // samples, which the commit warp confirms or refutes in the summary -- against the quads of the tree that are full at
-        // the start of this round (new vertices land in later quads); warp 0's columns are shared out by membership word.
-        int spec_try = 0;
-        if (KIND != RRTK_INFORMED && it0 + kact + 1 < n) spec_try = j / (4 * T);
-        if (warp != cw && spec_try > 0) {
-            int ax[K], ay[K], thr[K], best[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int4 c = scan_consts(samples[min(it0 + kact + k, n - 1)], true);
-                ax[k] = c.x; ay[k] = c.y; thr[k] = c.z;
-                best[k] = 0x7fffffff;
-            }
-            scan_quads(tid, 0, spec_try, false, false, ax, ay, thr, best);
-            fold_near(tid, thr, best, s_near2);
-#pragma unroll
-            for (int k = 0; k < K; ++k) best[k] = 0x7fffffff;
-            bool more = false;
-            // the committing warp's columns, one membership word at a time, shared out among the others
-            for (int w0 = (warp - cw - 1 + NW) % NW; 8 * w0 < spec_try; w0 += NW - 1) {
-                scan_quads(cw * 32 + lane, 8 * w0, min(spec_try, 8 * w0 + 8), false, false, ax, ay, thr, best);
-                more = true;
-            }
-            if (more) {
-#pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const bool any = best[k] != 0x7fffffff;
-                    const int key = best[k] + thr[k];
-                    const int dp = any ? (key >> sbits) : 0x7fffffff;
-                    const int v = (key & (S - 1)) * T + cw * 32 + lane;
-                    const int wd = __reduce_min_sync(RRTK_FULL, dp);
-                    const unsigned wi = __reduce_min_sync(RRTK_FULL, (any && dp == wd) ? (unsigned)v : 0xffffffffu);
-                    if (lane == 0) {
-                        const int2 cur = s_near2[k][warp];
-                        if (wd < cur.x || (wd == cur.x && (int)wi < cur.y)) s_near2[k][warp] = make_int2(wd, (int)wi);
-                    }
-                }
-            }
-        }
-#endif
         __syncthreads();                                                   // ---- barrier: tree updated
         PHASE_T(t_3);
         PHASE_ADD(clk_scan, t_0, t_1); PHASE_ADD(clk_owner, t_1, t_2); PHASE_ADD(clk_commit, t_2, t_3); PHASE_ADD(clk_ownwork, t_1, t_1b);
@@ -617,14 +552,8 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 #endif
         {
             const RoundSummary s = s_sum;
-#ifdef RRTK_SPEC_SCAN
-            spec_ok = spec_try > 0 && s.consumed == kact && !(s.flags & 2);
-            spec_quads = spec_try;
-            cw_prev = cw;
-            cw = (cw + 1) % NW;
-#ifdef RRTK_PHASE_CLOCKS
-            if (spec_ok) ++spec_hits;
-#endif
+#ifndef RRTK_FIXED_COMMIT
+            cw = (cw + 1 == NW) ? 0 : cw + 1;
 #endif
             j = s.j;
             it0 += s.consumed;
@@ -699,15 +628,13 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         opts[v] = o;
         if (v >= top) { cost[v] = CUDART_INF; parent[v] = -1; }
     }
-#ifdef RRTK_SPEC_SCAN
     if (lane == 0) {      // every warp has committed some rounds: add the counters up
         atomicAdd(&s_cnt[0], (unsigned long long)ell_iters); atomicAdd(&s_cnt[1], (unsigned long long)nn_pairs);
         atomicAdd(&s_cnt[2], (unsigned long long)ring_members); atomicAdd(&s_cnt[3], (unsigned long long)accepted);
     }
     __syncthreads();
     ell_iters = (long long)s_cnt[0]; nn_pairs = (long long)s_cnt[1]; ring_members = (long long)s_cnt[2]; accepted = (long long)s_cnt[3];
-#endif
-    if (tid == 0) {      // warp 0 carries the commit-phase counters
+    if (tid == 0) {
         if (found) { cost[j] = __longlong_as_double((long long)cstar_bits); parent[j] = vparent; }
         long long *st = P.stats + (size_t)plan * RRTK_STAT_COUNT;
         st[RRTK_STAT_J] = j;
@@ -728,7 +655,6 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         st[RRTK_STAT_ELL_ITERS] = clk_commit;
         st[RRTK_STAT_FIRST_SOL_ITER] = clk_ownwork;
         st[RRTK_STAT_RING_MEMBERS] = rounds;
-        st[RRTK_STAT_NN_PAIRS] = spec_hits;
 #endif
     }
 #undef WALK

@@ -103,9 +103,21 @@ class RRTDubins(RRT):
     def collisionfree(self, og, a, b) -> bool:  # noqa: D102 -- configurations instead of points
         return dubins_collisionfree(og, a, b, self.rho, self.nheadings, self.ds)
 
+    def _sampler_overridden(self) -> bool:
+        return type(self).sample_all_free is not RRTDubins.sample_all_free
+
     def _draw_configs(self, count: int) -> Tuple[np.ndarray, np.ndarray]:
-        """``count`` cells, then ``count`` headings, from the planner's generator."""
-        cells = self._draw_samples(count)
+        """``count`` cells, then ``count`` headings, from the planner's generator; a subclass's own
+        ``sample_all_free`` is called ``count`` times instead (one configuration per iteration)."""
+        if self._sampler_overridden():
+            rows = np.asarray([np.asarray(self.sample_all_free()) for _ in range(count)])
+            if rows.ndim != 2 or rows.shape[1] != 3:
+                raise TypeError("sample_all_free() must return a configuration (x, y, heading index)")
+            heads = rows[:, 2].astype(np.int64)
+            if heads.size and (heads.min() < 0 or heads.max() >= self.nheadings):
+                raise ValueError("sample_all_free() returned a heading index outside [0, nheadings)")
+            return self._as_samples(rows[:, :2]), heads
+        cells = RRT._draw_samples(self, count)
         heads = self.rand_gen.integers(0, self.nheadings, size=count)
         return cells, heads
 

@@ -42,6 +42,39 @@ def gather_records(local: Dict[str, np.ndarray], nplans: int, dst: int = 0, devi
     return out
 
 
+def gather_tensors(local: Dict[str, "torch.Tensor"], nplans: int, dst: int = 0, group=None):
+    """Device-resident form of gather_records: per-plan torch tensors (leading dimension = this rank's shard) are
+    gathered to ``dst`` with one ``torch.distributed.gather`` per field on the tensors' own device (NCCL over NVLink for
+    CUDA tensors, gloo for CPU tensors) -- no host staging.  Returns the concatenated tensors on ``dst``, None elsewhere.
+    Shards are padded to the common size ceil(nplans / world); the padding is dropped on ``dst``."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    per = (nplans + world - 1) // world
+    out = {} if rank == dst else None
+    for name in sorted(local):
+        a = local[name].contiguous()
+        tail, dtype = tuple(a.shape[1:]), a.dtype
+        m, rowbytes = a.shape[0], int(np.prod(tail, dtype=np.int64)) * a.element_size()
+        if m == per:
+            raw = a.reshape(m, -1).view(torch.uint8)                     # bytes: every backend moves uint8
+        else:                                                            # short (or empty) shard: pad to the common size
+            raw = torch.zeros((per, rowbytes), dtype=torch.uint8, device=a.device)
+            if m:
+                raw[:m] = a.reshape(m, -1).view(torch.uint8)
+        if rank == dst:
+            whole = torch.empty((world * per, raw.shape[1]), dtype=torch.uint8, device=raw.device)
+            bucket = list(whole.split(per, dim=0))
+        else:
+            whole, bucket = None, None
+        dist.gather(raw, bucket, dst=dst, group=group)
+        if rank == dst:
+            # shards are contiguous index ranges of `per` plans each (batch.shard), so only the tail is padding
+            out[name] = whole[:nplans].view(dtype).reshape((nplans,) + tail)
+    return out
+
+
 def run_sharded(nplans: int, run_shard: Callable[[range], Dict[str, np.ndarray]], dst: int = 0, device=None, group=None):
     """Run ``run_shard(plan_indices)`` on every rank and gather the records on ``dst``."""
     import torch.distributed as dist

@@ -21,6 +21,15 @@ section 0):
 * points must be integer arrays inside the grid (the reference's Numba kernel rejects float
   points with a TypingError and reads out of bounds for outside points); grids up to
   16384 x 16384, n <= 65534.
+* ``within`` answers over the filled rows only.  The reference's unfilled rows hold INT64_MIN, whose
+  squared distance wraps around in int64 to |x|^2, so whenever |x| < r it also returns every
+  unfilled row (rrt.py:174-181); their cost is inf, so no plan depends on them.
+* override points.  ``plan()`` is one fused kernel launch, so of the methods a subclass may replace
+  (rrt.py:131,157,183,231) it honours the samplers -- an overridden ``sample_all_free`` (and
+  ``unitball`` for RRTStarInformed) is called on the host exactly as often and in the same order as the
+  reference's loop calls it, and its results become the device's sample stream -- and it refuses the
+  three geometric primitives: a subclass that overrides ``near``, ``within`` or ``collisionfree`` gets a
+  ``NotImplementedError`` from ``plan()`` (same reason as ``costfn``), never the stock behaviour silently.
 """
 from __future__ import annotations
 
@@ -142,14 +151,26 @@ class RRT(object):
         out, ln = ctx.within(points, x, r)
         return out[0, : ln[0]].astype(np.int64)
 
+    # grid the shared context holds for the static collisionfree(): (occupancy as bool, copy)
+    _cf_cache = None
+
     @staticmethod
     def collisionfree(og, a, b) -> bool:
-        """True iff the integer line walk a -> b meets no non-zero cell (rrt.py:183-229)."""
+        """True iff the integer line walk a -> b meets no non-zero cell (rrt.py:183-229).
+
+        The reference's function is stateless; a caller looping it over one grid (as go2goal's callers
+        do) must not pay an upload and a packing kernel per segment, so the shared context keeps the
+        last grid.  The cache is validated by content (one host compare of the occupancy, ~15 us for
+        512 x 512), not by identity: in-place edits of ``og`` between calls are seen."""
         og = np.asarray(og)
         a = _as_point(a, og.shape, "a")
         b = _as_point(b, og.shape, "b")
         ctx = _lib.shared_context()
-        ctx.set_grids((og != 0).astype(np.uint8)[None])
+        occ = og != 0
+        cached = RRT._cf_cache
+        if cached is None or cached[0] is not ctx or cached[1].shape != occ.shape or not np.array_equal(cached[1], occ):
+            ctx.set_grids(occ.astype(np.uint8)[None])
+            RRT._cf_cache = (ctx, occ)
         return bool(ctx.collision(np.concatenate([a, b])[None])[0])
 
     def sample_all_free(self):
@@ -214,9 +235,36 @@ class RRT(object):
         return T
 
     # ---- shared plan() machinery ----------------------------------------------------------------------
+    def _check_hooks(self):
+        """The reference's override points (rrt.py:131,157,183): the fused plan kernel cannot call back
+        into Python, so a subclass that replaces one of the geometric primitives is refused."""
+        cls = type(self)
+        for name in ("near", "within", "collisionfree"):
+            if getattr(cls, name) is not getattr(RRT, name):
+                raise NotImplementedError(
+                    f"{cls.__name__} overrides RRT.{name}: a Python callable cannot run on the device and "
+                    "rrtplanner_b200 has no CPU fallback (plan() uses the stock primitive inside one kernel)")
+
+    def _sampler_overridden(self) -> bool:
+        return type(self).sample_all_free is not RRT.sample_all_free
+
+    def _as_samples(self, rows) -> np.ndarray:
+        a = np.asarray(rows)
+        shape = np.asarray(self.og).shape
+        if a.ndim != 2 or a.shape[1] != 2 or not np.issubdtype(a.dtype, np.integer) and not np.all(a == np.floor(a)):
+            raise TypeError("sample_all_free() must return integer grid points of shape (2,)")
+        a = a.astype(np.int64)
+        if a.size and (a.min() < 0 or a[:, 0].max() >= shape[0] or a[:, 1].max() >= shape[1]):
+            raise ValueError("sample_all_free() returned a point outside the grid")
+        return a
+
     def _draw_samples(self, count: int) -> np.ndarray:
-        """``count`` successive sample_all_free() results; numpy's bounded-integer stream for
-        size=count equals count scalar choice() calls and leaves the generator in the same state."""
+        """``count`` successive sample_all_free() results.  Stock sampler: numpy's bounded-integer stream
+        for size=count equals count scalar choice() calls and leaves the generator in the same state.
+        Overridden sampler (the reference's injection point, rrt.py:231): called ``count`` times, as the
+        reference's loop does (rrt.py:420,501)."""
+        if type(self).sample_all_free is not RRT.sample_all_free and self._sampler_overridden():
+            return self._as_samples([np.asarray(self.sample_all_free()) for _ in range(count)])
         idx = self.rand_gen.integers(0, self.free.shape[0], size=count)
         return self.free[idx]
 
@@ -267,6 +315,7 @@ class RRTStandard(RRT):
         super().__init__(og, n, costfn=costfn, pbar=pbar, seed=seed)
 
     def plan(self, xstart: np.ndarray, xgoal: np.ndarray) -> Tuple[nx.DiGraph, int]:
+        self._check_hooks()
         shape = np.asarray(self.og).shape
         xstart, xgoal = _as_point(xstart, shape, "xstart"), _as_point(xgoal, shape, "xgoal")
         ctx = self._device()
@@ -297,6 +346,7 @@ class RRTStar(RRT):
         self.rewire = rewire
 
     def plan(self, xstart: np.ndarray, xgoal: np.ndarray):
+        self._check_hooks()
         shape = np.asarray(self.og).shape
         xstart, xgoal = _as_point(xstart, shape, "xstart"), _as_point(xgoal, shape, "xgoal")
         ctx = self._device()
@@ -387,22 +437,45 @@ class RRTStarInformed(RRT):
         as: (1) a probe launch on a copy of the generator's free-space stream that stops at the
         first solution vertex; (2) the real generator is advanced by exactly the draws the
         reference would have consumed up to there, the ellipse-phase uniforms are drawn from it,
-        and the full plan is launched (the first phase replays identically)."""
+        and the full plan is launched (the first phase replays identically).
+
+        With an overridden ``sample_all_free`` the generator cannot be copied, so the free-space phase
+        is drawn call by call instead: a solution vertex can only appear at an iteration whose sample
+        lies within ``r_goal`` of the goal (rrt.py:744), so the sampler is called until such a sample
+        turns up, a probe launch on the stream so far says whether that iteration produced the first
+        solution, and drawing continues if it did not -- the sampler is called exactly as often as
+        the reference's loop would call it.  ``unitball`` is always called on the host, once per
+        ellipse-phase iteration, overridden or not."""
+        self._check_hooks()
         shape = np.asarray(self.og).shape
         xstart, xgoal = _as_point(xstart, shape, "xstart"), _as_point(xgoal, shape, "xgoal")
         ctx = self._device()
         n = self.n
-        nfree = self.free.shape[0]
-        probe_gen = copy.deepcopy(self.rand_gen)
-        samples = self.free[probe_gen.integers(0, nfree, size=n)].astype(np.int16)[None]
         desc = self._desc(xstart, xgoal)
-        _, _, _, st, _ = ctx.plan(self._KIND, desc, n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples)
-        first = int(st[0][5])
-        balls = np.zeros((1, n, 2))
-        if first < 0:
-            self.rand_gen.integers(0, nfree, size=n)             # whole plan sampled free space
+        if self._sampler_overridden():
+            samples = np.zeros((1, n, 2), dtype=np.int16)
+            first, drawn = -1, 0
+            while drawn < n and first < 0:
+                x = self._as_samples([np.asarray(self.sample_all_free())])[0]
+                samples[0, drawn] = x
+                drawn += 1
+                if r2norm(x - xgoal) < self.r_goal:
+                    # the probe sees iterations 0 .. drawn-1 only (later rows repeat the last sample: duplicates)
+                    samples[0, drawn:] = x
+                    _, _, _, st, _ = ctx.plan(self._KIND, desc, n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples)
+                    f = int(st[0][5])
+                    if 0 <= f < drawn:
+                        first = f
         else:
-            self.rand_gen.integers(0, nfree, size=first + 1)
+            nfree = self.free.shape[0]
+            probe_gen = copy.deepcopy(self.rand_gen)
+            samples = self.free[probe_gen.integers(0, nfree, size=n)].astype(np.int16)[None]
+            _, _, _, st, _ = ctx.plan(self._KIND, desc, n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples)
+            first = int(st[0][5])
+            # advance the real generator by exactly the free-space draws the reference consumes
+            self.rand_gen.integers(0, nfree, size=n if first < 0 else first + 1)
+        balls = np.zeros((1, n, 2))
+        if first >= 0:
             rot = self.rotation_to_world_frame(xstart, xgoal)    # LinAlgError if xstart == xgoal, as the reference
             desc = self._desc(xstart, xgoal, rot)
             for i in range(first + 1, n):

@@ -22,7 +22,6 @@ e0.record(); db.run(); e1.record(); torch.cuda.synchronize()
 st = db.out["stats"].cpu().numpy()
 S = {nm: st[:, i].astype(np.float64) for i, nm in enumerate(_lib.STAT_NAMES)}
 names = list(_lib.STAT_NAMES)
-scan, owner, commit, ownwork, rounds = (st[:, names.index(k)].astype(np.float64) for k in ("reserved0", "reserved1", "ellipse_iters", "first_solution_iter", "ring_members"))
-tot = scan + owner + commit
-print("rounds whose scan was mostly done during the previous commit (RRTK_SPEC_SCAN builds):", st[:, names.index("nn_pairs")].mean())
-print(f"P={P} T={T or 'default'} kernel {e0.elapsed_time(e1):.2f} ms; rounds/plan {rounds.mean():.0f}; cycles/round: scan {np.mean(scan/rounds):.0f} owner {np.mean(owner/rounds):.0f} (warp0 own work {np.mean(ownwork/rounds):.0f}) commit {np.mean(commit/rounds):.0f}; total/plan {tot.mean()/1e6:.2f} Mcycles")
+scan, owner, retire, ownwork, rounds = (st[:, names.index(k)].astype(np.float64) for k in ("reserved0", "reserved1", "ellipse_iters", "first_solution_iter", "ring_members"))
+tot = scan + owner
+print(f"P={P} T={T or 'default'} kernel {e0.elapsed_time(e1):.2f} ms; rounds/plan {rounds.mean():.0f}; cycles/round: scan {np.mean(scan/rounds):.0f} owner+retire {np.mean(owner/rounds):.0f} (warp 0: busy {np.mean(ownwork/rounds):.0f}, of which retiring {np.mean(retire/rounds):.0f}); total/plan {tot.mean()/1e6:.2f} Mcycles")

@@ -126,3 +126,51 @@ def test_go2goal_standalone():
     assert int(vgoal) == int(t.vgoal)
     if t.found:
         assert par[vgoal] == int(t.parents[t.vgoal]) and C2[vgoal] == t.vcosts[t.vgoal]
+
+
+def test_subclass_injection_reproduces_the_golden_trees(golden_plan):
+    """The reference's injection point (rrt.py:231; unitball :579 for the informed planner): drive the drop-in classes
+    exactly the way tests/golden/make_golden.py drives the reference -- a subclass whose sample_all_free / unitball read
+    pre-generated streams through one shared iteration counter -- and get the golden graph of every fixture."""
+    g = golden_plan
+    base = {"standard": R.RRTStandard, "star": R.RRTStar, "informed": R.RRTStarInformed}[g["kind"]]
+    state = {"i": 0, "free": 0, "ball": 0}
+    samples, balls = g["samples"], g["balls"]
+
+    class Driven(base):
+        def sample_all_free(self):
+            i = state["i"]; state["i"] += 1; state["free"] += 1
+            return samples[i].copy()
+
+        def unitball(self):
+            i = state["i"]; state["i"] += 1; state["ball"] += 1
+            return balls[i].copy()
+
+    if g["kind"] == "standard":
+        p = Driven(g["og"], g["n"], pbar=False)
+    elif g["kind"] == "star":
+        p = Driven(g["og"], g["n"], float(g["r_rewire"]), pbar=False)
+    else:
+        p = Driven(g["og"], g["n"], float(g["r_rewire"]), float(g["r_goal"]), pbar=False)
+    T, gv = p.plan(g["xstart"], g["xgoal"])
+    graph_matches(T, gv, {f"x_{k}": v for k, v in g.items()}, "x")
+    # the samplers were called as often as the reference's loop calls them: once per iteration, free space first
+    assert state["i"] == g["n"]
+    if g["kind"] == "informed":
+        first = p.last_stats["first_solution_iter"]
+        assert state["free"] == (g["n"] if first < 0 else first + 1) and state["ball"] == g["n"] - state["free"]
+        assert sorted(p.ellipses) == [int(k) for k in g["ell_keys"]]
+    else:
+        assert state["ball"] == 0
+
+
+def test_static_collisionfree_sees_in_place_edits():
+    """The static wrapper keeps the last grid on the device between calls, validated by content."""
+    og = np.zeros((40, 60), dtype=np.int64)
+    a, b = np.array([2, 3]), np.array([35, 50])
+    assert R.RRT.collisionfree(og, a, b) is True
+    assert R.RRT.collisionfree(og, a, b) is True          # served from the cached grid
+    og[20, :] = 7                                           # in-place edit, same array object
+    assert R.RRT.collisionfree(og, a, b) is False
+    og[20, :] = 0
+    assert R.RRT.collisionfree(og, a, b) is True

@@ -301,11 +301,44 @@ def test_plan_golden(ctx, golden_plan):
     assert (pts[0][top:] == -32768).all() and np.isinf(cost[0][top:]).all() and (parent[0][top:] == -1).all()
 
 
+def test_plan_golden_wide_kernel(ctx, golden_plan, monkeypatch):
+    """The 32-bit-distance kernel (csrc/plan_wide.cu: grids beyond the packed-key kernel's 2896 / 2048 / 1448 cells a side,
+    or tree shapes it does not take) on every golden fixture; RRTK_PLAN_IMPL is read at each launch."""
+    monkeypatch.setenv("RRTK_PLAN_IMPL", "wide")
+    test_plan_golden(ctx, golden_plan)
+
+
+@pytest.mark.parametrize("kind", ["standard", "star", "informed"])
+def test_wide_grid_takes_the_wide_kernel_by_default(kind):
+    """A 3008 x 3008 world is beyond the packed keys: the default dispatch must hand it to plan_wide.cu and still equal the
+    C oracle bit for bit (also with the environment override absent)."""
+    assert "RRTK_PLAN_IMPL" not in os.environ
+    W = H = 3008
+    n = 700
+    og = worlds.perlin_occupancygrid(W, H, seed=worlds.world_seed(5))
+    xs, xg = worlds.start_goal(og, 5)
+    if kind == "informed":                       # a goal the tree reaches early, so the ellipse phase runs
+        free = np.argwhere(og == 0)
+        near = free[np.argsort(((free - xs) ** 2).sum(1), kind="stable")]
+        xg = near[min(len(near) - 1, 4000)]
+    smp = O.sample_stream(og, n, 9)
+    rot = O.ellipse_rotation(xs, xg) if kind == "informed" else None
+    u = np.random.default_rng(3).uniform(0, 1, size=(n, 2))
+    balls = np.stack([np.sqrt(u[:, 0]) * np.cos(2 * np.pi * u[:, 1]), np.sqrt(u[:, 0]) * np.sin(2 * np.pi * u[:, 1])], axis=-1) if kind == "informed" else None
+    r, rg = (0.0, 0.0) if kind == "standard" else (400.0, 300.0 if kind == "informed" else 0.0)
+    db = batch.DeviceBatch(kind, W, H, n, r, rg)
+    db.set_worlds_host(og[None].astype(np.uint8))
+    db.set_plans(batch.make_desc([0], xs[None], xg[None], None if rot is None else rot[None]))
+    db.set_samples_host(smp[None])
+    if kind == "informed":
+        db.set_balls_host(balls[None])
+    res = db.run().download()
+    assert_same_as_oracle(res, 0, oracle_tree(kind, og.astype(np.uint8), n, xs, xg, smp, r, rg, balls, rot))
+
+
 @pytest.mark.parametrize("threads", [64, 128, 256])
 def test_plan_result_independent_of_block_size(golden_plan, threads):
     g = golden_plan
-    if g["n"] > 400:
-        pytest.skip("covered at default size")
     db = batch.DeviceBatch(g["kind"], g["og"].shape[0], g["og"].shape[1], g["n"], float(g["r_rewire"]), float(g["r_goal"]), threads=threads)
     db.set_worlds_host(g["og"][None])
     rot = O.ellipse_rotation(g["xstart"], g["xgoal"]) if g["kind"] == "informed" else None

@@ -32,3 +32,41 @@ def test_world_generator_properties():
     assert stack.shape == (3, 64, 64)
     a, b = worlds.start_goal(og, 3)
     assert og[a[0], a[1]] == 0 and og[b[0], b[1]] == 0 and not np.array_equal(a, b)
+
+
+def test_overridden_primitives_are_refused_not_ignored():
+    """rrt.py:131,157,183 are the reference's override points; plan() is one fused kernel, so a subclass that
+    replaces one of them must get an error (like costfn), never the stock behaviour.  Needs no GPU: the check runs first."""
+    import pytest
+    from rrtplanner_b200 import rrt
+
+    og = np.zeros((16, 16), dtype=np.uint8)
+    for name in ("near", "within", "collisionfree"):
+        for base, args in ((rrt.RRTStandard, (og, 10)), (rrt.RRTStar, (og, 10, 5.0)), (rrt.RRTStarInformed, (og, 10, 5.0, 2.0))):
+            Sub = type("Sub", (base,), {name: staticmethod(lambda *a, **k: None)})
+            with pytest.raises(NotImplementedError, match=name):
+                Sub(*args, pbar=False).plan(np.array([1, 1]), np.array([5, 5]))
+
+    class Mine(rrt.RRTStar):
+        def sample_all_free(self):
+            return np.array([3, 4])
+
+    assert Mine(og, 10, 5.0, pbar=False)._sampler_overridden() and not rrt.RRTStar(og, 10, 5.0, pbar=False)._sampler_overridden()
+    got = Mine(og, 4, 5.0, pbar=False)._draw_samples(4)
+    assert got.dtype == np.int64 and got.tolist() == [[3, 4]] * 4
+    from rrtplanner_b200 import dubins
+    assert not dubins.RRTDubins(og, 4, 2.0, pbar=False)._sampler_overridden()       # its own sampler is the stock one
+
+    class Bad(rrt.RRTStandard):
+        def sample_all_free(self):
+            return np.array([3, 99])
+
+    with pytest.raises(ValueError, match="outside"):
+        Bad(og, 4, pbar=False)._draw_samples(2)
+
+
+def test_plan_batch_informed_needs_streams():
+    import pytest
+    og = np.zeros((1, 32, 32), dtype=np.uint8)
+    with pytest.raises(ValueError, match="balls"):
+        batch.plan_batch("informed", og, 50, [[1, 1]], [[20, 20]], r_rewire=5.0, r_goal=2.0, seeds=[0])

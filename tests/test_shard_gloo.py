@@ -38,16 +38,21 @@ def _worker(rank, world, port, nplans, q):
                 "pts": np.stack([ids.astype(np.int16), (ids * 2).astype(np.int16)], axis=1)[:, None, :].repeat(3, axis=1)}
 
     got = multigpu.run_sharded(nplans, fake_run, dst=0)
+    # the device-resident form (bench.py's strong-scaling leg gathers path records with it over NCCL): here CPU tensors / gloo
+    mine = {k: torch.from_numpy(v) for k, v in fake_run(batch.shard(nplans, rank, world)).items()}
+    got_t = multigpu.gather_tensors(mine, nplans, dst=0)
     if rank == 0:
         want = fake_run(range(nplans))
-        q.put(all(np.array_equal(got[k], want[k]) and got[k].dtype == want[k].dtype for k in want))
+        ok = all(np.array_equal(got[k], want[k]) and got[k].dtype == want[k].dtype for k in want)
+        ok = ok and all(np.array_equal(got_t[k].numpy(), want[k]) and got_t[k].numpy().dtype == want[k].dtype for k in want)
+        q.put(ok)
     else:
-        assert got is None
+        assert got is None and got_t is None
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nplans", [9, 64])
+@pytest.mark.parametrize("nplans", [9, 64, 1])
 def test_gather_world_size_2_gloo(nplans):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
