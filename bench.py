@@ -39,7 +39,8 @@ W = H = 512
 N_ITER = 5000
 R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
-NCU_DRAM_BYTES_PER_PLAN = 104936448.0 / 1036          # profiles/r1_v6_plan_kernel_ncu.txt
+NCU_DRAM_BYTES_PER_PLAN = 104936448.0 / 1036          # re-captured whenever the plan kernel changes
+NCU_DRAM_SOURCE = "profiles/r1_v6_plan_kernel_ncu.txt: 104.94 MB for 1036 plans"
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
 
 
@@ -122,15 +123,34 @@ def _cpu_warm():
     O.plan_star(og, 20, 5.0, [1, 1], [20, 20], O.sample_stream(og, 20, 0))
 
 
-def cpu_baseline_single(nplans: int = 3):
+def cpu_baseline_single(nplans: int = 3, gpu_trees=None):
+    """Plans 0..nplans-1 of the workload through the oracle's port, one after the other on one core.  `gpu_trees`
+    (pts, cost, parent, stats of the timed GPU batch, host arrays) makes the headline self-certifying: the trees the CPU leg
+    computes anyway are compared with them bit for bit (`matches_oracle`)."""
+    from oracle import rrt_oracle as O
     _cpu_warm()
-    t0 = time.perf_counter()
-    recs = [_cpu_one(p) for p in range(nplans)]
-    dt = time.perf_counter() - t0
-    return {"value": nplans / dt, "unit": "plans/s", "cores": 1, "kind": "port",
-            "sample": f"plans 0..{nplans - 1} of the workload run sequentially with oracle/rrt_oracle.py:plan_star "
-                      f"(numpy + Numba port with the reference's per-iteration cost profile), {dt:.1f} s",
-            "checks_per_s": sum(r[2] for r in recs) / dt}
+    dt, checks, ok = 0.0, 0, True
+    for pid in range(nplans):
+        og, xs, xg = host_world_and_pair(pid)
+        smp = O.sample_stream(og, N_ITER, pid)
+        t0 = time.perf_counter()
+        tree = O.plan_star(og, N_ITER, R_REWIRE, xs, xg, smp)
+        dt += time.perf_counter() - t0
+        checks += tree.checks
+        if gpu_trees is not None:
+            pts, cost, parent, stats = gpu_trees
+            top = tree.j + (1 if tree.found else 0)
+            ok = ok and int(stats[pid, 0]) == tree.j and bool(stats[pid, 2]) == bool(tree.found) and \
+                np.array_equal(pts[pid, :tree.j].astype(np.int64), tree.points[:tree.j]) and \
+                np.array_equal(cost[pid, :tree.j].view(np.int64), tree.vcosts[:tree.j].view(np.int64)) and \
+                all(int(parent[pid, v]) == int(tree.parents[v]) for v in range(1, tree.j))
+            if tree.found:
+                ok = ok and cost[pid, tree.j].view(np.int64) == np.float64(tree.vcosts[tree.vgoal]).view(np.int64) and top == tree.j + 1
+    out = {"value": nplans / dt, "unit": "plans/s", "cores": 1, "kind": "port",
+           "sample": f"plans 0..{nplans - 1} of the workload run sequentially with oracle/rrt_oracle.py:plan_star "
+                     f"(numpy + Numba port with the reference's per-iteration cost profile), {dt:.1f} s",
+           "checks_per_s": checks / dt}
+    return out, (bool(ok) if gpu_trees is not None else None)
 
 
 def reference_arm(args):
@@ -211,20 +231,22 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
     alg = 4.0 * ncells                                          # 4 B per cell the reference would test
     achieved = alg / (ms / 1e3) / 1e9
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    l2_peak = 6300.0 * sm_mhz * 1e6 / 1e9                       # B300_MICROARCH.md: LTS cap ~6300 B/clk full chip
-    out = {
-        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
-        "segments_per_s": CC_NSEG / (ms / 1e3), "cells_per_s": ncells / (ms / 1e3), "ms_per_launch": ms,
-        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
-        "obstacle_fraction": float(db.og.float().mean().item()), "gpu_launches": reps,
-        "roofline": {"kernel": "rrtk::collision_global_kernel", "bound": "l2", "achieved": achieved, "peak": l2_peak, "unit": "GB/s",
-                     "frac": achieved / l2_peak, "traffic": 17309440.0,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch (profiles/r1_v6_cc_ncu.txt): "
-                                       "16 MB of segment records + the 512 KB grid, once",
-                     "algorithmic_bytes_per_launch": alg,
-                     "bytes_model": "4 B (one grid word) x cells the reference's walk tests (first hit inclusive)",
-                     "peak_source": "L2: ~6300 B/clk full chip (B300_MICROARCH.md LTS cap; no L2 figure in MEASURED_PEAKS.json) x %.0f MHz" % sm_mhz,
-                     "smem_view": {"peak": 128.0 * sms * sm_mhz * 1e6 / 1e9, "frac": achieved / (128.0 * sms * sm_mhz * 1e6 / 1e9)}},
+    l2_peak = float(peaks["l2_read_GBps"])                      # measured on this device in this run (rrtplanner_b200/peaks.py)
+    l2_src = ("measured in this run: rrtk_peak_l2_read, every thread streaming a 64 MB L2-resident buffer with 16-byte loads, best of 5 "
+              "(%.0f GB/s; the figure assumed in round 1 was 6300 B/clk x SM clock = %.0f GB/s)" % (l2_peak, 6300.0 * sm_mhz * 1e6 / 1e9))
+
+    def roof(kernel, ms_k, traffic, traffic_src):
+        return {"kernel": kernel, "bound": "l2", "achieved": alg / (ms_k / 1e3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                "frac": alg / (ms_k / 1e3) / 1e9 / l2_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg,
+                "bytes_model": "4 B (one grid word) x cells the reference's walk tests (first hit inclusive)", "peak_source": l2_src}
+
+    bit_grid = {
+        "kernel": "rrtk::collision_global_kernel (warp per segment on the tiled bit grid)", "segments_per_s": CC_NSEG / (ms / 1e3),
+        "cells_per_s": ncells / (ms / 1e3), "ms_per_launch": ms, "gpu_launches": reps,
+        "roofline": roof("rrtk::collision_global_kernel", ms, 17309440.0,
+                         "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
+                         "this launch (profiles/r1_v6_cc_ncu.txt): 16 MB of segment records + the 512 KB grid, once"),
     }
     # K1b: same outputs from the clearance field (built once per grid, outside the timed region like the packing)
     cap = 128
@@ -250,14 +272,20 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
     e1.record(stream)
     torch.cuda.synchronize(dev)
     ms_cf = e0.elapsed_time(e1) / reps
-    out["clearance_field_kernel"] = {
-        "kernel": "rrtk::collision_cf_kernel (thread per segment on a uint8 clearance field, cap %d)" % cap,
-        "segments_per_s": CC_NSEG / (ms_cf / 1e3), "cells_per_s": ncells / (ms_cf / 1e3), "ms_per_launch": ms_cf,
+    out = {
+        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
+        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
+        "obstacle_fraction": float(db.og.float().mean().item()),
+        # the faster of the two kernels carries the leg's headline numbers; both are listed with their own roofline object
+        "kernel": "rrtk::collision_cf_kernel (thread per segment on a uint8 clearance field, cap %d; rrtk_collision_segments_cf)" % cap,
+        "segments_per_s": CC_NSEG / (ms_cf / 1e3), "cells_per_s": ncells / (ms_cf / 1e3), "ms_per_launch": ms_cf, "gpu_launches": reps,
         "field_build_ms": eb0.elapsed_time(eb1), "field_bytes": CC_SIZE * CC_SIZE,
         "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free2) and torch.equal(cells, cells2)),
-        "algorithmic_GBps": alg / (ms_cf / 1e3) / 1e9, "frac_of_l2_peak": alg / (ms_cf / 1e3) / 1e9 / l2_peak,
-        "note": "skips cells the field proves free, so its algorithmic rate (4 B x cells the reference would read) is not bounded by "
-                "the L2 roofline of the cell-by-cell walk; gpu_launches of this leg: %d" % reps,
+        "roofline": roof("rrtk::collision_cf_kernel", ms_cf, None, "not captured for this kernel version"),
+        "note": "the clearance-field walk skips cells the field proves free, so it reads fewer bytes than the algorithmic 4 B x cells the "
+                "reference would test; what bounds it is the rate of scattered L1 reads (~1.08 cycles per lane-load per SM, "
+                "scripts/micro/scatter.cu), about 11 per segment",
+        "bit_grid_kernel": bit_grid,
     }
     if cpu:
         from oracle import c_oracle                            # checker + CPU baseline only
@@ -378,6 +406,104 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
 
 
 # ------------------------------------------------------------------------------------------------
+# shared set-up of a cfg3 batch: worlds made on the device, start/goal pairs from the device sampler
+# ------------------------------------------------------------------------------------------------
+def cfg3_batch(local: int, ids: np.ndarray, threads: int = 0):
+    """DeviceBatch with world / pair / descriptor of the plans `ids` resident in HBM.  World of plan p = seed 1000+p;
+    start/goal of plan p = first two distinct draws of free[default_rng(2000+p).integers(nfree)] (worlds.start_goal),
+    produced with the device sampler so no grid has to visit the host."""
+    import torch
+
+    from rrtplanner_b200 import batch, worlds
+    P = len(ids)
+    db = batch.DeviceBatch("star", W, H, N_ITER, R_REWIRE, device=local, threads=threads)
+    db.gen_worlds([worlds.world_seed(int(p)) for p in ids])
+    pair_db = batch.DeviceBatch("star", W, H, 8, device=local)
+    pair_db.bits, pair_db.rowcum = db.bits, db.rowcum
+    pair_db.set_plans(batch.make_desc(np.arange(P), np.zeros((P, 2)), np.zeros((P, 2))))
+    pair_db.seed_samples(2000 + ids)
+    draws = pair_db.samples.cpu().numpy().astype(np.int64)
+    starts = draws[:, 0]
+    differs = (draws[:, 1:] != starts[:, None]).any(axis=2)
+    goals = draws[np.arange(P), 1 + differs.argmax(axis=1)]
+    desc = batch.make_desc(np.arange(P), starts, goals)
+    db.set_plans(desc)
+    dev = torch.device("cuda", local)
+    states = torch.from_numpy(batch.seed_states(ids).view(np.int64)).to(dev)
+    db.samples = torch.empty((P, N_ITER, 2), dtype=torch.int16, device=dev)
+    return db, desc, states, starts, goals
+
+
+# ------------------------------------------------------------------------------------------------
+# strong scaling: BASELINE cfg3 as worded -- 4096 worlds in total, sharded over the ranks, paths gathered
+# ------------------------------------------------------------------------------------------------
+STRONG_PLANS, PATH_CAP = 4096, 256
+
+
+def strong_leg(local: int, rank: int, world: int, steps: int, warmup: int, barrier, total: int = STRONG_PLANS):
+    """Fixed total work: `total` plans, rank r runs batch.shard(total, r, world); every step ends with the final gather
+    the north star names -- the path record of every plan (vertex ids, points, length, cost: what route2gv /
+    vertices_as_ndarray give the reference's caller, rrt.py:87-129) and its statistics row -- to rank 0 with one
+    torch.distributed.gather per field on the device (NCCL over NVLink), inside the timed region.  Rank 0 then re-runs
+    all `total` plans alone (untimed) and checks that the gathered records are the ones a single GPU computes."""
+    import torch
+    import torch.distributed as dist
+
+    from rrtplanner_b200 import _lib, batch, multigpu
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+    ids = np.asarray(list(batch.shard(total, rank, world)), dtype=np.int64)
+    db, _, states, _, _ = cfg3_batch(local, ids)
+    L, P = db.L, len(ids)
+
+    def step():
+        _lib.check(L.rrtk_sample_streams(db.bits.data_ptr(), db.rowcum.data_ptr(), W, H, db.desc.data_ptr(), P, states.data_ptr(),
+                                         N_ITER, db.samples.data_ptr(), stream.cuda_stream), "sample_streams")
+        db.run()
+        rec = db.path_records(PATH_CAP)
+        return multigpu.gather_tensors(rec, total, dst=0) if world > 1 else rec
+
+    for _ in range(max(1, warmup)):
+        got = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        got = step()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    if rank != 0:
+        return None
+    rec_bytes = PATH_CAP * 4 + PATH_CAP * 4 + 4 + 8 + _lib.STAT_COUNT * 8
+    out = {"scaling": "strong", "plans_total": total, "plans_per_gpu": int(np.ceil(total / world)), "value": total / (ms / 1e3),
+           "unit": "plans/s", "ms_per_step": ms,
+           "gather": {"what": "path vertex ids + points (cap %d), path length, path cost, statistics row of every plan" % PATH_CAP,
+                      "bytes_per_plan": rec_bytes, "bytes_to_rank0_per_step": int(rec_bytes * (total - P)),
+                      "transport": "torch.distributed.gather on device tensors (NCCL)" if world > 1 else "none (one rank)",
+                      "inside_timed_region": True},
+           "long_paths": int((got["len"] > PATH_CAP).sum().item())}
+    if world > 1:
+        # the same `total` plans on this GPU alone: the gathered records must be bit-identical
+        full, _, fstates, _, _ = cfg3_batch(local, np.arange(total, dtype=np.int64))
+        _lib.check(L.rrtk_sample_streams(full.bits.data_ptr(), full.rowcum.data_ptr(), W, H, full.desc.data_ptr(), total, fstates.data_ptr(),
+                                         N_ITER, full.samples.data_ptr(), stream.cuda_stream), "sample_streams")
+        full.run()
+        want = full.path_records(PATH_CAP)
+        # rows longer than the cap are left unwritten by design: compare the defined part
+        ok = all(bool(torch.equal(got[k], want[k])) for k in ("len", "path_cost", "stats"))
+        short = want["len"] <= PATH_CAP
+        ok = ok and bool(torch.equal(got["path"][short], want["path"][short])) and bool(torch.equal(got["xy"][short], want["xy"][short]))
+        out["gathered_equals_single_gpu_run"] = ok
+    else:
+        out["gathered_equals_single_gpu_run"] = True     # one rank: the records are the single-GPU run
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def gpu_arm(args):
@@ -405,22 +531,7 @@ def gpu_arm(args):
     ids = plan_ids(rank, P)
 
     # ---- setup (untimed): worlds, pairs, descriptors resident in HBM -------------------------
-    db = batch.DeviceBatch("star", W, H, N_ITER, R_REWIRE, device=local, threads=args.threads)
-    db.gen_worlds([worlds.world_seed(int(p)) for p in ids])
-    # start/goal of plan p = first two distinct draws of free[default_rng(2000+p).integers(nfree)]
-    # (worlds.start_goal), produced with the device sampler so no grid has to visit the host
-    pair_db = batch.DeviceBatch("star", W, H, 8, device=local)
-    pair_db.bits, pair_db.rowcum = db.bits, db.rowcum
-    pair_db.set_plans(batch.make_desc(np.arange(P), np.zeros((P, 2)), np.zeros((P, 2))))
-    pair_db.seed_samples(2000 + ids)
-    draws = pair_db.samples.cpu().numpy().astype(np.int64)
-    starts = draws[:, 0]
-    differs = (draws[:, 1:] != starts[:, None]).any(axis=2)
-    goals = draws[np.arange(P), 1 + differs.argmax(axis=1)]
-    desc = batch.make_desc(np.arange(P), starts, goals)
-    db.set_plans(desc)
-    states = torch.from_numpy(batch.seed_states(ids).view(np.int64)).to(dev)
-    db.samples = torch.empty((P, N_ITER, 2), dtype=torch.int16, device=dev)
+    db, desc, states, starts, goals = cfg3_batch(local, ids, args.threads)
     L = db.L
     stream = torch.cuda.current_stream(dev)
 
@@ -477,48 +588,78 @@ def gpu_arm(args):
         all_stats = stats
 
     # ---- end-to-end through the host-buffer C ABI (what a Python caller of plan_batch gets) ----
+    # Headline form: the caller keeps its worlds packed (rrtk_pack_grid_host, once per set_og) and asks for what the reference's
+    # caller keeps of a plan -- the path (ids, points, cost) and the statistics; beside it the round-1 form (uint8 grids in,
+    # every tree out).  Both move everything through pinned host buffers inside the timed region.
     e2e = None
-    blocks_per_sm_e2e = db.footprint()[1]
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     if not args.no_e2e:
         Pe = min(P, args.e2e_plans)
         og_pinned = torch.empty((Pe, W, H), dtype=torch.uint8, pin_memory=True)
         og_pinned.copy_(db.og[:Pe])
+        bits_pinned = torch.empty((Pe, db.words), dtype=torch.int32, pin_memory=True)
+        bits_pinned.copy_(db.bits[:Pe])
         torch.cuda.synchronize(dev)
         og_host = og_pinned.numpy()
-        out = (torch.empty((Pe, N_ITER + 1, 2), dtype=torch.int16, pin_memory=True).numpy(),
-               torch.empty((Pe, N_ITER + 1), dtype=torch.float64, pin_memory=True).numpy(),
-               torch.empty((Pe, N_ITER + 1), dtype=torch.int32, pin_memory=True).numpy(),
-               torch.empty((Pe, _lib.STAT_COUNT), dtype=torch.int64, pin_memory=True).numpy(), None)
+        bits_host = bits_pinned.numpy().view(np.uint32)
+        packer_ok = bool(np.array_equal(_lib.pack_grids_host(og_host[:4]), bits_host[:4]))     # the host packer makes the same words
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()          # noqa: E731
+        out_paths = {"stats": pin((Pe, _lib.STAT_COUNT), torch.int64), "path": pin((Pe, PATH_CAP), torch.int32),
+                     "xy": pin((Pe, PATH_CAP, 2), torch.int16), "len": pin((Pe,), torch.int32), "path_cost": pin((Pe,), torch.float64)}
+        out_trees = {"stats": pin((Pe, _lib.STAT_COUNT), torch.int64), "pts": pin((Pe, N_ITER + 1, 2), torch.int16),
+                     "cost": pin((Pe, N_ITER + 1), torch.float64), "parent": pin((Pe, N_ITER + 1), torch.int32)}
         ctx = _lib.Context()
         desc_e = desc[:Pe]
 
-        def e2e_step():
+        def e2e_step(mode):
             st = batch.seed_states(ids[:Pe])                         # seeds -> PCG64 states (host)
-            # chunked pipeline: H2D grids, K0 + free index, sampler, K7, D2H of every tree
-            ctx.plan_worlds(_lib.KIND_STAR, og_host, desc_e, N_ITER, R_REWIRE, states=st, out=out, chunk=args.e2e_chunk)
+            # chunked pipeline: H2D grids, (K0) + free index, sampler, K7, (path extraction), D2H
+            if mode == "paths":
+                ctx.plan_worlds2(_lib.KIND_STAR, bits_host, W, H, desc_e, N_ITER, R_REWIRE, states=st, bits=True, trees=False, paths=True,
+                                 path_cap=PATH_CAP, out=out_paths, chunk=args.e2e_chunk)
+            else:
+                ctx.plan_worlds2(_lib.KIND_STAR, og_host, W, H, desc_e, N_ITER, R_REWIRE, states=st, bits=False, trees=True, paths=False,
+                                 out=out_trees, chunk=args.e2e_chunk)
 
-        for _ in range(max(1, args.warmup - 1)):
-            e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        same = np.array_equal(out[3][:, :3], stats[:Pe, :3]) and np.array_equal(out[1], db.out["cost"][:Pe].cpu().numpy())
-        e2e = {"value": Pe * world * args.steps / dt, "unit": "plans/s",
-               "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
-               "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8 + 4)),
-               "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt / args.steps,
-               "api": "rrtk_ctx_plan_worlds (seed mode, chunks of %d plans on 8 rotating streams) via rrtplanner_b200._lib.Context, "
-                      "pinned host buffers" % (args.e2e_chunk or 2 * sms),
-               "matches_device_arm": bool(same)}
+        def timed(mode):
+            for _ in range(max(1, args.warmup - 1)):
+                e2e_step(mode)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step(mode)
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+
+        dt_paths, dt_trees = timed("paths"), timed("trees")
+        rec = db.path_records(PATH_CAP)
+        torch.cuda.synchronize(dev)
+        short = out_paths["len"] <= PATH_CAP
+        same_paths = (np.array_equal(out_paths["stats"][:, :3], stats[:Pe, :3]) and np.array_equal(out_paths["len"], rec["len"][:Pe].cpu().numpy())
+                      and np.array_equal(out_paths["path_cost"].view(np.int64), rec["path_cost"][:Pe].cpu().numpy().view(np.int64))
+                      and np.array_equal(out_paths["xy"][short], rec["xy"][:Pe].cpu().numpy()[short]))
+        same_trees = np.array_equal(out_trees["stats"][:, :3], stats[:Pe, :3]) and np.array_equal(out_trees["cost"], db.out["cost"][:Pe].cpu().numpy())
+        rec_bytes = PATH_CAP * 8 + 4 + 8 + _lib.STAT_COUNT * 8
+        e2e = {"value": Pe * world * args.steps / dt_paths, "unit": "plans/s",
+               "h2d_bytes_per_step": int(Pe * (db.words * 4 + 64 + 32)),
+               "d2h_bytes_per_step": int(Pe * rec_bytes),
+               "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt_paths / args.steps,
+               "api": "rrtk_ctx_plan_worlds2(RRTK_IN_BITS | RRTK_OUT_PATHS) via rrtplanner_b200._lib.Context.plan_worlds2: tiled bit grids, plan "
+                      "descriptors and PCG64 states up; path record (ids + points, cap %d; length; cost) and statistics of every plan down; "
+                      "chunks of %d plans on 8 rotating streams, pinned host buffers" % (PATH_CAP, args.e2e_chunk or 2 * sms),
+               "matches_device_arm": bool(same_paths), "host_packer_matches_device_packer": packer_ok,
+               "trees_mode": {"value": Pe * world * args.steps / dt_trees, "unit": "plans/s", "ms_per_step": 1000 * dt_trees / args.steps,
+                              "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
+                              "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8)),
+                              "api": "rrtk_ctx_plan_worlds2(RRTK_OUT_TREES): uint8 grids up, every tree down (the round-1 call)",
+                              "matches_device_arm": bool(same_trees)}}
         ctx.close()
+
+    # ---- strong scaling: the same 4096 plans in total whatever N, with the final gather of the paths ----
+    strong = None if args.no_strong else strong_leg(local, rank, world, max(2, min(args.steps, 10)), args.warmup, barrier)
 
     if rank != 0:
         if world > 1:
@@ -538,17 +679,21 @@ def gpu_arm(args):
         pass
     sm_mhz = clocks.get("sm_mhz") or peaks.get("clocks_under_load", {}).get("sm_mhz_median") or 1965.0
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    smem_peak = 128.0 * sms * sm_mhz * 1e6 / 1e9                      # 128 B/clk/SM x SMs x measured SM clock
+    from rrtplanner_b200 import peaks as onchip
+    measured = onchip.measure(local)                                  # L2 -> SM and shared-memory read bandwidth of this device (csrc/peaks.cu)
+    smem_peak = measured["smem_read_GBps"]
+    smem_nominal = 128.0 * sms * sm_mhz * 1e6 / 1e9                   # 128 B/clk/SM x SMs x SM clock, for comparison
     hbm_bytes = P * (db.words * 4 + N_ITER * 4 + (N_ITER + 1) * 16 + 64 + _lib.STAT_COUNT * 8)
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     smem_b, blocks_per_sm = db.footprint()
     roofline = {
         "kernel": "rrtk::plan_scan_kernel<RRTK_STAR, K=%s samples per round, T=%s threads>" % (os.environ.get("RRTK_PLAN_K", "8"), args.threads or "128 (default)"), "bound": "smem", "achieved": achieved, "peak": smem_peak,
         "unit": "GB/s", "frac": achieved / smem_peak, "traffic": NCU_DRAM_BYTES_PER_PLAN * P,
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture (profiles/r1_v6_plan_kernel_ncu.txt: 104.94 MB for "
-                          "1036 plans), scaled to the plans of this launch; the tree, grid and sample stream of a plan cross HBM once",
-        "peak_source": f"128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz SM clock sampled during the timed region (SURVEY.md 8(d)); "
-                       "MEASURED_PEAKS.json has no shared-memory figure",
+        "traffic_source": "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                          "(" + NCU_DRAM_SOURCE + "), scaled to the plans of this launch; the tree, grid and sample stream of a plan cross HBM once",
+        "peak_source": "measured in this run: rrtk_peak_smem_read (one block per SM reading its shared memory with conflict-free 16-byte loads, "
+                       f"best of 5); nominal 128 B/clk/SM x {sms} SMs x {sm_mhz:.0f} MHz = {smem_nominal:.0f} GB/s",
+        "measured_peaks": measured,
         "algorithmic_bytes_per_launch": alg_bytes,
         "bytes_model": "8 B x (iteration, filled vertex) pairs + 8 B x radius-set members + 4 B x grid cells tested",
         "kernel_ms": ms_plan, "smem_bytes_actually_read_per_launch": 4.0 * nn_pairs + 4.0 * ring + 4.0 * cells,
@@ -574,10 +719,14 @@ def gpu_arm(args):
         "gpu_launches": 2 * args.steps,
         "e2e": e2e,
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
     if world == 1 and not args.no_cpu:
-        line["cpu_baseline"] = cpu_baseline_single(args.cpu_plans)
+        m = args.cpu_plans
+        gpu_trees = tuple(db.out[k][:m].cpu().numpy() for k in ("pts", "cost", "parent", "stats"))
+        line["cpu_baseline"], line["matches_oracle"] = cpu_baseline_single(m, gpu_trees)
     if world == 1 and not args.no_collision:
-        line["collision_microbench"] = collision_microbench(local, args.steps, args.warmup, not args.no_cpu, sm_mhz, peaks)
+        line["collision_microbench"] = collision_microbench(local, args.steps, args.warmup, not args.no_cpu, sm_mhz, measured)
     if world == 1 and not args.no_dubins:
         line["dubins_bench"] = dubins_bench(local, args.steps, not args.no_cpu)
     print(json.dumps(line), flush=True)
@@ -598,6 +747,7 @@ def main():
     ap.add_argument("--cpu-plans", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (4096 plans in total, paths gathered to rank 0)")
     ap.add_argument("--no-collision", action="store_true", help="skip the cfg2 collision microbenchmark")
     ap.add_argument("--collision-only", action="store_true", help="run only the cfg2 collision microbenchmark (profiling aid)")
     ap.add_argument("--no-dubins", action="store_true", help="skip the cfg5 Dubins RRT* leg")
@@ -609,7 +759,8 @@ def main():
     if args.collision_only:
         import torch
         torch.cuda.set_device(0)
-        print(json.dumps(collision_microbench(0, args.steps, args.warmup, not args.no_cpu, 1965.0, {})), flush=True)
+        from rrtplanner_b200 import peaks as onchip
+        print(json.dumps(collision_microbench(0, args.steps, args.warmup, not args.no_cpu, 1965.0, onchip.measure(0))), flush=True)
     elif args.dubins_only:
         import torch
         torch.cuda.set_device(0)

@@ -348,6 +348,30 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *ctx, int kind, const uint8_t *h_og, int nworl
                          int16_t *h_pts, double *h_cost, int32_t *h_parent, int64_t *h_stats, double *h_ell_c,
                          int chunk_plans);
 
+/* The same pipeline with the two ends a batch caller can choose (what `set_og` + `plan` + `route2gv` /
+ * `vertices_as_ndarray` amount to for many plans, rrt.py:261-272, 87-129):
+ *   RRTK_IN_BITS    h_grids holds tiled bit grids (rrtk_grid_words(W,H) uint32 per world, the layout at the top of
+ *                   this file; rrtk_pack_grid_host makes them) instead of uint8 cells: 1/8 of the upload
+ *   RRTK_OUT_TREES  download every tree (h_pts, h_cost, h_parent, and h_ell_c for informed plans)
+ *   RRTK_OUT_PATHS  download the path record of every plan as rrtk_extract_paths_xy writes it (path_cap entries per
+ *                   plan in h_path / h_xy, h_len, h_path_cost): ~2 KB per plan instead of 16 B per tree row
+ * h_stats always comes back.  Output pointers of a mode that is not requested may be NULL.  On an error after the first
+ * copy was enqueued the call drains every stream before it returns, so no transfer is still writing into the caller's
+ * buffers. */
+#define RRTK_IN_BITS 1
+#define RRTK_OUT_TREES 2
+#define RRTK_OUT_PATHS 4
+int rrtk_ctx_plan_worlds2(rrtk_ctx *ctx, int kind, const void *h_grids, int nworlds, int W, int H,
+                          const rrtk_plan_desc *h_plans, int nplans, int n, double r_rewire, double r_goal,
+                          const int16_t *h_samples, const uint64_t *h_state, const double *h_balls, int flags,
+                          int path_cap, int16_t *h_pts, double *h_cost, int32_t *h_parent, int64_t *h_stats,
+                          double *h_ell_c, int32_t *h_path, int16_t *h_xy, int32_t *h_len, double *h_path_cost,
+                          int chunk_plans);
+
+/* K0 on the host, for callers that keep their worlds packed (`og[x, y] != 0`, rrt.py:218, one bit per cell in the
+ * tiled layout; cells outside the grid are set).  Plain CPU loop, no device needed. */
+int rrtk_pack_grid_host(const uint8_t *h_og, int nworlds, int W, int H, uint32_t *h_bits);
+
 /* the sample stream a planner seeded with h_state would draw (seed mode of rrtk_ctx_plan, exposed
  * so RRT.sample_all_free can be served from the same generator) */
 int rrtk_ctx_samples(rrtk_ctx *ctx, const rrtk_plan_desc *h_plans, int nplans, int n, const uint64_t *h_state,

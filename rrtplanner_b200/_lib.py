@@ -85,6 +85,9 @@ SIGNATURES = {
     "rrtk_ctx_inflate": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
     "rrtk_ctx_plan": (_i, [_vp, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrtk_ctx_plan_worlds": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i]),
+    "rrtk_ctx_plan_worlds2": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp,
+                                   _vp, _vp, _vp, _vp, _i]),
+    "rrtk_pack_grid_host": (_i, [_vp, _i, _i, _i, _vp]),
     "rrtk_ctx_samples": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "rrtk_ctx_collision": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
     "rrtk_ctx_nearest": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),
@@ -125,6 +128,18 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def pack_grids_host(ogs) -> np.ndarray:
+    """(nworlds, W, H) occupancy (non-zero = obstacle, rrt.py:218) -> (nworlds, rrtk_grid_words(W, H)) uint32 tiled bit grids
+    on the host (rrtk_pack_grid_host): the form RRTK_IN_BITS callers keep their worlds in."""
+    og = np.ascontiguousarray((np.asarray(ogs) != 0).astype(np.uint8))
+    if og.ndim == 2:
+        og = og[None]
+    nw, W, H = og.shape
+    bits = np.empty((nw, int(lib().rrtk_grid_words(W, H))), dtype=np.uint32)
+    check(lib().rrtk_pack_grid_host(ptr(og), nw, W, H, ptr(bits)), "rrtk_pack_grid_host")
+    return bits
 
 
 def check(rc: int, what: str = ""):
@@ -238,6 +253,40 @@ class Context:
                                          ptr(samples), ptr(states), ptr(balls), ptr(pts), ptr(cost), ptr(parent), ptr(stats),
                                          ptr(ell), int(chunk)), "rrtk_ctx_plan_worlds")
         return pts, cost, parent, stats, ell
+
+    def plan_worlds2(self, kind, grids, W, H, desc, n, r_rewire=0.0, r_goal=0.0, samples=None, states=None, balls=None,
+                     bits=False, trees=False, paths=True, path_cap=256, out=None, chunk=0):
+        """rrtk_ctx_plan_worlds2: ``grids`` is (nworlds, W, H) uint8, or with ``bits=True`` the (nworlds, words) uint32 tiled
+        bit grids of pack_grids_host.  Returns a dict with ``stats`` and, as requested, the trees (``pts``, ``cost``,
+        ``parent``, ``ell``) and / or the path records (``path``, ``xy``, ``len``, ``path_cost``).  ``out``: optional dict of
+        preallocated (e.g. pinned) host arrays under the same names."""
+        grids = np.ascontiguousarray(grids, dtype=np.uint32 if bits else np.uint8)
+        nw = grids.shape[0]
+        nplans = desc.shape[0]
+        desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
+        out = dict(out or {})
+        def buf(name, shape, dtype):
+            if name not in out:
+                out[name] = np.empty(shape, dtype=dtype)
+            return out[name]
+        buf("stats", (nplans, STAT_COUNT), np.int64)
+        flags = (1 if bits else 0) | (2 if trees else 0) | (4 if paths else 0)
+        if trees:
+            buf("pts", (nplans, n + 1, 2), np.int16); buf("cost", (nplans, n + 1), np.float64); buf("parent", (nplans, n + 1), np.int32)
+            if kind == KIND_INFORMED:
+                buf("ell", (nplans, n + 1), np.float64)
+        if paths:
+            buf("path", (nplans, path_cap), np.int32); buf("xy", (nplans, path_cap, 2), np.int16)
+            buf("len", (nplans,), np.int32); buf("path_cost", (nplans,), np.float64)
+        samples = None if samples is None else np.ascontiguousarray(samples, dtype=np.int16)
+        states = None if states is None else np.ascontiguousarray(states, dtype=np.uint64)
+        balls = None if balls is None else np.ascontiguousarray(balls, dtype=np.float64)
+        g = out.get
+        check(lib().rrtk_ctx_plan_worlds2(self._h, kind, ptr(grids), nw, W, H, ptr(desc), nplans, n, float(r_rewire), float(r_goal),
+                                          ptr(samples), ptr(states), ptr(balls), flags, int(path_cap), ptr(g("pts")), ptr(g("cost")),
+                                          ptr(g("parent")), ptr(out["stats"]), ptr(g("ell")), ptr(g("path")), ptr(g("xy")), ptr(g("len")),
+                                          ptr(g("path_cost")), int(chunk)), "rrtk_ctx_plan_worlds2")
+        return out
 
     def samples(self, desc, n, states):
         nplans = desc.shape[0]

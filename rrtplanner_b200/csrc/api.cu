@@ -125,6 +125,7 @@ struct DevBuf {
 struct PipeSlot {
     cudaStream_t stream = nullptr;
     DevBuf og, bits, rowcum, plans, samples, state, balls, pts, cost, parent, stats, ell;
+    DevBuf path, xy, len, pcost;                // path records (RRTK_OUT_PATHS)
     std::vector<rrtk_plan_desc> desc;
 };
 constexpr int kPipeSlots = 8;
@@ -520,23 +521,30 @@ int rrtk_ctx_plan(rrtk_ctx *c, int kind, const rrtk_plan_desc *h_plans, int npla
 
 // Upload, plan and download in chunks of plans on rotating streams, so that host<->device copies of
 // one chunk overlap the kernels of its neighbours.  Plans must be ordered by world index.
-int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds, int W, int H, const rrtk_plan_desc *h_plans,
-                         int nplans, int n, double r_rewire, double r_goal, const int16_t *h_samples, const uint64_t *h_state,
-                         const double *h_balls, int16_t *h_pts, double *h_cost, int32_t *h_parent, int64_t *h_stats,
-                         double *h_ell_c, int chunk_plans)
+// flags: RRTK_IN_BITS (h_grids = tiled bit grids, 1/8 of the bytes), RRTK_OUT_TREES, RRTK_OUT_PATHS (path records of
+// path_cap entries per plan); statistics always come back.
+int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworlds, int W, int H, const rrtk_plan_desc *h_plans,
+                          int nplans, int n, double r_rewire, double r_goal, const int16_t *h_samples, const uint64_t *h_state,
+                          const double *h_balls, int flags, int path_cap, int16_t *h_pts, double *h_cost, int32_t *h_parent,
+                          int64_t *h_stats, double *h_ell_c, int32_t *h_path, int16_t *h_xy, int32_t *h_len, double *h_path_cost,
+                          int chunk_plans)
 {
-    RRTK_REQUIRE(c && h_og && h_plans && h_pts && h_cost && h_parent && h_stats, "rrtk_ctx_plan_worlds: null pointer");
-    RRTK_REQUIRE((h_samples != nullptr) != (h_state != nullptr), "rrtk_ctx_plan_worlds: pass exactly one of h_samples / h_state");
-    RRTK_REQUIRE(kind != RRTK_INFORMED || h_ell_c, "rrtk_ctx_plan_worlds: informed plans need h_ell_c");
-    RRTK_REQUIRE(nworlds >= 1 && nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan_worlds: need nworlds >= 1, nplans >= 0, 1 <= n <= 65534");
+    const bool in_bits = flags & RRTK_IN_BITS, out_trees = flags & RRTK_OUT_TREES, out_paths = flags & RRTK_OUT_PATHS;
+    RRTK_REQUIRE(c && h_grids && h_plans && h_stats, "rrtk_ctx_plan_worlds2: null pointer");
+    RRTK_REQUIRE(!out_trees || (h_pts && h_cost && h_parent), "rrtk_ctx_plan_worlds2: RRTK_OUT_TREES needs h_pts, h_cost, h_parent");
+    RRTK_REQUIRE(!out_paths || (h_path && h_xy && h_len && h_path_cost && path_cap >= 1),
+                 "rrtk_ctx_plan_worlds2: RRTK_OUT_PATHS needs h_path, h_xy, h_len, h_path_cost and path_cap >= 1");
+    RRTK_REQUIRE((h_samples != nullptr) != (h_state != nullptr), "rrtk_ctx_plan_worlds2: pass exactly one of h_samples / h_state");
+    RRTK_REQUIRE(kind != RRTK_INFORMED || !out_trees || h_ell_c, "rrtk_ctx_plan_worlds2: informed trees need h_ell_c");
+    RRTK_REQUIRE(nworlds >= 1 && nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan_worlds2: need nworlds >= 1, nplans >= 0, 1 <= n <= 65534");
     RRTK_TRY(check_grid_dims(W, H, 16384));
     if (nplans == 0) return RRTK_OK;
     bool ramp = false;
     if (chunk_plans <= 0) {
         // Chunks of two plan blocks per SM (a fraction of a wave): the next chunks' uploads, packing and sampler kernel
-        // (one sequential PCG64 thread per plan: ~2.6 ms however few plans) need free SM resources to overlap the running
-        // plan blocks, and a chunk that fills every SM leaves none until its first blocks retire.  Measured on B200, cfg3,
-        // 4096 plans (scripts/e2e_breakdown.py): 222..740 plans per chunk 61.6-64 ms, 1036 (one wave) 75 ms, unpipelined 82 ms.
+        // need free SM resources to overlap the running plan blocks, and a chunk that fills every SM leaves none until
+        // its first blocks retire.  Measured on B200, cfg3, 4096 plans (scripts/e2e_breakdown.py): 222..740 plans per
+        // chunk 61.6-64 ms, 1036 (one wave) 75 ms, unpipelined 82 ms.
         DevInfo *di;
         RRTK_TRY(dev_info(&di));
         int smem = 0, per_sm = 0;
@@ -570,7 +578,7 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
     DevInfo *di;
     RRTK_TRY(dev_info(&di));
     const size_t cells = (size_t)W * H, words = grid_words(W, H), rows1 = (size_t)n + 1;
-    int status = RRTK_OK;
+    const size_t grid_bytes = in_bits ? words * 4 : cells;
     // chunk list, then every slot sized once for the largest chunk (growing a buffer later would free it under the pipeline)
     std::vector<int> starts;
     {
@@ -588,65 +596,124 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
         max_m = m > max_m ? m : max_m;
         max_nw = nw > max_nw ? nw : max_nw;
     }
+    // Everything that can fail on the host side happens before the first copy is enqueued; from then on an error is
+    // recorded, the loop stops, and every stream is drained before returning, so that no copy is still writing into the
+    // caller's buffers when the call comes back.
+    int status = RRTK_OK;
+    auto cuda_ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && status == RRTK_OK) status = cuda_fail(e, what);
+        return e == cudaSuccess;
+    };
+    auto rrtk_ok = [&](int rc) {
+        if (rc != RRTK_OK && status == RRTK_OK) status = rc;
+        return rc == RRTK_OK;
+    };
     const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
-    for (size_t k = 0; k < nslots; ++k) {
+    for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
         PipeSlot &s = c->pipe[k];
-        if (!s.stream) RRTK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        const bool grow = s.og.cap < cells * max_nw || s.pts.cap < rows1 * max_m * 4 || s.samples.cap < max_m * n * 4 ||
-                          (kind == RRTK_INFORMED && (s.ell.cap < rows1 * max_m * 8 || (h_balls && s.balls.cap < max_m * n * 16)));
-        if (grow) RRTK_CUDA(cudaStreamSynchronize(s.stream));
-        RRTK_TRY(s.og.reserve(cells * max_nw));
-        RRTK_TRY(s.bits.reserve(words * 4 * max_nw));
-        RRTK_TRY(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw));
-        RRTK_TRY(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m));
-        RRTK_TRY(s.samples.reserve(max_m * n * 4));
-        RRTK_TRY(s.state.reserve(max_m * 32));
-        RRTK_TRY(s.pts.reserve(rows1 * max_m * 4));
-        RRTK_TRY(s.cost.reserve(rows1 * max_m * 8));
-        RRTK_TRY(s.parent.reserve(rows1 * max_m * 4));
-        RRTK_TRY(s.stats.reserve(max_m * RRTK_STAT_COUNT * 8));
-        if (kind == RRTK_INFORMED) {
-            RRTK_TRY(s.ell.reserve(rows1 * max_m * 8));
-            if (h_balls) RRTK_TRY(s.balls.reserve(max_m * n * 16));
-        }
+        if (!s.stream && !cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags")) break;
+        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");       // buffers may be regrown below
+        bool ok = rrtk_ok(s.bits.reserve(words * 4 * max_nw)) && rrtk_ok(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw)) &&
+                  rrtk_ok(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m)) && rrtk_ok(s.samples.reserve(max_m * n * 4)) &&
+                  rrtk_ok(s.state.reserve(max_m * 32)) && rrtk_ok(s.pts.reserve(rows1 * max_m * 4)) &&
+                  rrtk_ok(s.cost.reserve(rows1 * max_m * 8)) && rrtk_ok(s.parent.reserve(rows1 * max_m * 4)) &&
+                  rrtk_ok(s.stats.reserve(max_m * RRTK_STAT_COUNT * 8));
+        if (ok && !in_bits) ok = rrtk_ok(s.og.reserve(cells * max_nw));
+        if (ok && kind == RRTK_INFORMED) ok = rrtk_ok(s.ell.reserve(rows1 * max_m * 8)) && (!h_balls || rrtk_ok(s.balls.reserve(max_m * n * 16)));
+        if (ok && out_paths)
+            ok = rrtk_ok(s.path.reserve(max_m * path_cap * 4)) && rrtk_ok(s.xy.reserve(max_m * path_cap * 4)) &&
+                 rrtk_ok(s.len.reserve(max_m * 4)) && rrtk_ok(s.pcost.reserve(max_m * 8));
     }
     for (size_t ci = 0; ci + 1 < starts.size() && status == RRTK_OK; ++ci) {
         const int p0 = starts[ci], m = starts[ci + 1] - starts[ci];
         PipeSlot &s = c->pipe[ci % kPipeSlots];
         cudaStream_t st = s.stream;
         const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
-        RRTK_CUDA(cudaMemcpyAsync(s.og.p, h_og + cells * w0, cells * nw, cudaMemcpyHostToDevice, st));
-        RRTK_TRY(pack_launch(s.og.as<uint8_t>(), nw, W, H, s.bits.as<uint32_t>(), st));
-        RRTK_TRY(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st));
+        const uint8_t *src = static_cast<const uint8_t *>(h_grids) + grid_bytes * w0;
+        if (in_bits) {
+            if (!cuda_ok(cudaMemcpyAsync(s.bits.p, src, grid_bytes * nw, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(bits)")) break;
+        } else {
+            if (!cuda_ok(cudaMemcpyAsync(s.og.p, src, grid_bytes * nw, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(og)")) break;
+            if (!rrtk_ok(pack_launch(s.og.as<uint8_t>(), nw, W, H, s.bits.as<uint32_t>(), st))) break;
+        }
+        if (!rrtk_ok(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st))) break;
         s.desc.assign(h_plans + p0, h_plans + p0 + m);
         for (rrtk_plan_desc &d : s.desc) d.world -= w0;
-        RRTK_CUDA(cudaMemcpyAsync(s.plans.p, s.desc.data(), sizeof(rrtk_plan_desc) * m, cudaMemcpyHostToDevice, st));
+        if (!cuda_ok(cudaMemcpyAsync(s.plans.p, s.desc.data(), sizeof(rrtk_plan_desc) * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(plans)")) break;
         if (h_samples) {
-            RRTK_CUDA(cudaMemcpyAsync(s.samples.p, h_samples + (size_t)p0 * n * 2, (size_t)m * n * 4, cudaMemcpyHostToDevice, st));
+            if (!cuda_ok(cudaMemcpyAsync(s.samples.p, h_samples + (size_t)p0 * n * 2, (size_t)m * n * 4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(samples)")) break;
         } else {
-            RRTK_CUDA(cudaMemcpyAsync(s.state.p, h_state + (size_t)p0 * 4, (size_t)m * 32, cudaMemcpyHostToDevice, st));
-            RRTK_TRY(sample_streams_launch(s.bits.as<uint32_t>(), s.rowcum.as<int32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m,
-                                           s.state.as<uint64_t>(), n, s.samples.as<int16_t>(), di->optin, st));
+            if (!cuda_ok(cudaMemcpyAsync(s.state.p, h_state + (size_t)p0 * 4, (size_t)m * 32, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(state)")) break;
+            if (!rrtk_ok(sample_streams_launch(s.bits.as<uint32_t>(), s.rowcum.as<int32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m,
+                                               s.state.as<uint64_t>(), n, s.samples.as<int16_t>(), di->optin, st))) break;
         }
-        if (kind == RRTK_INFORMED && h_balls)
-            RRTK_CUDA(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st));
-        RRTK_TRY(rrtk_plan_batch(kind, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, r_rewire, r_goal,
-                                 s.samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? s.balls.as<double>() : nullptr,
-                                 s.pts.as<int16_t>(), s.cost.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(),
-                                 s.ell.as<double>(), 0, st));
-        RRTK_CUDA(cudaMemcpyAsync(h_pts + (size_t)p0 * rows1 * 2, s.pts.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st));
-        RRTK_CUDA(cudaMemcpyAsync(h_cost + (size_t)p0 * rows1, s.cost.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st));
-        RRTK_CUDA(cudaMemcpyAsync(h_parent + (size_t)p0 * rows1, s.parent.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st));
-        RRTK_CUDA(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st));
-        if (kind == RRTK_INFORMED)
-            RRTK_CUDA(cudaMemcpyAsync(h_ell_c + (size_t)p0 * rows1, s.ell.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st));
+        if (kind == RRTK_INFORMED && h_balls &&
+            !cuda_ok(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(balls)")) break;
+        if (!rrtk_ok(rrtk_plan_batch(kind, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, r_rewire, r_goal,
+                                     s.samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? s.balls.as<double>() : nullptr,
+                                     s.pts.as<int16_t>(), s.cost.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(),
+                                     s.ell.as<double>(), 0, st))) break;
+        bool ok = true;
+        if (out_paths) {
+            ok = rrtk_ok(paths_xy_launch(s.parent.as<int32_t>(), s.pts.as<int16_t>(), s.cost.as<double>(), s.stats.as<int64_t>(), m, n, path_cap,
+                                         s.path.as<int32_t>(), s.xy.as<int16_t>(), s.len.as<int32_t>(), s.pcost.as<double>(), st)) &&
+                 cuda_ok(cudaMemcpyAsync(h_path + (size_t)p0 * path_cap, s.path.p, (size_t)m * path_cap * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(path)") &&
+                 cuda_ok(cudaMemcpyAsync(h_xy + (size_t)p0 * path_cap * 2, s.xy.p, (size_t)m * path_cap * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(xy)") &&
+                 cuda_ok(cudaMemcpyAsync(h_len + p0, s.len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(len)") &&
+                 cuda_ok(cudaMemcpyAsync(h_path_cost + p0, s.pcost.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(path_cost)");
+        }
+        if (ok && out_trees) {
+            ok = cuda_ok(cudaMemcpyAsync(h_pts + (size_t)p0 * rows1 * 2, s.pts.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(pts)") &&
+                 cuda_ok(cudaMemcpyAsync(h_cost + (size_t)p0 * rows1, s.cost.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(cost)") &&
+                 cuda_ok(cudaMemcpyAsync(h_parent + (size_t)p0 * rows1, s.parent.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(parent)");
+            if (ok && kind == RRTK_INFORMED)
+                ok = cuda_ok(cudaMemcpyAsync(h_ell_c + (size_t)p0 * rows1, s.ell.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(ell)");
+        }
+        if (ok) cuda_ok(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(stats)");
     }
     for (PipeSlot &s : c->pipe)
-        if (s.stream) {
-            cudaError_t e = cudaStreamSynchronize(s.stream);
-            if (e != cudaSuccess && status == RRTK_OK) status = cuda_fail(e, "cudaStreamSynchronize");
-        }
+        if (s.stream) cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
     return status;
+}
+
+// the round-1 form: uint8 grids in, every tree out
+int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds, int W, int H, const rrtk_plan_desc *h_plans,
+                         int nplans, int n, double r_rewire, double r_goal, const int16_t *h_samples, const uint64_t *h_state,
+                         const double *h_balls, int16_t *h_pts, double *h_cost, int32_t *h_parent, int64_t *h_stats,
+                         double *h_ell_c, int chunk_plans)
+{
+    RRTK_REQUIRE(c && h_og && h_plans && h_pts && h_cost && h_parent && h_stats, "rrtk_ctx_plan_worlds: null pointer");
+    RRTK_REQUIRE(kind != RRTK_INFORMED || h_ell_c, "rrtk_ctx_plan_worlds: informed plans need h_ell_c");
+    return rrtk_ctx_plan_worlds2(c, kind, h_og, nworlds, W, H, h_plans, nplans, n, r_rewire, r_goal, h_samples, h_state, h_balls,
+                                 RRTK_OUT_TREES, 0, h_pts, h_cost, h_parent, h_stats, h_ell_c, nullptr, nullptr, nullptr, nullptr, chunk_plans);
+}
+
+// K0 on the host (include/rrtk.h: the tiled bit layout), for callers that keep their worlds packed
+int rrtk_pack_grid_host(const uint8_t *h_og, int nworlds, int W, int H, uint32_t *h_bits)
+{
+    RRTK_REQUIRE(h_og && h_bits && nworlds >= 0, "rrtk_pack_grid_host: null pointer or negative count");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    const int TX = tiles_x(W), TY = tiles_y(H);
+    const size_t words = grid_words(W, H), cells = (size_t)W * H;
+    for (int w = 0; w < nworlds; ++w) {
+        const uint8_t *og = h_og + cells * w;
+        uint32_t *bits = h_bits + words * w;
+        for (int tx = 0; tx < TX; ++tx)
+            for (int ty = 0; ty < TY; ++ty)
+                for (int xl = 0; xl < 32; ++xl) {
+                    const int x = tx * 32 + xl;
+                    uint32_t word = 0xffffffffu;                                 // cells outside the grid count as occupied
+                    if (x < W) {
+                        word = 0u;
+                        for (int b = 0; b < 32; ++b) {
+                            const int y = ty * 32 + b;
+                            if (y >= H || og[(size_t)x * H + y] != 0) word |= 1u << b;
+                        }
+                    }
+                    bits[(((size_t)tx * TY + ty) << 5) | xl] = word;
+                }
+    }
+    return RRTK_OK;
 }
 
 int rrtk_ctx_samples(rrtk_ctx *c, const rrtk_plan_desc *h_plans, int nplans, int n, const uint64_t *h_state, int16_t *h_samples)

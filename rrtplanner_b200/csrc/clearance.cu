@@ -16,6 +16,8 @@
 // taken from an fp32 reciprocal estimate with an exact +-1 integer fix-up (num < 2^31 for grids up to
 // 32768 cells a side), then one byte load.  A warp finishes with its slowest lane, so lanes whose
 // segment is done take the next one from the warp's block of segments while the others keep stepping.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rrtk {
@@ -131,29 +133,65 @@ __device__ __forceinline__ void cf_unpack(CfSeg &s, int4 p, int slot, int H)
     s.slot = slot;
 }
 
-constexpr int kCfPerWarp = 128;      // segments per warp: staged in shared memory, drawn by the lanes as they finish
-constexpr int kCfThreads = 256;
+// Scheduling.  A segment needs anything between one and ~60 dependent reads, and a warp finishes with its slowest lane.
+// Each warp owns a pool of kPool segments staged in shared memory; lanes draw the next one as they finish.  What keeps
+// the lanes busy to the end is the ORDER of the draw: a long segment started last leaves 31 lanes idle (17 of 32 threads
+// were active with the pool drawn in input order, profiles/r1_v7_cf_ncu.txt), so the pool is drawn longest first --
+// a bucket sort on max(|dx|, |dy|) made with ballots when the pool is staged -- and ends with segments of a few cells.
+// The pool size (32 .. 256 segments per warp, chosen by the launcher) trades the evenness of the draw against the number
+// of warps in flight: every lane has one dependent read outstanding, and an SM needs several hundred of them to keep
+// its L1 busy (a scattered byte read costs the SM ~1.08 cycles whatever the path: scripts/micro/scatter.cu).
+constexpr int kCfThreads = 128;
 
+__device__ __forceinline__ int cf_bucket(int major) { return major >= 512 ? 0 : major >= 128 ? 1 : major >= 32 ? 2 : 3; }
+
+template <int kCfPerWarp>
 __global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t *__restrict__ clear, size_t cells_per, int W, int H,
                                                                   const int4 *__restrict__ segs, const int *__restrict__ world,
                                                                   int64_t nseg, uint8_t *__restrict__ free_out, int *__restrict__ cells_out)
 {
     __shared__ int4 s_seg[kCfThreads / 32][kCfPerWarp];      // a finished segment's slot holds its result in .x
+    __shared__ uint8_t s_order[kCfThreads / 32][kCfPerWarp]; // slots in the order they are drawn
+    static_assert(kCfPerWarp % 32 == 0 && kCfPerWarp <= 256, "pool shape");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * kCfThreads + threadIdx.x) >> 5;
     const int64_t first = warp * kCfPerWarp;
     if (first >= nseg) return;
     const int cnt = (int)min((int64_t)kCfPerWarp, nseg - first);
     int4 *mine = s_seg[wib];
-    for (int i = lane; i < cnt; i += 32) mine[i] = cf_pack(__ldg(segs + first + i));   // coalesced: 512 bytes per step
+    uint8_t *order = s_order[wib];
+    {
+        int bucket[kCfPerWarp / 32];
+#pragma unroll
+        for (int c = 0; c < kCfPerWarp / 32; ++c) {
+            const int i = 32 * c + lane;
+            bucket[c] = 4;                                   // beyond the pool
+            if (i < cnt) {
+                const int4 p = cf_pack(__ldg(segs + first + i));   // coalesced: 512 bytes per step
+                mine[i] = p;
+                bucket[c] = cf_bucket(p.y);
+            }
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        int at = 0;
+        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+            for (int c = 0; c < kCfPerWarp / 32; ++c) {
+                const unsigned m = __ballot_sync(RRTK_FULL, bucket[c] == b);
+                if (bucket[c] == b) order[at + __popc(m & lt)] = (uint8_t)(32 * c + lane);
+                at += __popc(m);
+            }
+        }
+    }
     __syncwarp();
-    int next = 32;                                   // next undistributed slot (warp-uniform)
+    int next = 32;                                   // next position of the draw order (warp-uniform)
     CfSeg s;
     bool active = lane < cnt;
     const uint8_t *field = clear;
     if (active) {
-        cf_unpack(s, mine[lane], lane, H);
-        if (world) field = clear + (size_t)__ldg(world + first + lane) * cells_per;
+        const int slot = order[lane];
+        cf_unpack(s, mine[slot], slot, H);
+        if (world) field = clear + (size_t)__ldg(world + first + slot) * cells_per;
     }
     while (__any_sync(RRTK_FULL, active)) {
         bool done = false;
@@ -181,9 +219,10 @@ __global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t 
         const unsigned fin = __ballot_sync(RRTK_FULL, active && done);
         if (fin) {
             if (active && done) {
-                const int slot = next + __popc(fin & ((1u << lane) - 1u));
-                active = slot < cnt;
+                const int at = next + __popc(fin & ((1u << lane) - 1u));
+                active = at < cnt;
                 if (active) {
+                    const int slot = order[at];
                     cf_unpack(s, mine[slot], slot, H);
                     if (world) field = clear + (size_t)__ldg(world + first + slot) * cells_per;
                 }
@@ -199,15 +238,28 @@ __global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t 
     }
 }
 
+template <int kPool>
+static void cf_launch_pool(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int64_t nseg,
+                           uint8_t *d_free, int32_t *d_cells, cudaStream_t st)
+{
+    const int64_t warps = (nseg + kPool - 1) / kPool;
+    const int64_t blocks = (warps * 32 + kCfThreads - 1) / kCfThreads;
+    collision_cf_kernel<kPool><<<(unsigned)blocks, kCfThreads, 0, st>>>(d_clear, (size_t)W * H, W, H, reinterpret_cast<const int4 *>(d_segs),
+                                                                      d_world, nseg, d_free, d_cells);
+}
+
 int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int64_t nseg,
                         uint8_t *d_free, int32_t *d_cells, int sm_count, cudaStream_t st)
 {
     if (nseg == 0) return RRTK_OK;
-    const int64_t warps = (nseg + kCfPerWarp - 1) / kCfPerWarp;
-    int64_t blocks = (warps * 32 + kCfThreads - 1) / kCfThreads;
-    (void)sm_count;
-    collision_cf_kernel<<<(unsigned)blocks, kCfThreads, 0, st>>>(d_clear, (size_t)W * H, W, H, reinterpret_cast<const int4 *>(d_segs), d_world,
-                                                               nseg, d_free, d_cells);
+    // segments per warp: about 28 resident warps per SM on a full launch (see the scheduling note), RRTK_CF_POOL overrides
+    int64_t per = nseg / ((int64_t)sm_count * 28) + 1;
+    const char *env = getenv("RRTK_CF_POOL");
+    if (env && *env) per = atoi(env);
+    if (per > 128) cf_launch_pool<256>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
+    else if (per > 64) cf_launch_pool<128>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
+    else if (per > 32) cf_launch_pool<64>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
+    else cf_launch_pool<32>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
     RRTK_CUDA(cudaGetLastError());
     return RRTK_OK;
 }

@@ -251,6 +251,11 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         __syncthreads();                                                   // ---- barrier: scan results visible
         PHASE_T(t_1);
 
+        // the stream samples the next round can start with (it0 + consumed + k, consumed <= kact <= K): requested by the
+        // committing warp before its owner work, so that the load is long done when the commit phase stages them
+        short2 ahead = make_short2(0, 0);
+        if (warp == cw && lane < 2 * K) ahead = samples[min(it0 + lane, n - 1)];
+
         // ---- owner phase: warp (k mod NW) evaluates sample k against the round-start tree ---------
         // a sample costs anything between a duplicate test and several walks: warps take the next free one as they finish
         for (int k = warp; k < K;) {
@@ -435,9 +440,6 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         // ---- commit phase: warp 0 replays the results in sample order; lane m holds the m-th vertex
         //      accepted in this round ----------------------------------------------------------------
         if (warp == cw) {
-            // the stream samples the next round can start with (it0 + consumed + k, consumed <= kact <= K)
-            short2 ahead = make_short2(0, 0);
-            if (lane < 2 * K) ahead = samples[min(it0 + lane, n - 1)];
             uint32_t newp = 0;
             double newc = 0.0;
             int nnew = 0, consumed = 0, jc = j;
@@ -445,7 +447,81 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             int vs = vsol;
             double cs = csol;
             long long fs = first_sol;
-            for (int k = 0; k < kact; ++k) {
+            // Lane k replays sample k.  What a sample has to be checked against -- the vertices accepted earlier in the same round --
+            // is settled one earlier sample per step: at step kk sample kk is final (every sample before it has had its say),
+            // so its point, verdict and cost are broadcast and the later lanes test themselves against it: same cell -> the
+            // later sample is a duplicate; strictly nearer than its recorded nearest vertex -> the round ends before it; inside
+            // its radius -> one more radius-set member, and a candidate parent if it is cheaper than what the sample has (those
+            // few edges are walked one after the other, by the whole warp).  Candidates meet a sample in index order and replace
+            // its parent only when strictly cheaper, which is the reference's choose-parent order (rrt.py:510-521).  The in-order
+            // loop below (one sample at a time) remains for the rounds in which the tree may fill up, and under -DRRTK_SEQ_COMMIT.
+            bool fast = false;
+#ifndef RRTK_SEQ_COMMIT
+            if (j + kact <= n) {
+                const SampleRec r = s_rec[min(lane, K - 1)];
+                const bool in = lane < kact;
+                bool a = in && !(r.flags & 2) && (r.flags & 4);              // accepted unless the round interferes
+                double bc = r.bc;
+                int bv = r.bv;
+                const int x = px(r.pnew), y = py(r.pnew);
+                int extra = 0, stop = kact, nacc = 0;                        // samples [stop, kact) are left for the next round
+                for (int kk = 0; kk < stop; ++kk) {
+                    if (!__shfl_sync(RRTK_FULL, (int)a, kk)) continue;       // sample kk adds no vertex
+                    const double myc = (bv != 0x7fffffff) ? bc : r.c0;       // final for lane kk
+                    const double ck = __shfl_sync(RRTK_FULL, myc, kk);
+                    const uint32_t pk = __shfl_sync(RRTK_FULL, r.pnew, kk);
+                    if (KIND == RRTK_INFORMED) {
+                        const uint32_t dg = dist2(pk, gx, gy);
+                        if (__dsqrt_rn((double)dg) < P.r_goal) {               // rrt.py:744-745
+                            const bool changed = !hs || ck < cs;
+                            if (!hs) fs = it0 + kk;
+                            if (changed) { cs = ck; vs = j + nacc; }
+                            hs = true;
+                            if (changed) { stop = kk + 1; ++nacc; break; }     // later samples of the round used the old sampler state
+                        }
+                    }
+                    const uint32_t du = dist2(pk, x, y);
+                    const unsigned cutm = __ballot_sync(RRTK_FULL, in && lane > kk && lane < stop && du != 0 && du < r.bd);
+                    if (cutm) stop = min(stop, __ffs(cutm) - 1);             // it would be their nearest vertex: redo from there
+                    const bool later = in && lane > kk && lane < stop;
+                    if (later && du == 0) a = false;                          // now in `sampled` (rrt.py:426/508/708)
+                    const bool inr = KIND != RRTK_STANDARD && later && a && du < r2x;
+                    if (__any_sync(RRTK_FULL, inr)) {
+                        double cn = CUDART_INF;
+                        if (inr) { ++extra; cn = reach_cost(ck, du); }
+                        unsigned wm = __ballot_sync(RRTK_FULL, inr && cn < r.c0 && cn < bc);    // higher index: loses cost ties
+                        while (wm) {
+                            const int dst = __ffs(wm) - 1;
+                            wm &= wm - 1;
+                            const uint32_t pq = __shfl_sync(RRTK_FULL, r.pnew, dst);
+                            const int h = WALK(px(pk), py(pk), px(pq), py(pq));
+                            my_checks += 1; my_cells += cells_tested(h);
+                            if (h < 0 && lane == dst) { bc = cn; bv = j + nacc; }
+                        }
+                    }
+                    ++nacc;
+                }
+                const bool cons = lane < stop;
+                const bool acc = a && cons;
+                const unsigned accm = __ballot_sync(RRTK_FULL, acc);
+                const int myj = j + __popc(accm & ((1u << lane) - 1u));      // the tree size when this sample is reached
+                if (acc) {                                                    // rrt.py:524-529
+                    const bool hasbv = bv != 0x7fffffff;
+                    s_pts[tree_slot<T>(myj)] = r.pnew; cost[myj] = hasbv ? bc : r.c0; parent[myj] = hasbv ? bv : r.vnear;
+                }
+                if (KIND == RRTK_INFORMED && ellipse_mode) {
+                    if (cons) ell_c[myj] = r.ell;                            // rrt.py:701
+                    ell_iters += stop;
+                }
+                consumed = stop;
+                jc = j + __popc(accm);
+                nn_pairs += __reduce_add_sync(RRTK_FULL, cons ? myj : 0);
+                ring_members += __reduce_add_sync(RRTK_FULL, acc ? r.ring + extra : 0);
+                accepted += __popc(accm);
+                fast = true;
+            }
+#endif
+            for (int k = 0; k < kact && !fast; ++k) {
                 const SampleRec r = s_rec[k];
                 if (KIND != RRTK_INFORMED && jc == n) { finished = true; break; }
                 const int x = px(r.pnew), y = py(r.pnew);

@@ -22,6 +22,7 @@ e0.record(); db.run(); e1.record(); torch.cuda.synchronize()
 st = db.out["stats"].cpu().numpy()
 S = {nm: st[:, i].astype(np.float64) for i, nm in enumerate(_lib.STAT_NAMES)}
 names = list(_lib.STAT_NAMES)
-scan, owner, retire, ownwork, rounds = (st[:, names.index(k)].astype(np.float64) for k in ("reserved0", "reserved1", "ellipse_iters", "first_solution_iter", "ring_members"))
-tot = scan + owner
-print(f"P={P} T={T or 'default'} kernel {e0.elapsed_time(e1):.2f} ms; rounds/plan {rounds.mean():.0f}; cycles/round: scan {np.mean(scan/rounds):.0f} owner+retire {np.mean(owner/rounds):.0f} (warp 0: busy {np.mean(ownwork/rounds):.0f}, of which retiring {np.mean(retire/rounds):.0f}); total/plan {tot.mean()/1e6:.2f} Mcycles")
+scan, owner, commit, ownwork, rounds = (st[:, names.index(k)].astype(np.float64) for k in ("reserved0", "reserved1", "ellipse_iters", "first_solution_iter", "ring_members"))
+tot = scan + owner + commit
+print(f"P={P} T={T or 'default'} kernel {e0.elapsed_time(e1):.2f} ms; rounds/plan {rounds.mean():.0f}; cycles/round: scan {np.mean(scan/rounds):.0f} owner {np.mean(owner/rounds):.0f} (warp 0 busy {np.mean(ownwork/rounds):.0f}) commit {np.mean(commit/rounds):.0f}; total/plan {tot.mean()/1e6:.2f} Mcycles")
+print(f"   per-plan cycles: mean {tot.mean()/1e6:.2f}M  p50 {np.percentile(tot,50)/1e6:.2f}M  p90 {np.percentile(tot,90)/1e6:.2f}M  max {tot.max()/1e6:.2f}M; rounds p50 {np.percentile(rounds,50):.0f} max {rounds.max():.0f}; kernel = {e0.elapsed_time(e1)*1.965e3/1e3:.2f} Mcycles at 1965 MHz")

@@ -70,3 +70,20 @@ def test_plan_batch_informed_needs_streams():
     og = np.zeros((1, 32, 32), dtype=np.uint8)
     with pytest.raises(ValueError, match="balls"):
         batch.plan_batch("informed", og, 50, [[1, 1]], [[20, 20]], r_rewire=5.0, r_goal=2.0, seeds=[0])
+
+
+def test_host_packer_matches_the_documented_bit_layout():
+    """rrtk_pack_grid_host (K0 on the CPU, for callers that keep worlds packed) against the numpy statement of the tiled
+    layout documented in include/rrtk.h; the GPU packer is held to the same statement in tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(4)
+    for W, H in ((64, 64), (43, 100), (100, 43), (33, 31), (1, 1), (96, 160)):
+        og = (rng.random((2, W, H)) < 0.3) * rng.integers(1, 200, size=(2, W, H))
+        got = _lib.pack_grids_host(og)
+        TX, TY = (W + 31) // 32, (H + 31) // 32
+        assert got.shape == (2, TX * TY * 32) and got.dtype == np.uint32
+        for w in range(2):
+            pad = np.ones((TX * 32, TY * 32), dtype=np.uint64)
+            pad[:W, :H] = og[w] != 0
+            t = pad.reshape(TX, 32, TY, 32).transpose(0, 2, 1, 3)
+            want = (t << np.arange(32, dtype=np.uint64)).sum(axis=3).reshape(-1).astype(np.uint32)
+            assert np.array_equal(got[w], want)
