@@ -303,6 +303,144 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
 
 
 # ------------------------------------------------------------------------------------------------
+# cfg4: RRTStarInformed, 1024 start/goal pairs on one 1024x1024 world, n=20000 (BASELINE.json configs[3])
+# ------------------------------------------------------------------------------------------------
+INF_SIZE, INF_PLANS, INF_N, INF_RGOAL = 1024, 1024, 20000, 5.0
+
+
+def informed_bench(local: int, steps: int, cpu: bool, peaks: dict, plans: int = INF_PLANS):
+    """One 1024x1024 value-noise world (seed 1000), `plans` start/goal pairs (device sampler, seed 2000+p), n = 20000,
+    r_rewire = 50, r_goal = 5; free-space stream of plan p = default_rng(p); the unit-disc points of the ellipse phase are
+    pre-generated per plan (default_rng(7).uniform) and the rotations come from the reference's own numpy
+    construction (rrt.py:601-613).  Device arm with CUDA events, end to end through rrtk_ctx_plan_worlds2 (bit grid, states and
+    unit-disc streams up; path records down), two plans against the C oracle."""
+    import torch
+
+    from rrtplanner_b200 import _lib, batch, worlds
+    from rrtplanner_b200.rrt import RRTStarInformed
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream(dev)
+    S, n, P = INF_SIZE, INF_N, plans
+    db = batch.DeviceBatch("informed", S, S, n, R_REWIRE, INF_RGOAL, device=local).gen_worlds([worlds.world_seed(0)])
+    pair = batch.DeviceBatch("star", S, S, 8, device=local)
+    pair.bits, pair.rowcum = db.bits, db.rowcum
+    pair.set_plans(batch.make_desc(np.zeros(P, int), np.zeros((P, 2)), np.zeros((P, 2))))
+    pair.seed_samples(2000 + np.arange(P))
+    d = pair.samples.cpu().numpy().astype(np.int64)
+    starts = d[:, 0]
+    differs = (d[:, 1:] != starts[:, None]).any(axis=2)
+    goals = d[np.arange(P), 1 + differs.argmax(axis=1)]
+    og = db.og[0].cpu().numpy()
+    helper = RRTStarInformed(og, 8, R_REWIRE, INF_RGOAL, pbar=False)
+    rots = np.stack([np.asarray(helper.rotation_to_world_frame(a, b), dtype=np.float64) for a, b in zip(starts, goals)])
+    desc = batch.make_desc(np.zeros(P, int), starts, goals, rots)
+    db.set_plans(desc)
+    db.seed_samples(np.arange(P))
+    u = np.random.default_rng(7).uniform(0, 1, size=(P, n, 2))
+    balls = np.stack([np.sqrt(u[..., 0]) * np.cos(2 * np.pi * u[..., 1]), np.sqrt(u[..., 0]) * np.sin(2 * np.pi * u[..., 1])], axis=-1)
+    db.set_balls_host(balls)
+    for _ in range(2):
+        db.run()
+    torch.cuda.synchronize(dev)
+    reps = max(2, min(steps, 4))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        db.run()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    st = db.out["stats"].cpu().numpy()
+    Sx = {nm: st[:, i].astype(np.float64) for i, nm in enumerate(_lib.STAT_NAMES)}
+    alg = 8.0 * Sx["nn_pairs"].sum() + 8.0 * Sx["ring_members"].sum() + 4.0 * Sx["cells"].sum()
+    smem_b, blocks = db.footprint()
+    out = {"workload": "cfg4: RRTStarInformed, one %dx%d world, %d start/goal pairs, n=%d, r_rewire=%g, r_goal=%g" % (S, S, P, n, R_REWIRE, INF_RGOAL),
+           "plans_per_s": P / (ms / 1e3), "ms_per_launch": ms, "gpu_launches": reps, "goal_found_frac": float(st[:, 2].mean()),
+           "solution_found_frac": float((st[:, 5] >= 0).mean()),
+           "mean_first_solution_iter": float(st[st[:, 5] >= 0, 5].mean()) if (st[:, 5] >= 0).any() else None,
+           "ellipse_iter_frac": float(st[:, 6].mean() / n), "mean_vertices": float(st[:, 0].mean()),
+           "kernel": "rrtk::plan_scan_kernel<RRTK_INFORMED, K=8, T=256>", "blocks_per_sm": blocks, "smem_bytes_per_block": smem_b,
+           "roofline": {"bound": "smem", "achieved": alg / (ms / 1e3) / 1e9, "peak": peaks["smem_read_GBps"], "unit": "GB/s",
+                        "frac": alg / (ms / 1e3) / 1e9 / peaks["smem_read_GBps"], "traffic": None,
+                        "algorithmic_bytes_per_launch": alg, "peak_source": "measured in this run (rrtk_peak_smem_read)",
+                        "bytes_model": "8 B x (iteration, filled vertex) pairs + 8 B x radius-set members + 4 B x grid cells tested"}}
+    # end to end: one packed grid, descriptors, PCG64 states and the unit-disc streams up; path records + statistics down
+    ctx = _lib.Context()
+    bits_host = _lib.pack_grids_host(og[None])
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()          # noqa: E731
+    balls_pin, states = pin(balls), batch.seed_states(np.arange(P))
+    best = None
+    for rep in range(2):
+        t0 = time.perf_counter()
+        got = ctx.plan_worlds2(_lib.KIND_INFORMED, bits_host, S, S, desc, n, R_REWIRE, INF_RGOAL, states=states, balls=balls_pin, bits=True,
+                               trees=False, paths=True, path_cap=PATH_CAP)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    ctx.close()
+    keep = [i for i, nm in enumerate(_lib.STAT_NAMES) if nm not in ("checks", "cells")]
+    out["e2e"] = {"value": P / best, "unit": "plans/s", "h2d_bytes_per_step": int(bits_host.nbytes + P * (64 + 32 + n * 16)),
+                  "d2h_bytes_per_step": int(P * (PATH_CAP * 8 + 12 + _lib.STAT_COUNT * 8)),
+                  "api": "rrtk_ctx_plan_worlds2(RRTK_IN_BITS | RRTK_OUT_PATHS), seed mode + unit-disc streams from pinned host memory",
+                  "matches_device_arm": bool(np.array_equal(got["stats"][:, keep], st[:, keep]))}
+    if cpu:
+        from oracle import c_oracle                            # checker + CPU baseline only
+        res = db.download()
+        smp = db.samples.cpu().numpy()
+        ok, dt, m = True, 0.0, 2
+        for p in range(m):
+            t0 = time.perf_counter()
+            wp, wc, wpar, wst, _ = c_oracle.plan_raw("informed", og, n, starts[p], goals[p], smp[p], R_REWIRE, INF_RGOAL, balls[p], rots[p])
+            dt += time.perf_counter() - t0
+            top = wst["j"] + (1 if wst["found"] else 0)
+            ok = ok and int(res.stats[p, 0]) == wst["j"] and np.array_equal(res.pts[p, :top], wp[:top]) and \
+                np.array_equal(res.parent[p, :top], wpar[:top]) and np.array_equal(res.cost[p, :top].view(np.int64), wc[:top].view(np.int64))
+        out["matches_oracle"] = bool(ok)
+        out["cpu_baseline"] = {"value": m / dt, "unit": "plans/s", "cores": 1, "kind": "port",
+                               "sample": "plans 0..%d of the workload through oracle/rrt_oracle.c:orc_plan (compiled C restatement of rrt.py:690-748; "
+                                         "far faster than the Python reference), %.2f s" % (m - 1, dt)}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# cfg1: one RRTStar plan through the drop-in class (BASELINE.json configs[0], the reference's own CPU-runnable case)
+# ------------------------------------------------------------------------------------------------
+def class_api_bench(cpu: bool):
+    """RRTStar(og, n=1000, r_rewire=50, seed=0).plan() on a 256x256 world, timed around the public call including the
+    networkx graph it returns -- the latency a user of the reference's API sees (the reference: about 0.6 s)."""
+    from rrtplanner_b200 import rrt, worlds
+    og = worlds.perlin_occupancygrid(256, 256, seed=worlds.world_seed(0))
+    xs, xg = worlds.start_goal(og, 0)
+    pl = rrt.RRTStar(og, 1000, 50.0, pbar=False, seed=0)
+    pl.plan(xs, xg)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pl = rrt.RRTStar(og, 1000, 50.0, pbar=False, seed=0)
+        T, gv = pl.plan(xs, xg)
+    dt = (time.perf_counter() - t0) / reps
+    out = {"workload": "cfg1: RRTStar(og 256x256, n=1000, r_rewire=50, seed=0).plan(), class API incl. set-up of the grid on the device and "
+                       "the networkx graph", "s_per_plan": dt, "plans_per_s": 1 / dt, "nodes": T.number_of_nodes(), "gpu_launches": 3 * reps,
+           "e2e": {"value": 1 / dt, "unit": "plans/s", "h2d_bytes_per_step": int(256 * 256 + 64 + 1000 * 4),
+                   "d2h_bytes_per_step": int(1001 * 16 + 96), "api": "rrtplanner_b200.RRTStar(...).plan(xstart, xgoal)"}}
+    if cpu:
+        from oracle import rrt_oracle as O                     # checker + CPU baseline only
+        _cpu_warm()
+        smp = O.sample_stream(og, 1000, 0)
+        t0 = time.perf_counter()
+        tree = O.plan_star(og, 1000, 50.0, xs, xg, smp)
+        dtc = time.perf_counter() - t0
+        pts = np.stack([np.asarray(T.nodes[v]["pt"]) for v in range(tree.j)])
+        par = {int(b): int(a) for a, b in T.edges}
+        ok = int(gv) == int(tree.vgoal) and np.array_equal(pts, tree.points[: tree.j]) and \
+            all(par[v] == int(tree.parents[v]) for v in range(1, tree.j)) and \
+            all(T.edges[par[v], v]["cost"] == tree.vcosts[v] for v in range(1, tree.j))
+        out["matches_oracle"] = bool(ok)
+        out["cpu_baseline"] = {"value": 1 / dtc, "unit": "plans/s", "cores": 1, "kind": "port",
+                               "sample": "the same plan through oracle/rrt_oracle.py:plan_star (numpy + Numba port), %.2f s" % dtc}
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # cfg5: Dubins-vehicle RRT* (BASELINE.json configs[4]); no reference code exists for it -- parity UNPINNED
 # ------------------------------------------------------------------------------------------------
 DUB_PLANS, DUB_NH, DUB_RHO, DUB_DS = 1024, 16, 6.0, 1.0
@@ -727,6 +865,10 @@ def gpu_arm(args):
         line["cpu_baseline"], line["matches_oracle"] = cpu_baseline_single(m, gpu_trees)
     if world == 1 and not args.no_collision:
         line["collision_microbench"] = collision_microbench(local, args.steps, args.warmup, not args.no_cpu, sm_mhz, measured)
+    if world == 1 and not args.no_informed:
+        line["informed_bench"] = informed_bench(local, args.steps, not args.no_cpu, measured)
+    if world == 1 and not args.no_class_api:
+        line["class_api_bench"] = class_api_bench(not args.no_cpu)
     if world == 1 and not args.no_dubins:
         line["dubins_bench"] = dubins_bench(local, args.steps, not args.no_cpu)
     print(json.dumps(line), flush=True)
@@ -751,9 +893,14 @@ def main():
     ap.add_argument("--no-collision", action="store_true", help="skip the cfg2 collision microbenchmark")
     ap.add_argument("--collision-only", action="store_true", help="run only the cfg2 collision microbenchmark (profiling aid)")
     ap.add_argument("--no-dubins", action="store_true", help="skip the cfg5 Dubins RRT* leg")
+    ap.add_argument("--no-informed", action="store_true", help="skip the cfg4 RRTStarInformed leg")
+    ap.add_argument("--no-class-api", action="store_true", help="skip the cfg1 class-API latency leg")
     ap.add_argument("--dubins-only", action="store_true", help="run only the cfg5 Dubins RRT* leg (profiling aid)")
     ap.add_argument("--dubins-plans", type=int, default=DUB_PLANS)
+    ap.add_argument("--plan-only", action="store_true", help="device arm of the headline only (experiments): implies every --no-* flag")
     args = ap.parse_args()
+    if args.plan_only:
+        args.no_e2e = args.no_cpu = args.no_strong = args.no_collision = args.no_dubins = args.no_informed = args.no_class_api = True
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3
     if args.collision_only:

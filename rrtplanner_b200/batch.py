@@ -259,6 +259,11 @@ class DeviceBatch:
     def nfree(self) -> np.ndarray:
         return self.rowcum[:, self.W].cpu().numpy()
 
+    def _require_free_cells(self):
+        """Seed mode draws free[choice(nfree)] (rrt.py:240): a world without a free cell has nothing to draw (numpy raises)."""
+        if self.rowcum is not None and (self.nfree() <= 0).any():
+            raise ValueError("world %d has no free cell to sample" % int(np.flatnonzero(self.nfree() <= 0)[0]))
+
     # -- plans ---------------------------------------------------------------------------------
     def set_plans(self, desc: np.ndarray):
         t = self.torch
@@ -286,6 +291,7 @@ class DeviceBatch:
     def seed_samples(self, seeds: Sequence[int]):
         """Sample streams on the device from numpy-compatible PCG64 (rrt.py:85,231-240)."""
         t = self.torch
+        self._require_free_cells()
         st = t.from_numpy(seed_states(seeds).view(np.int64)).to(self.dev)
         self.samples = self._empty((self.nplans, self.n, 2), t.int16)
         with t.cuda.device(self.dev):

@@ -133,17 +133,20 @@ __device__ __forceinline__ void cf_unpack(CfSeg &s, int4 p, int slot, int H)
     s.slot = slot;
 }
 
-// Scheduling.  A segment needs anything between one and ~60 dependent reads, and a warp finishes with its slowest lane.
-// Each warp owns a pool of kPool segments staged in shared memory; lanes draw the next one as they finish.  What keeps
-// the lanes busy to the end is the ORDER of the draw: a long segment started last leaves 31 lanes idle (17 of 32 threads
-// were active with the pool drawn in input order, profiles/r1_v7_cf_ncu.txt), so the pool is drawn longest first --
-// a bucket sort on max(|dx|, |dy|) made with ballots when the pool is staged -- and ends with segments of a few cells.
-// The pool size (32 .. 256 segments per warp, chosen by the launcher) trades the evenness of the draw against the number
-// of warps in flight: every lane has one dependent read outstanding, and an SM needs several hundred of them to keep
-// its L1 busy (a scattered byte read costs the SM ~1.08 cycles whatever the path: scripts/micro/scatter.cu).
+// Scheduling.  A segment needs anything between one and ~60 dependent reads (how far it gets before it hits something is
+// close to exponential, whatever its length), and a warp finishes with its slowest lane.  Each warp owns a pool of kPool
+// segments staged in shared memory and every lane walks kCfIlp of them at once (1 by default), drawing the next one as one finishes: the
+// throughput of this kernel is the number of reads in flight per SM over their latency (one scattered byte read costs the
+// SM ~1.08 cycles whatever the path -- LDG, texture: scripts/micro/scatter.cu -- so an SM wants ~2000 of them in flight),
+// and with one segment per lane half of the lanes sit idle behind the longest walk of their warp (17 of 32 threads active,
+// profiles/r1_v7_cf_ncu.txt).  Tried and measured without effect on cfg2: drawing the pool longest first (length does not
+// predict the work), time-slicing the segments between the lanes (0.130 ms instead of 0.089: the swaps cost more than the
+// idle lanes); several segments per lane at once (-DRRTK_CF_ILP=2, 3, 4: 0.112, 0.152, 0.179 ms against 0.091 with one).
+#ifndef RRTK_CF_ILP
+#define RRTK_CF_ILP 1
+#endif
+constexpr int kCfIlp = RRTK_CF_ILP;
 constexpr int kCfThreads = 128;
-
-__device__ __forceinline__ int cf_bucket(int major) { return major >= 512 ? 0 : major >= 128 ? 1 : major >= 32 ? 2 : 3; }
 
 template <int kCfPerWarp>
 __global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t *__restrict__ clear, size_t cells_per, int W, int H,
@@ -151,83 +154,78 @@ __global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t 
                                                                   int64_t nseg, uint8_t *__restrict__ free_out, int *__restrict__ cells_out)
 {
     __shared__ int4 s_seg[kCfThreads / 32][kCfPerWarp];      // a finished segment's slot holds its result in .x
-    __shared__ uint8_t s_order[kCfThreads / 32][kCfPerWarp]; // slots in the order they are drawn
-    static_assert(kCfPerWarp % 32 == 0 && kCfPerWarp <= 256, "pool shape");
+    static_assert(kCfPerWarp % 32 == 0, "pool shape");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * kCfThreads + threadIdx.x) >> 5;
     const int64_t first = warp * kCfPerWarp;
     if (first >= nseg) return;
     const int cnt = (int)min((int64_t)kCfPerWarp, nseg - first);
     int4 *mine = s_seg[wib];
-    uint8_t *order = s_order[wib];
-    {
-        int bucket[kCfPerWarp / 32];
-#pragma unroll
-        for (int c = 0; c < kCfPerWarp / 32; ++c) {
-            const int i = 32 * c + lane;
-            bucket[c] = 4;                                   // beyond the pool
-            if (i < cnt) {
-                const int4 p = cf_pack(__ldg(segs + first + i));   // coalesced: 512 bytes per step
-                mine[i] = p;
-                bucket[c] = cf_bucket(p.y);
-            }
-        }
-        const unsigned lt = (1u << lane) - 1u;
-        int at = 0;
-        for (int b = 0; b < 4; ++b) {
-#pragma unroll
-            for (int c = 0; c < kCfPerWarp / 32; ++c) {
-                const unsigned m = __ballot_sync(RRTK_FULL, bucket[c] == b);
-                if (bucket[c] == b) order[at + __popc(m & lt)] = (uint8_t)(32 * c + lane);
-                at += __popc(m);
-            }
-        }
-    }
+    for (int i = lane; i < cnt; i += 32) mine[i] = cf_pack(__ldg(segs + first + i));   // coalesced: 512 bytes per step
     __syncwarp();
-    int next = 32;                                   // next position of the draw order (warp-uniform)
-    CfSeg s;
-    bool active = lane < cnt;
-    const uint8_t *field = clear;
-    if (active) {
-        const int slot = order[lane];
-        cf_unpack(s, mine[slot], slot, H);
-        if (world) field = clear + (size_t)__ldg(world + first + slot) * cells_per;
-    }
-    while (__any_sync(RRTK_FULL, active)) {
-        bool done = false;
-        if (active) {
-            // cell k of the walk: q(k) = floor((2 k minor + major) / (2 major))
-            int q = 0;
-            if (s.major > 0) {
-                const unsigned den = 2u * (unsigned)s.major;
-                const unsigned num = 2u * (unsigned)s.k * (unsigned)s.minor + (unsigned)s.major;      // < 2^31
-                q = __float2int_rz(__uint2float_rn(num) * s.inv);
-                int r = (int)(num - (unsigned)q * den);
-                if (r < 0) { --q; r += (int)den; }
-                if (r >= (int)den) ++q;
-            }
-            const int d = __ldg(field + (s.base + s.k * s.step_k + q * s.step_q));
-            int result = 0;
-            if (d == 0) { done = true; result = s.k; }                               // first occupied cell
-            else {
-                s.k += d;                                                            // cells k+1 .. k+d-1 are free
-                if (s.k > s.major) { done = true; result = -(s.major + 1); }
-            }
-            if (done) mine[s.slot].x = result;
+    int next = 32 * kCfIlp;                          // next undistributed slot (warp-uniform)
+    CfSeg s[kCfIlp];
+    bool active[kCfIlp];
+    const uint8_t *field[kCfIlp];
+    bool any = false;
+#pragma unroll
+    for (int u = 0; u < kCfIlp; ++u) {
+        const int slot = 32 * u + lane;
+        active[u] = slot < cnt;
+        field[u] = clear;
+        if (active[u]) {
+            cf_unpack(s[u], mine[slot], slot, H);
+            if (world) field[u] = clear + (size_t)__ldg(world + first + slot) * cells_per;
         }
-        // lanes that finished take the next slots of the block, in lane order
-        const unsigned fin = __ballot_sync(RRTK_FULL, active && done);
-        if (fin) {
-            if (active && done) {
-                const int at = next + __popc(fin & ((1u << lane) - 1u));
-                active = at < cnt;
-                if (active) {
-                    const int slot = order[at];
-                    cf_unpack(s, mine[slot], slot, H);
-                    if (world) field = clear + (size_t)__ldg(world + first + slot) * cells_per;
+        any |= active[u];
+    }
+    while (__any_sync(RRTK_FULL, any)) {
+        int d[kCfIlp];
+        // all reads of the turn are requested before the first one is consumed
+#pragma unroll
+        for (int u = 0; u < kCfIlp; ++u) {
+            d[u] = 1;
+            if (active[u]) {
+                // cell k of the walk: q(k) = floor((2 k minor + major) / (2 major))
+                int q = 0;
+                if (s[u].major > 0) {
+                    const unsigned den = 2u * (unsigned)s[u].major;
+                    const unsigned num = 2u * (unsigned)s[u].k * (unsigned)s[u].minor + (unsigned)s[u].major;      // < 2^31
+                    q = __float2int_rz(__uint2float_rn(num) * s[u].inv);
+                    int r = (int)(num - (unsigned)q * den);
+                    if (r < 0) { --q; r += (int)den; }
+                    if (r >= (int)den) ++q;
                 }
+                d[u] = __ldg(field[u] + (s[u].base + s[u].k * s[u].step_k + q * s[u].step_q));
             }
-            next += __popc(fin);
+        }
+        any = false;
+#pragma unroll
+        for (int u = 0; u < kCfIlp; ++u) {
+            bool done = false;
+            if (active[u]) {
+                int result = 0;
+                if (d[u] == 0) { done = true; result = s[u].k; }                     // first occupied cell
+                else {
+                    s[u].k += d[u];                                                  // cells k+1 .. k+d-1 are free
+                    if (s[u].k > s[u].major) { done = true; result = -(s[u].major + 1); }
+                }
+                if (done) mine[s[u].slot].x = result;
+            }
+            // lanes that finished take the next slots of the pool, in lane order
+            const unsigned fin = __ballot_sync(RRTK_FULL, active[u] && done);
+            if (fin) {
+                if (active[u] && done) {
+                    const int slot = next + __popc(fin & ((1u << lane) - 1u));
+                    active[u] = slot < cnt;
+                    if (active[u]) {
+                        cf_unpack(s[u], mine[slot], slot, H);
+                        if (world) field[u] = clear + (size_t)__ldg(world + first + slot) * cells_per;
+                    }
+                }
+                next += __popc(fin);
+            }
+            any |= active[u];
         }
     }
     __syncwarp();
@@ -252,8 +250,9 @@ int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_s
                         uint8_t *d_free, int32_t *d_cells, int sm_count, cudaStream_t st)
 {
     if (nseg == 0) return RRTK_OK;
-    // segments per warp: about 28 resident warps per SM on a full launch (see the scheduling note), RRTK_CF_POOL overrides
-    int64_t per = nseg / ((int64_t)sm_count * 28) + 1;
+    // segments per warp: enough for several draws per lane, few enough for the SMs to be full of warps on a big launch
+    // (cfg2, 1 Mi segments, one segment per lane: pools of 64 / 128 / 256 -> 0.094 / 0.089 / 0.114 ms); RRTK_CF_POOL overrides
+    int64_t per = nseg / ((int64_t)sm_count * 56) + 1;
     const char *env = getenv("RRTK_CF_POOL");
     if (env && *env) per = atoi(env);
     if (per > 128) cf_launch_pool<256>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);

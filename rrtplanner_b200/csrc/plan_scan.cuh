@@ -300,8 +300,11 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 if (KIND != RRTK_STANDARD) {
                     // membership words of this sample: nwords rows of T thread-private words
                     int mine = 0;
-                    for (int w = 0; w < nwords; ++w)
-                        for (int c = lane; c < T; c += 32) mine += __popc(s_hits[(w * K + k) * T + c]);
+                    for (int w = 0; w < nwords; ++w) {
+                        const uint32_t *hw = s_hits + (w * K + k) * T + lane;
+#pragma unroll
+                        for (int c = 0; c < T / 32; ++c) mine += __popc(hw[32 * c]);
+                    }
                     total = __reduce_add_sync(RRTK_FULL, mine);
                     if (total <= cap) {
                         // compaction: exclusive prefix of the per-lane counts, then every lane lists its members
@@ -311,17 +314,20 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                             const int t = __shfl_up_sync(RRTK_FULL, incl, o);
                             if (lane >= o) incl += t;
                         }
-                        int pos = incl - mine;
-                        for (int w = 0; w < nwords; ++w)
-                            for (int c = lane; c < T; c += 32) {
-                                uint32_t bits = s_hits[(w * K + k) * T + c];
-                                const int vbase = 32 * w * T + c;
+                        uint16_t *out = list + (incl - mine);
+                        for (int w = 0; w < nwords; ++w) {
+                            const uint32_t *hw = s_hits + (w * K + k) * T + lane;
+#pragma unroll
+                            for (int c = 0; c < T / 32; ++c) {
+                                uint32_t bits = hw[32 * c];
+                                const int vtop = (32 * w + 31) * T + 32 * c + lane;      // bit b of the word <-> row 32 w + 31 - b
                                 while (bits) {
-                                    const int p = __clz(bits);
-                                    bits &= ~(0x80000000u >> p);
-                                    list[pos++] = (uint16_t)(vbase + p * T);
+                                    const int b = 31 - __clz(bits);
+                                    bits ^= 1u << b;
+                                    *out++ = (uint16_t)(vtop - b * T);
                                 }
                             }
+                        }
                         __syncwarp();
                     }
                 }
@@ -465,27 +471,33 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 int bv = r.bv;
                 const int x = px(r.pnew), y = py(r.pnew);
                 int extra = 0, stop = kact, nacc = 0;                        // samples [stop, kact) are left for the next round
+                unsigned addm = __ballot_sync(RRTK_FULL, a);                 // who adds a vertex, as far as settled (bit kk is final at step kk)
                 for (int kk = 0; kk < stop; ++kk) {
-                    if (!__shfl_sync(RRTK_FULL, (int)a, kk)) continue;       // sample kk adds no vertex
+                    if (!((addm >> kk) & 1u)) continue;                      // sample kk adds no vertex
+                    const uint32_t pk = __shfl_sync(RRTK_FULL, r.pnew, kk);
+                    const uint32_t du = dist2(pk, x, y);
+                    const bool later = in && lane > kk && lane < stop;
+                    bool special = false;                                     // INFORMED: the vertex lies in the goal region
+                    if (KIND == RRTK_INFORMED) special = __dsqrt_rn((double)dist2(pk, gx, gy)) < P.r_goal;     // rrt.py:744-745
+                    // the common step: nobody later in the round is touched by this vertex (one ballot, nothing else to exchange)
+                    if (!special && !__any_sync(RRTK_FULL, later && (du < r.bd || (a && (du == 0 || du < r2x))))) { ++nacc; continue; }
                     const double myc = (bv != 0x7fffffff) ? bc : r.c0;       // final for lane kk
                     const double ck = __shfl_sync(RRTK_FULL, myc, kk);
-                    const uint32_t pk = __shfl_sync(RRTK_FULL, r.pnew, kk);
-                    if (KIND == RRTK_INFORMED) {
-                        const uint32_t dg = dist2(pk, gx, gy);
-                        if (__dsqrt_rn((double)dg) < P.r_goal) {               // rrt.py:744-745
-                            const bool changed = !hs || ck < cs;
-                            if (!hs) fs = it0 + kk;
-                            if (changed) { cs = ck; vs = j + nacc; }
-                            hs = true;
-                            if (changed) { stop = kk + 1; ++nacc; break; }     // later samples of the round used the old sampler state
-                        }
+                    if (special) {
+                        const bool changed = !hs || ck < cs;
+                        if (!hs) fs = it0 + kk;
+                        if (changed) { cs = ck; vs = j + nacc; }
+                        hs = true;
+                        if (changed) { stop = kk + 1; ++nacc; break; }         // later samples of the round used the old sampler state
                     }
-                    const uint32_t du = dist2(pk, x, y);
-                    const unsigned cutm = __ballot_sync(RRTK_FULL, in && lane > kk && lane < stop && du != 0 && du < r.bd);
+                    const unsigned cutm = __ballot_sync(RRTK_FULL, later && du != 0 && du < r.bd);
                     if (cutm) stop = min(stop, __ffs(cutm) - 1);             // it would be their nearest vertex: redo from there
-                    const bool later = in && lane > kk && lane < stop;
-                    if (later && du == 0) a = false;                          // now in `sampled` (rrt.py:426/508/708)
-                    const bool inr = KIND != RRTK_STANDARD && later && a && du < r2x;
+                    const bool still = later && lane < stop;
+                    if (still && du == 0 && a) {                              // now in `sampled` (rrt.py:426/508/708)
+                        a = false;
+                    }
+                    addm = __ballot_sync(RRTK_FULL, a);
+                    const bool inr = KIND != RRTK_STANDARD && still && a && du < r2x;
                     if (__any_sync(RRTK_FULL, inr)) {
                         double cn = CUDART_INF;
                         if (inr) { ++extra; cn = reach_cost(ck, du); }

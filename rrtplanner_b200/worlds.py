@@ -9,9 +9,9 @@ the function name and signature, the normalise/threshold rule and the 0 = free /
 convention.
 
 The generator below is value-noise fBm (3 octaves, lacunarity 2, gain 1/2, base frequency
-about 0.02 cells^-1, i.e. blobs 40-80 cells across; about 16 % obstacle cover at the default
-threshold) evaluated entirely in 32/64-bit *integer* fixed point, so that this numpy
-version and the CUDA kernel ``rrtk_gen_worlds`` (csrc/worlds.cu) produce bit-identical grids and
+about 0.02 cells^-1, i.e. blobs 40-80 cells across; about 17 % obstacle cover at the default
+threshold -- SURVEY.md 8(d) expected 0.2-0.3 from the reference's figures; the cover is reported in every bench line) evaluated entirely in 32/64-bit *integer* fixed point, so that this numpy
+version and the CUDA kernel ``rrtk_gen_worlds`` (csrc/grid.cu) produce bit-identical grids and
 the CPU baseline and the GPU arm of ``bench.py`` see exactly the same worlds without any
 cross-device copies.
 """
@@ -66,15 +66,43 @@ def _octave(xq, yq, seed):
     return (a * (ONE - sy) + b * sy) >> FRAC_BITS
 
 
-def fbm_field(w: int, h: int, seed: int = 0, frame: int = 0) -> np.ndarray:
-    """(w, h) int64 field; ``frame`` shifts the lattice seed so successive frames differ."""
+def fbm_field(w: int, h: int, seed: int = 0) -> np.ndarray:
+    """(w, h) int64 field of one world (bit-identical to the CUDA generator rrtk_gen_worlds, csrc/grid.cu)."""
     x = np.arange(w, dtype=np.int64)[:, None] * BASE_FREQ_Q16
     y = np.arange(h, dtype=np.int64)[None, :] * BASE_FREQ_Q16
     x, y = np.broadcast_arrays(x, y)
     total = np.zeros((w, h), dtype=np.int64)
     for o in range(OCTAVES):
-        total += _octave(x << o, y << o, seed * 31 + o * 7919 + frame * 104729) << (OCTAVES - 1 - o)
+        total += _octave(x << o, y << o, seed * 31 + o * 7919) << (OCTAVES - 1 - o)
     return total
+
+
+_M6 = np.uint32(0x27D4EB2F)
+
+
+def _octave3(zq, xq, yq, seed):
+    """Trilinear value noise: the frame index is a third, continuous lattice coordinate, so that consecutive frames are
+    neighbouring slices of one smooth 3-D field, as in the reference's genAsGrid([frames, w, h]) (oggen.py:33-38)."""
+    iz, fz = zq >> FRAC_BITS, zq & (ONE - 1)
+    sz = _smooth(np.int64(fz))
+    with np.errstate(over="ignore"):
+        s0 = int((np.uint32(seed & 0xFFFFFFFF) + np.uint32(iz & 0xFFFFFFFF) * _M6) & np.uint32(0xFFFFFFFF))
+        s1 = int((np.uint32(seed & 0xFFFFFFFF) + np.uint32((iz + 1) & 0xFFFFFFFF) * _M6) & np.uint32(0xFFFFFFFF))
+    return (_octave(xq, yq, s0) * (ONE - int(sz)) + _octave(xq, yq, s1) * int(sz)) >> FRAC_BITS
+
+
+def fbm_field_3d(frames: int, w: int, h: int, seed: int = 0) -> np.ndarray:
+    """(frames, w, h) int64 field: one frame = one step of BASE_FREQ along the third axis (the reference uses the same
+    frequency on all three axes), so obstacles drift and deform from frame to frame instead of being redrawn."""
+    x = np.arange(w, dtype=np.int64)[:, None] * BASE_FREQ_Q16
+    y = np.arange(h, dtype=np.int64)[None, :] * BASE_FREQ_Q16
+    x, y = np.broadcast_arrays(x, y)
+    out = np.zeros((frames, w, h), dtype=np.int64)
+    for f in range(frames):
+        z = f * BASE_FREQ_Q16
+        for o in range(OCTAVES):
+            out[f] += _octave3(z << o, x << o, y << o, seed * 31 + o * 7919) << (OCTAVES - 1 - o)
+    return out
 
 
 def threshold_field(field: np.ndarray, thresh: float = 0.33) -> np.ndarray:
@@ -89,12 +117,12 @@ def perlin_occupancygrid(w: int, h: int, thresh: float = 0.33, frames: int = Non
     """Drop-in for ``oggen.perlin_occupancygrid`` (oggen.py:7-45) plus a ``seed``.
 
     Returns an int array, 1 = obstacle, 0 = free, shape (w, h) or (frames, w, h).  With
-    ``frames`` the normalisation runs over the whole stack, as in the reference
-    (oggen.py:36,41-42)."""
+    ``frames`` the stack is a run of neighbouring slices of one 3-D noise field (a smoothly
+    changing environment, which the replanning loop of anim.py:56-115 relies on) and the
+    normalisation runs over the whole stack, as in the reference (oggen.py:36,41-42)."""
     if frames is None:
         return threshold_field(fbm_field(w, h, seed), thresh)
-    stack = np.stack([fbm_field(w, h, seed, f) for f in range(frames)])
-    return threshold_field(stack, thresh)
+    return threshold_field(fbm_field_3d(frames, w, h, seed), thresh)
 
 
 def world_seed(world_id: int) -> int:

@@ -6,6 +6,6 @@ for v in base main oo; do
   L=$PWD/exp_$v.so; [ "$v" = main ] && L=$PWD/rrtplanner_b200/librrtk.so
   RRTK_LIB=$L timeout 600 ncu --metrics smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.max,smsp__warps_active.avg.per_cycle_active \
      --clock-control none -k regex:plan_scan -s 3 -c 1 --csv --log-file gpurun_out/r2_inst_$v.csv \
-     python bench.py --steps 1 --warmup 3 --plans 1036 --no-e2e --no-cpu --no-collision --no-dubins > /dev/null 2>&1
+     python bench.py --steps 1 --warmup 3 --plans 1036 --plan-only > /dev/null 2>&1
   echo "== $v"; grep -v "^==" gpurun_out/r2_inst_$v.csv | cut -d, -f5,13- | tail -5
 done

@@ -490,6 +490,77 @@ def test_pipelined_host_call_equals_device_batch():
         c.plan_worlds(1, ogs, batch.make_desc([1, 0], starts[:2], goals[:2]), n, 30.0, states=batch.seed_states(seeds[:2]))
 
 
+def test_packed_grids_in_path_records_out():
+    """rrtk_ctx_plan_worlds2: tiled bit grids from the host packer in (RRTK_IN_BITS), path records out (RRTK_OUT_PATHS) ==
+    the trees the tree mode returns, walked on the host the way RRT.route2gv / vertices_as_ndarray do (rrt.py:87-129)."""
+    W, H, n, nworlds = 100, 70, 500, 6                       # H not a multiple of 32: padded tiles
+    ogs = np.stack([worlds.perlin_occupancygrid(W, H, seed=60 + w) for w in range(nworlds)]).astype(np.uint8)
+    wid = np.repeat(np.arange(nworlds), 3)
+    nplans = wid.size
+    pairs = [worlds.start_goal(ogs[wid[p]], 7 * p) for p in range(nplans)]
+    desc = batch.make_desc(wid, [a for a, _ in pairs], [b for _, b in pairs])
+    st = batch.seed_states(np.arange(500, 500 + nplans))
+    c = _lib.Context()
+    cap = 64
+    trees = c.plan_worlds2(1, ogs, W, H, desc, n, 25.0, states=st, bits=False, trees=True, paths=False, chunk=5)
+    bits = _lib.pack_grids_host(ogs)
+    assert np.array_equal(bits, np.stack([tiled_bits(g) for g in ogs]))
+    both = c.plan_worlds2(1, bits, W, H, desc, n, 25.0, states=st, bits=True, trees=True, paths=True, path_cap=cap, chunk=4)
+    only = c.plan_worlds2(1, bits, W, H, desc, n, 25.0, states=st, bits=True, trees=False, paths=True, path_cap=cap)
+    c.close()
+    keep = [i for i, nm in enumerate(_lib.STAT_NAMES) if nm not in ("checks", "cells")]
+    for k in ("pts", "parent"):
+        assert np.array_equal(trees[k], both[k])
+    assert np.array_equal(trees["cost"].view(np.int64), both["cost"].view(np.int64))
+    assert np.array_equal(trees["stats"][:, keep], both["stats"][:, keep]) and np.array_equal(only["stats"][:, keep], both["stats"][:, keep])
+    assert "pts" not in only
+    res = batch.BatchResult(trees["pts"], trees["cost"], trees["parent"], trees["stats"])
+    some_found = False
+    for p in range(nplans):
+        want = res.path(p)                                   # parent walk on the host
+        some_found |= bool(trees["stats"][p, 2])
+        for got in (both, only):
+            assert int(got["len"][p]) == len(want)
+            assert got["path_cost"][p].view(np.int64) == np.float64(res.path_cost(p)).view(np.int64)
+            if len(want) <= cap:
+                assert got["path"][p, : len(want)].tolist() == want and (got["path"][p, len(want):] == -1).all()
+                assert np.array_equal(got["xy"][p, : len(want)], trees["pts"][p][want])
+                assert (got["xy"][p, len(want):] == -32768).all()
+    assert some_found
+    with pytest.raises(ValueError):                          # a requested mode without its buffers is refused by the C entry point
+        L = _lib.lib()
+        _lib.check(L.rrtk_ctx_plan_worlds2(_lib.Context()._h, 1, _lib.ptr(bits), nworlds, W, H, _lib.ptr(desc), nplans, n, 25.0, 0.0, None,
+                                           _lib.ptr(st), None, 1 | 4, cap, None, None, None, _lib.ptr(only["stats"]), None, None, None, None, None, 0))
+
+
+def test_device_path_records_and_gather_single_rank():
+    """DeviceBatch.path_records (rrtk_extract_paths_xy) on real trees; multigpu.gather_tensors with one rank over NCCL."""
+    import torch
+    import torch.distributed as dist
+    from rrtplanner_b200 import multigpu
+    W, H, n, P = 128, 128, 800, 24
+    db = batch.DeviceBatch("star", W, H, n, 30.0).gen_worlds([worlds.world_seed(w) for w in range(P)])
+    ogs = db.og.cpu().numpy()
+    pairs = [worlds.start_goal(ogs[p], p) for p in range(P)]
+    db.set_plans(batch.make_desc(np.arange(P), [a for a, _ in pairs], [b for _, b in pairs]))
+    db.seed_samples(np.arange(P))
+    res = db.run().download()
+    rec = db.path_records(96)
+    torch.cuda.synchronize()
+    for p in range(P):
+        want = res.path(p)
+        assert int(rec["len"][p]) == len(want) and rec["path"][p, : len(want)].tolist() == want
+        assert np.array_equal(rec["xy"][p, : len(want)].cpu().numpy(), res.pts[p][want])
+        assert rec["path_cost"][p].item() == res.path_cost(p)
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29531")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    got = multigpu.gather_tensors(rec, P, dst=0)
+    assert all(torch.equal(got[k], rec[k]) for k in rec)
+    dist.destroy_process_group()
+
+
 # ---- edge cases ----------------------------------------------------------------------------------------
 def small_case(ctx, kind, og, n, xs, xg, samples, r=0.0, rg=0.0, balls=None):
     ctx.set_grids((og != 0).astype(np.uint8)[None])
@@ -554,3 +625,23 @@ def test_plan_rejects_bad_inputs(ctx):
         ctx.plan(1, good, 10, 5.0)                      # neither samples nor seeds
     with pytest.raises(MemoryError):
         ctx.plan(1, good, 65000, 5.0, samples=np.zeros((1, 65000, 2), dtype=np.int16))   # tree does not fit shared memory
+
+
+def test_world_without_free_cells_cannot_be_sampled(ctx):
+    """Seed mode draws free[choice(nfree)] (rrt.py:240); numpy raises for nfree = 0, and so do the host-buffer entry points and
+    the DeviceBatch wrapper instead of handing the planner an occupied cell (explicit sample streams stay legal)."""
+    full = np.ones((2, 40, 40), dtype=np.uint8)
+    full[1, 3, 4] = 0                                             # world 1 has exactly one free cell
+    assert ctx.set_grids(full).tolist() == [0, 1]
+    st = batch.seed_states([5])
+    with pytest.raises(ValueError, match="no free cell"):
+        ctx.plan(1, batch.make_desc([0], [[1, 1]], [[2, 2]]), 10, 5.0, states=st)
+    with pytest.raises(ValueError, match="no free cell"):
+        ctx.samples(batch.make_desc([0], [[1, 1]], [[2, 2]]), 10, st)
+    smp = ctx.samples(batch.make_desc([1], [[1, 1]], [[2, 2]]), 10, st)        # one free cell: every draw is that cell
+    assert (smp[0] == [3, 4]).all()
+    ctx.plan(1, batch.make_desc([0], [[1, 1]], [[2, 2]]), 4, 5.0, samples=np.zeros((1, 4, 2), dtype=np.int16))
+    db = batch.DeviceBatch("star", 40, 40, 10, 5.0).set_worlds_host(full)
+    db.set_plans(batch.make_desc([0], [[1, 1]], [[2, 2]]))
+    with pytest.raises(ValueError, match="no free cell"):
+        db.seed_samples([5])

@@ -30,6 +30,10 @@ def test_world_generator_properties():
     assert not np.array_equal(og, worlds.perlin_occupancygrid(128, 96, seed=6))
     stack = worlds.perlin_occupancygrid(64, 64, frames=3, seed=2)
     assert stack.shape == (3, 64, 64)
+    # frames are neighbouring slices of one smooth 3-D field (oggen.py:33-38): the environment changes gradually
+    long = worlds.perlin_occupancygrid(128, 128, frames=8, seed=2)
+    step = [(long[i] != long[i + 1]).mean() for i in range(7)]
+    assert 0 < max(step) < 0.05 and (long[0] != long[7]).mean() > max(step)
     a, b = worlds.start_goal(og, 3)
     assert og[a[0], a[1]] == 0 and og[b[0], b[1]] == 0 and not np.array_equal(a, b)
 
