@@ -446,15 +446,18 @@ def class_api_bench(cpu: bool):
 DUB_PLANS, DUB_NH, DUB_RHO, DUB_DS = 1024, 16, 6.0, 1.0
 
 
-def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, threads: int = 0):
+def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, threads: int = 0, rank: int = 0, world: int = 1):
     """1024 Dubins RRT* plans (rewire on) on independent 512x512 worlds, n=5000, r=50, 16 headings, rho=6, ds=1;
     sample cells from the device PCG64 stream of plan p, headings = default_rng(7000+p).integers(0, 16, n) (host).
-    Also times the same shape with the Euclidean model + rewire (the RRT* the reference's rewire block intends)."""
+    Also times the same shape with the Euclidean model + rewire (the RRT* the reference's rewire block intends).
+    With world > 1 every rank runs its own `plans` plans (ids rank * plans ...: weak scaling, no collective in the path);
+    the time is the maximum over the ranks and only the device arm is measured."""
     import torch
 
     from rrtplanner_b200 import _lib, batch, worlds
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream(dev)
+    ids = rank * plans + np.arange(plans)
     out = {"workload": "cfg5: %d Dubins RRT* plans (choose-parent + rewire), independent %dx%d worlds, n=%d, r_rewire=%g, "
                        "%d headings, rho=%g cells, ds=%g" % (plans, W, H, N_ITER, R_REWIRE, DUB_NH, DUB_RHO, DUB_DS),
            "parity": "UNPINNED: the reference ships no Dubins code; bit-exact against this project's specification oracle/rewire_oracle.c"}
@@ -462,11 +465,11 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
     for model in ("dubins", "euclid"):
         db = batch.DeviceBatch2(model, W, H, N_ITER, r_rewire=R_REWIRE, nheadings=DUB_NH, rho=DUB_RHO, ds=DUB_DS, device=local,
                                 threads=threads)
-        db.gen_worlds([worlds.world_seed(p) for p in range(plans)])
+        db.gen_worlds([worlds.world_seed(int(p)) for p in ids])
         pair_db = batch.DeviceBatch("star", W, H, 8, device=local)
         pair_db.bits, pair_db.rowcum = db.bits, db.rowcum
         pair_db.set_plans(batch.make_desc(np.arange(plans), np.zeros((plans, 2)), np.zeros((plans, 2))))
-        pair_db.seed_samples(2000 + np.arange(plans))
+        pair_db.seed_samples(2000 + ids)
         draws = pair_db.samples.cpu().numpy().astype(np.int64)
         starts = draws[:, 0]
         differs = (draws[:, 1:] != starts[:, None]).any(axis=2)
@@ -474,9 +477,9 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
         hs = np.random.default_rng(6000).integers(0, DUB_NH, size=(plans, 2))
         db.set_plans(batch.make_desc2(np.arange(plans), np.concatenate([starts, hs[:, :1]], axis=1),
                                       np.concatenate([goals, hs[:, 1:]], axis=1)))
-        db.seed_samples(np.arange(plans))
+        db.seed_samples(ids)
         if model == "dubins":
-            db.seed_heads(7000 + np.arange(plans))
+            db.seed_heads(7000 + ids)
         for _ in range(2):
             db.run()
         torch.cuda.synchronize(dev)
@@ -488,13 +491,21 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
         e1.record(stream)
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            import torch.distributed as dist
+            tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
         st = db.out["stats"].cpu().numpy()
         smem, blocks = db.footprint()
-        rec = {"plans_per_s": plans / (ms / 1e3), "ms_per_launch": ms, "gpu_launches": reps, "mean_vertices": float(st[:, 0].mean()),
+        rec = {"plans_per_s": plans * world / (ms / 1e3), "n_gpus": world, "plans_per_gpu": plans, "ms_per_launch": ms, "gpu_launches": reps, "mean_vertices": float(st[:, 0].mean()),
                "goal_found_frac": float(st[:, 2].mean()), "rewires_per_plan": float(st[:, 5].mean()),
                "edge_length_evals_per_s": float(st[:, 8].sum()) / (ms / 1e3), "edge_tests_per_s": float(st[:, 3].sum()) / (ms / 1e3),
                "smem_bytes_per_block": smem, "blocks_per_sm": blocks, "overflow": int(st[:, 9].sum()),
                "kernel": "rrtk::plan_rewire_kernel<%s, T=%d>" % (model.upper(), threads or 256)}
+        if world > 1:
+            out["dubins_rrtstar" if model == "dubins" else "euclid_rrtstar_with_rewire"] = rec
+            continue
         # end to end through the host-buffer C ABI: grids, descriptors, PCG64 states and headings up, every tree down
         ctx = _lib.Context()
         og_pin = torch.empty(tuple(db.og.shape), dtype=torch.uint8, pin_memory=True)
@@ -510,7 +521,7 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
         for rep in range(2):
             t0 = time.perf_counter()
             ctx.set_grids(og_host)
-            r_host = ctx.plan2(db.cfg, desc_h, N_ITER, states=batch.seed_states(np.arange(plans)), heads=heads_h, out=out_pin)
+            r_host = ctx.plan2(db.cfg, desc_h, N_ITER, states=batch.seed_states(ids), heads=heads_h, out=out_pin)
             dt = time.perf_counter() - t0
             t_best = dt if t_best is None else min(t_best, dt)
         ctx.close()
@@ -520,7 +531,7 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
                       "matches_device_arm": bool(np.array_equal(r_host[4], db.out["parent"].cpu().numpy()))}
         out["dubins_rrtstar" if model == "dubins" else "euclid_rrtstar_with_rewire"] = rec
         keep[model] = (db, starts, goals, hs)
-    if cpu:
+    if cpu and world == 1:
         from oracle import rewire_oracle as O2                # checker + CPU baseline only
         for model, key in (("dubins", "dubins_rrtstar"), ("euclid", "euclid_rrtstar_with_rewire")):
             db, starts, goals, hs = keep[model]
@@ -799,6 +810,9 @@ def gpu_arm(args):
     # ---- strong scaling: the same 4096 plans in total whatever N, with the final gather of the paths ----
     strong = None if args.no_strong else strong_leg(local, rank, world, max(2, min(args.steps, 10)), args.warmup, barrier)
 
+    # cfg5 on every rank (weak scaling like the headline; K8 plans shard by index exactly like K7's)
+    dub_multi = dubins_bench(local, args.steps, False, rank=rank, world=world) if (world > 1 and not args.no_dubins) else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -871,6 +885,8 @@ def gpu_arm(args):
         line["class_api_bench"] = class_api_bench(not args.no_cpu)
     if world == 1 and not args.no_dubins:
         line["dubins_bench"] = dubins_bench(local, args.steps, not args.no_cpu)
+    if dub_multi is not None:
+        line["dubins_bench"] = dub_multi
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -98,10 +98,13 @@ int clearance_launch(const uint32_t *d_bits, int nworlds, int W, int H, int cap,
 }
 
 // ---- the walk ---------------------------------------------------------------------------------------
-// A segment as the walk wants it, 16 bytes, made lane-parallel when the warp stages its block:
-//   .x = ax | ay << 16      .y = major      .z = minor << 3 | flags (1: x is the major axis, 2: sx < 0, 4: sy < 0)
-//   .w = fp32 bits of ~1 / (2 major)
-__device__ __forceinline__ int4 cf_pack(int4 e)
+// A segment as the walk wants it, made lane-parallel (all 32 lanes busy) when the warp stages its pool and kept in shared
+// memory as two 16-byte words, so that a lane that draws a new segment only loads them:
+//   a = (base, step_k, step_q, major)      cell k of the walk lives at clear[base + k * step_k + q(k) * step_q]
+//   b = (minor, fp32 bits of ~1 / (2 major), world, result)        result: written when the walk is over
+struct CfRec { int4 a, b; };
+
+__device__ __forceinline__ CfRec cf_prepare(int4 e, int world, int H)
 {
     const int dx = e.z - e.x, dy = e.w - e.y;
     const int adx = abs(dx), ady = abs(dy);
@@ -109,43 +112,21 @@ __device__ __forceinline__ int4 cf_pack(int4 e)
     const int major = xmajor ? adx : ady, minor = xmajor ? ady : adx;
     float inv = 0.f;
     if (major > 0) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__int2float_rn(2 * major)));
-    const int flags = (xmajor ? 1 : 0) | (dx > 0 ? 0 : 2) | (dy > 0 ? 0 : 4);         // sx = +1 iff x0 < x1 (rrt.py:207-215)
-    return make_int4(e.x | (e.y << 16), major, (minor << 3) | flags, __float_as_int(inv));
-}
-
-struct CfSeg {
-    int base, step_k, step_q;      // cell k of the walk lives at clear[base + k * step_k + q(k) * step_q]
-    int major, minor, k, slot;
-    float inv;
-};
-
-__device__ __forceinline__ void cf_unpack(CfSeg &s, int4 p, int slot, int H)
-{
-    const int ax = p.x & 0xffff, ay = (p.x >> 16) & 0xffff;
-    const int sxH = (p.z & 2) ? -H : H, sy = (p.z & 4) ? -1 : 1;
-    s.base = ax * H + ay;
-    s.step_k = (p.z & 1) ? sxH : sy;
-    s.step_q = (p.z & 1) ? sy : sxH;
-    s.major = p.y;
-    s.minor = p.z >> 3;
-    s.inv = __int_as_float(p.w);
-    s.k = 0;
-    s.slot = slot;
+    const int sxH = dx > 0 ? H : -H, sy = dy > 0 ? 1 : -1;                            // sx = +1 iff x0 < x1 (rrt.py:207-215)
+    CfRec r;
+    r.a = make_int4(e.x * H + e.y, xmajor ? sxH : sy, xmajor ? sy : sxH, major);
+    r.b = make_int4(minor, __float_as_int(inv), world, 0);
+    return r;
 }
 
 // Scheduling.  A segment needs anything between one and ~60 dependent reads (how far it gets before it hits something is
-// close to exponential, whatever its length), and a warp finishes with its slowest lane.  Each warp owns a pool of kPool
-// segments staged in shared memory and every lane walks kCfIlp of them at once (1 by default), drawing the next one as one finishes: the
-// throughput of this kernel is the number of reads in flight per SM over their latency (one scattered byte read costs the
-// SM ~1.08 cycles whatever the path -- LDG, texture: scripts/micro/scatter.cu -- so an SM wants ~2000 of them in flight),
-// and with one segment per lane half of the lanes sit idle behind the longest walk of their warp (17 of 32 threads active,
-// profiles/r1_v7_cf_ncu.txt).  Tried and measured without effect on cfg2: drawing the pool longest first (length does not
-// predict the work), time-slicing the segments between the lanes (0.130 ms instead of 0.089: the swaps cost more than the
-// idle lanes); several segments per lane at once (-DRRTK_CF_ILP=2, 3, 4: 0.112, 0.152, 0.179 ms against 0.091 with one).
-#ifndef RRTK_CF_ILP
-#define RRTK_CF_ILP 1
-#endif
-constexpr int kCfIlp = RRTK_CF_ILP;
+// close to exponential, whatever its length), and a warp finishes with its slowest lane: 17 of 32 threads are active on
+// average (profiles/r2_v2_cf_ncu.txt).  Each warp owns a pool of kCfPerWarp segments staged in shared memory and its lanes
+// draw the next one as they finish.  The kernel is bound by instruction issue (68 % of the issue slots, 48 warp
+// instructions per segment before the records were staged ready-made), so what pays is fewer instructions per step and
+// per draw.  Tried on cfg2 and measured without gain: drawing the pool longest first (length does not predict the work),
+// time-slicing the segments between the lanes (0.130 ms instead of 0.089: the swaps cost more than the idle lanes), several
+// segments per lane at once (2 / 3 / 4: 0.112 / 0.152 / 0.179 ms), larger pools with fewer warps (256: 0.114 ms).
 constexpr int kCfThreads = 128;
 
 template <int kCfPerWarp>
@@ -153,84 +134,67 @@ __global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t 
                                                                   const int4 *__restrict__ segs, const int *__restrict__ world,
                                                                   int64_t nseg, uint8_t *__restrict__ free_out, int *__restrict__ cells_out)
 {
-    __shared__ int4 s_seg[kCfThreads / 32][kCfPerWarp];      // a finished segment's slot holds its result in .x
+    __shared__ int4 s_a[kCfThreads / 32][kCfPerWarp];
+    __shared__ int4 s_b[kCfThreads / 32][kCfPerWarp];
     static_assert(kCfPerWarp % 32 == 0, "pool shape");
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * kCfThreads + threadIdx.x) >> 5;
     const int64_t first = warp * kCfPerWarp;
     if (first >= nseg) return;
     const int cnt = (int)min((int64_t)kCfPerWarp, nseg - first);
-    int4 *mine = s_seg[wib];
-    for (int i = lane; i < cnt; i += 32) mine[i] = cf_pack(__ldg(segs + first + i));   // coalesced: 512 bytes per step
-    __syncwarp();
-    int next = 32 * kCfIlp;                          // next undistributed slot (warp-uniform)
-    CfSeg s[kCfIlp];
-    bool active[kCfIlp];
-    const uint8_t *field[kCfIlp];
-    bool any = false;
-#pragma unroll
-    for (int u = 0; u < kCfIlp; ++u) {
-        const int slot = 32 * u + lane;
-        active[u] = slot < cnt;
-        field[u] = clear;
-        if (active[u]) {
-            cf_unpack(s[u], mine[slot], slot, H);
-            if (world) field[u] = clear + (size_t)__ldg(world + first + slot) * cells_per;
-        }
-        any |= active[u];
+    int4 *ra = s_a[wib], *rb = s_b[wib];
+    for (int i = lane; i < cnt; i += 32) {                                           // coalesced: 512 bytes per step
+        const CfRec r = cf_prepare(__ldg(segs + first + i), world ? __ldg(world + first + i) : 0, H);
+        ra[i] = r.a; rb[i] = r.b;
     }
-    while (__any_sync(RRTK_FULL, any)) {
-        int d[kCfIlp];
-        // all reads of the turn are requested before the first one is consumed
-#pragma unroll
-        for (int u = 0; u < kCfIlp; ++u) {
-            d[u] = 1;
-            if (active[u]) {
-                // cell k of the walk: q(k) = floor((2 k minor + major) / (2 major))
-                int q = 0;
-                if (s[u].major > 0) {
-                    const unsigned den = 2u * (unsigned)s[u].major;
-                    const unsigned num = 2u * (unsigned)s[u].k * (unsigned)s[u].minor + (unsigned)s[u].major;      // < 2^31
-                    q = __float2int_rz(__uint2float_rn(num) * s[u].inv);
-                    int r = (int)(num - (unsigned)q * den);
-                    if (r < 0) { --q; r += (int)den; }
-                    if (r >= (int)den) ++q;
-                }
-                d[u] = __ldg(field[u] + (s[u].base + s[u].k * s[u].step_k + q * s[u].step_q));
+    __syncwarp();
+    int next = 32;                                   // next undistributed slot (warp-uniform)
+    int slot = lane, k = 0;
+    bool active = lane < cnt;
+    int4 a = make_int4(0, 0, 0, 0), b = a;
+    const uint8_t *field = clear;
+    if (active) {
+        a = ra[slot]; b = rb[slot];
+        field = clear + (size_t)b.z * cells_per;
+    }
+    while (__any_sync(RRTK_FULL, active)) {
+        bool done = false;
+        if (active) {
+            // cell k of the walk: q(k) = floor((2 k minor + major) / (2 major)); a = (base, step_k, step_q, major), b.x = minor
+            int q = 0;
+            if (a.w > 0) {
+                const unsigned den = 2u * (unsigned)a.w;
+                const unsigned num = 2u * (unsigned)k * (unsigned)b.x + (unsigned)a.w;       // < 2^31
+                q = __float2int_rz(__uint2float_rn(num) * __int_as_float(b.y));
+                int r = (int)(num - (unsigned)q * den);
+                if (r < 0) { --q; r += (int)den; }
+                if (r >= (int)den) ++q;
             }
+            const int d = __ldg(field + (a.x + k * a.y + q * a.z));
+            int result = k;                                                          // d == 0: first occupied cell
+            done = d == 0;
+            k += d;                                                                  // cells k+1 .. k+d-1 are free
+            if (k > a.w) { done = true; result = -(a.w + 1); }
+            if (done) rb[slot].w = result;
         }
-        any = false;
-#pragma unroll
-        for (int u = 0; u < kCfIlp; ++u) {
-            bool done = false;
-            if (active[u]) {
-                int result = 0;
-                if (d[u] == 0) { done = true; result = s[u].k; }                     // first occupied cell
-                else {
-                    s[u].k += d[u];                                                  // cells k+1 .. k+d-1 are free
-                    if (s[u].k > s[u].major) { done = true; result = -(s[u].major + 1); }
+        // lanes that finished take the next slots of the pool, in lane order
+        const unsigned fin = __ballot_sync(RRTK_FULL, active && done);
+        if (fin) {
+            if (active && done) {
+                slot = next + __popc(fin & ((1u << lane) - 1u));
+                active = slot < cnt;
+                if (active) {
+                    a = ra[slot]; b = rb[slot];
+                    k = 0;
+                    field = clear + (size_t)b.z * cells_per;
                 }
-                if (done) mine[s[u].slot].x = result;
             }
-            // lanes that finished take the next slots of the pool, in lane order
-            const unsigned fin = __ballot_sync(RRTK_FULL, active[u] && done);
-            if (fin) {
-                if (active[u] && done) {
-                    const int slot = next + __popc(fin & ((1u << lane) - 1u));
-                    active[u] = slot < cnt;
-                    if (active[u]) {
-                        cf_unpack(s[u], mine[slot], slot, H);
-                        if (world) field[u] = clear + (size_t)__ldg(world + first + slot) * cells_per;
-                    }
-                }
-                next += __popc(fin);
-            }
-            any |= active[u];
+            next += __popc(fin);
         }
     }
     __syncwarp();
     for (int i = lane; i < cnt; i += 32) {                                            // coalesced results
-        const int r = mine[i].x;
+        const int r = rb[i].w;
         free_out[first + i] = r < 0;
         if (cells_out) cells_out[first + i] = cells_tested(r);
     }
