@@ -5,20 +5,28 @@
 One "step" = one pass of the hot path over one batch: P independent RRT* plans per GPU (world w
 seeded 1000+w, one start/goal pair per world, sample stream of plan p = default_rng(p)), i.e. the
 sampler kernel + the persistent plan kernel.  N > 1 is launched by torchrun, one rank per GPU;
-plans are independent so every rank runs its own P plans (weak scaling, no data-path collective);
-only per-plan statistics are gathered at the end of each step.
+plans are independent so every rank runs its own P plans (the headline: weak scaling, no data-path
+collective; only per-plan statistics are gathered at the end of each step).
 
-The JSON line carries, besides the contract keys: `roofline` (plan kernel: algorithmic bytes /
-CUDA-event time against the shared-memory bandwidth of SURVEY.md section 8(d), plus an HBM view), `e2e`
-(same metric through the host-buffer C-ABI call rrtk_ctx_plan_worlds: H2D of grids/descriptors/seeds and
-D2H of all trees inside the timed region), `cpu_baseline` (the oracle's Python/Numba port of the
-reference, one core, a bounded sample of the same plans), `clocks`, and `collision_microbench`
-(BASELINE cfg2, the "collision checks/sec" half of the metric: both collision kernels with their own
-roofline object and the C oracle on one core; N=1 only).
+The JSON line carries, besides the contract keys:
+  roofline             plan kernel: algorithmic bytes / CUDA-event time against the shared-memory read bandwidth MEASURED in the
+                       run (rrtplanner_b200/peaks.py; SURVEY.md section 8(d) names the bound), plus an HBM view
+  e2e                  the same metric through the host-buffer C-ABI call rrtk_ctx_plan_worlds2 -- packed grids, descriptors
+                       and PCG64 states up, the path record and statistics of every plan down, all inside the timed region;
+                       `trees_mode` beside it is the round-1 form (uint8 grids up, every tree down)
+  strong_scaling       BASELINE cfg3 as worded: 4096 plans IN TOTAL sharded over the ranks, every step ending with the gather
+                       of all path records to rank 0 over NCCL (inside the timed region), checked against a single-GPU run
+  cpu_baseline         the oracle's Python/Numba port of the reference on one core, a bounded sample of the same plans;
+                       `matches_oracle`: the trees of that sample equal the GPU's bit for bit
+  clocks               nvidia-smi samples during the timed region
+and, at N = 1, one object per other BASELINE configuration, each with its own roofline / e2e / cpu_baseline / matches_oracle:
+  collision_microbench (cfg2, both collision kernels against the measured L2 read bandwidth), informed_bench (cfg4),
+  class_api_bench (cfg1), dubins_bench (cfg5; also at N > 1, every rank its own 1024 plans).
 
 `--impl reference` times the reference's CPU algorithm (oracle/rrt_oracle.py: the numpy/Numba port
-with the reference's cost profile -- the Python reference itself cannot travel to the GPU box) on
-all host cores, one plan per process, on the same worlds / pairs / streams.
+with the reference's cost profile -- the Python reference itself cannot travel to the GPU box; BASELINE.md
+section 4 calibrates the port against the unmodified reference) on all host cores, one plan per process,
+on the same worlds / pairs / streams.
 """
 from __future__ import annotations
 
@@ -39,8 +47,8 @@ W = H = 512
 N_ITER = 5000
 R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
-NCU_DRAM_BYTES_PER_PLAN = 104936448.0 / 1036          # re-captured whenever the plan kernel changes
-NCU_DRAM_SOURCE = "profiles/r1_v6_plan_kernel_ncu.txt: 104.94 MB for 1036 plans"
+NCU_DRAM_BYTES_PER_PLAN = (71040000.0 + 32312576.0) / 1036          # re-captured whenever the plan kernel changes
+NCU_DRAM_SOURCE = "profiles/r2_v2_plan_ncu.txt: 71.04 MB read + 32.31 MB written for 1036 plans"
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
 
 
@@ -244,9 +252,9 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
     bit_grid = {
         "kernel": "rrtk::collision_global_kernel (warp per segment on the tiled bit grid)", "segments_per_s": CC_NSEG / (ms / 1e3),
         "cells_per_s": ncells / (ms / 1e3), "ms_per_launch": ms, "gpu_launches": reps,
-        "roofline": roof("rrtk::collision_global_kernel", ms, 17309440.0,
+        "roofline": roof("rrtk::collision_global_kernel", ms, 17309184.0,
                          "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
-                         "this launch (profiles/r1_v6_cc_ncu.txt): 16 MB of segment records + the 512 KB grid, once"),
+                         "this launch (profiles/r2_v2_cc_ncu.txt): 16 MB of segment records + the 512 KB grid, once"),
     }
     # K1b: same outputs from the clearance field (built once per grid, outside the timed region like the packing)
     cap = 128
@@ -281,7 +289,9 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
         "segments_per_s": CC_NSEG / (ms_cf / 1e3), "cells_per_s": ncells / (ms_cf / 1e3), "ms_per_launch": ms_cf, "gpu_launches": reps,
         "field_build_ms": eb0.elapsed_time(eb1), "field_bytes": CC_SIZE * CC_SIZE,
         "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free2) and torch.equal(cells, cells2)),
-        "roofline": roof("rrtk::collision_cf_kernel", ms_cf, None, "not captured for this kernel version"),
+        "roofline": roof("rrtk::collision_cf_kernel", ms_cf, 20984320.0,
+                         "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                         "launch (profiles/r2_v2_cf_ncu.txt): 16 MB of segment records + the 4 MB field, once (the 5 MB of results stay in L2)"),
         "note": "the clearance-field walk skips cells the field proves free, so it reads fewer bytes than the algorithmic 4 B x cells the "
                 "reference would test; what bounds it is the rate of scattered L1 reads (~1.08 cycles per lane-load per SM, "
                 "scripts/micro/scatter.cu), about 11 per segment",
@@ -643,7 +653,10 @@ def strong_leg(local: int, rank: int, world: int, steps: int, warmup: int, barri
         full.run()
         want = full.path_records(PATH_CAP)
         # rows longer than the cap are left unwritten by design: compare the defined part
-        ok = all(bool(torch.equal(got[k], want[k])) for k in ("len", "path_cost", "stats"))
+        # (the two walk counters of the statistics row depend on how the warps of a block interleave in the goal search -- a shared
+        #  bound prunes candidates -- and are left out, as in the parity tests)
+        keep = torch.tensor([i for i, nm in enumerate(_lib.STAT_NAMES) if nm not in ("checks", "cells")], device=dev)
+        ok = all(bool(torch.equal(got[k], want[k])) for k in ("len", "path_cost")) and bool(torch.equal(got["stats"][:, keep], want["stats"][:, keep]))
         short = want["len"] <= PATH_CAP
         ok = ok and bool(torch.equal(got["path"][short], want["path"][short])) and bool(torch.equal(got["xy"][short], want["xy"][short]))
         out["gathered_equals_single_gpu_run"] = ok
@@ -798,12 +811,12 @@ def gpu_arm(args):
                "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt_paths / args.steps,
                "api": "rrtk_ctx_plan_worlds2(RRTK_IN_BITS | RRTK_OUT_PATHS) via rrtplanner_b200._lib.Context.plan_worlds2: tiled bit grids, plan "
                       "descriptors and PCG64 states up; path record (ids + points, cap %d; length; cost) and statistics of every plan down; "
-                      "chunks of %d plans on 8 rotating streams, pinned host buffers" % (PATH_CAP, args.e2e_chunk or 2 * sms),
+                      "chunks of %d plans on 8 rotating streams, pinned host buffers" % (PATH_CAP, args.e2e_chunk or 4 * sms),
                "matches_device_arm": bool(same_paths), "host_packer_matches_device_packer": packer_ok,
                "trees_mode": {"value": Pe * world * args.steps / dt_trees, "unit": "plans/s", "ms_per_step": 1000 * dt_trees / args.steps,
                               "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
                               "d2h_bytes_per_step": int(Pe * ((N_ITER + 1) * 16 + _lib.STAT_COUNT * 8)),
-                              "api": "rrtk_ctx_plan_worlds2(RRTK_OUT_TREES): uint8 grids up, every tree down (the round-1 call)",
+                              "api": "rrtk_ctx_plan_worlds2(RRTK_OUT_TREES): uint8 grids up, every tree down (the round-1 call), chunks of %d plans" % (args.e2e_chunk or 2 * sms),
                               "matches_device_arm": bool(same_trees)}}
         ctx.close()
 

@@ -128,9 +128,12 @@ __device__ __forceinline__ CfRec cf_prepare(int4 e, int world, int H)
 // time-slicing the segments between the lanes (0.130 ms instead of 0.089: the swaps cost more than the idle lanes), several
 // segments per lane at once (2 / 3 / 4: 0.112 / 0.152 / 0.179 ms), larger pools with fewer warps (256: 0.114 ms).
 constexpr int kCfThreads = 128;
+#ifndef RRTK_CF_MINB
+#define RRTK_CF_MINB 12
+#endif
 
 template <int kCfPerWarp>
-__global__ void __launch_bounds__(kCfThreads) collision_cf_kernel(const uint8_t *__restrict__ clear, size_t cells_per, int W, int H,
+__global__ void __launch_bounds__(kCfThreads, RRTK_CF_MINB) collision_cf_kernel(const uint8_t *__restrict__ clear, size_t cells_per, int W, int H,
                                                                   const int4 *__restrict__ segs, const int *__restrict__ world,
                                                                   int64_t nseg, uint8_t *__restrict__ free_out, int *__restrict__ cells_out)
 {
@@ -216,7 +219,7 @@ int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_s
     if (nseg == 0) return RRTK_OK;
     // segments per warp: enough for several draws per lane, few enough for the SMs to be full of warps on a big launch
     // (cfg2, 1 Mi segments, one segment per lane: pools of 64 / 128 / 256 -> 0.094 / 0.089 / 0.114 ms); RRTK_CF_POOL overrides
-    int64_t per = nseg / ((int64_t)sm_count * 56) + 1;
+    int64_t per = nseg / ((int64_t)sm_count * 128) + 1;
     const char *env = getenv("RRTK_CF_POOL");
     if (env && *env) per = atoi(env);
     if (per > 128) cf_launch_pool<256>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
