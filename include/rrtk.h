@@ -368,6 +368,10 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *ctx, int kind, const void *h_grids, int nwor
                           double *h_ell_c, int32_t *h_path, int16_t *h_xy, int32_t *h_len, double *h_path_cost,
                           int chunk_plans);
 
+/* `np.random.default_rng(seed)` (rrt.py:85) -> the PCG64 start state the seed modes take: {state_hi, state_lo, inc_hi,
+ * inc_lo} per seed, by numpy's published SeedSequence + pcg_setseq_128_srandom_r path.  Plain CPU code, no device needed. */
+int rrtk_seed_states(const uint64_t *h_seeds, int nseeds, uint64_t *h_state);
+
 /* K0 on the host, for callers that keep their worlds packed (`og[x, y] != 0`, rrt.py:218, one bit per cell in the
  * tiled layout; cells outside the grid are set).  Plain CPU loop, no device needed. */
 int rrtk_pack_grid_host(const uint8_t *h_og, int nworlds, int W, int H, uint32_t *h_bits);

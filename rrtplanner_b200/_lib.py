@@ -88,6 +88,7 @@ SIGNATURES = {
     "rrtk_ctx_plan_worlds2": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp,
                                    _vp, _vp, _vp, _vp, _i]),
     "rrtk_pack_grid_host": (_i, [_vp, _i, _i, _i, _vp]),
+    "rrtk_seed_states": (_i, [_vp, _i, _vp]),
     "rrtk_ctx_samples": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "rrtk_ctx_collision": (_i, [_vp, _i, _vp, _i64, _vp, _vp]),
     "rrtk_ctx_nearest": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp]),

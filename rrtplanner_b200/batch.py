@@ -54,7 +54,18 @@ def _mul64_wide(a, b):
 
 def seed_states(seeds: Sequence[int]) -> np.ndarray:
     """PCG64 start states {state_hi, state_lo, inc_hi, inc_lo} of ``np.random.default_rng(seed)``
-    (rrt.py:85) for an array of non-negative integer seeds < 2**64, vectorised.
+    (rrt.py:85) for an array of non-negative integer seeds < 2**64 (rrtk_seed_states: host code of librrtk.so)."""
+    seeds = np.asarray(seeds)
+    if seeds.ndim != 1 or (seeds.size and (seeds.min() < 0)):
+        raise ValueError("seeds must be a 1-D array of non-negative integers")
+    s64 = np.ascontiguousarray(seeds.astype(np.uint64))
+    out = np.empty((s64.shape[0], 4), dtype=np.uint64)
+    _lib.check(_lib.lib().rrtk_seed_states(_lib.ptr(s64), int(s64.shape[0]), _lib.ptr(out)), "rrtk_seed_states")
+    return out
+
+
+def seed_states_numpy(seeds: Sequence[int]) -> np.ndarray:
+    """The same in vectorised numpy (kept as an independent statement for the tests).
 
     Restates numpy's published seeding path (numpy/random/bit_generator.pyx ``SeedSequence``:
     hashmix / mix over a 4-word pool, ``generate_state(4, uint64)``; numpy/random/_pcg64.pyx +

@@ -123,7 +123,10 @@ struct DevBuf {
 
 // one stage of the chunked upload / plan / download pipeline of rrtk_ctx_plan_worlds
 struct PipeSlot {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;              // plan kernel, path extraction, downloads
+    cudaStream_t prep = nullptr;                // uploads, packing, free-space index, sampler: highest priority, so that the next chunk's
+                                                // (short) preparation kernels get SM slots ahead of the pending plan blocks of the running chunks
+    cudaEvent_t ready = nullptr, done = nullptr;
     DevBuf og, bits, rowcum, plans, samples, state, balls, pts, cost, parent, stats, ell;
     DevBuf path, xy, len, pcost;                // path records (RRTK_OUT_PATHS)
     std::vector<rrtk_plan_desc> desc;
@@ -405,6 +408,9 @@ int rrtk_destroy(rrtk_ctx *c)
         DevBuf *pb[] = {&p.og, &p.bits, &p.rowcum, &p.plans, &p.samples, &p.state, &p.balls, &p.pts, &p.cost, &p.parent, &p.stats, &p.ell};
         for (DevBuf *b : pb) b->release();
         if (p.stream) cudaStreamDestroy(p.stream);
+        if (p.prep) cudaStreamDestroy(p.prep);
+        if (p.ready) cudaEventDestroy(p.ready);
+        if (p.done) cudaEventDestroy(p.done);
     }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -631,8 +637,16 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
     const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
     for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
         PipeSlot &s = c->pipe[k];
-        if (!s.stream && !cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags")) break;
+        if (!s.stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);                          // hi = numerically lowest = greatest priority
+            if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags") ||
+                !cuda_ok(cudaStreamCreateWithPriority(&s.prep, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority") ||
+                !cuda_ok(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming), "cudaEventCreateWithFlags") ||
+                !cuda_ok(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreateWithFlags")) break;
+        }
         cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");       // buffers may be regrown below
+        cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
         bool ok = rrtk_ok(s.bits.reserve(words * 4 * max_nw)) && rrtk_ok(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw)) &&
                   rrtk_ok(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m)) && rrtk_ok(s.samples.reserve(max_m * n * 4)) &&
                   rrtk_ok(s.state.reserve(max_m * 32)) && rrtk_ok(s.pts.reserve(rows1 * max_m * 4)) &&
@@ -647,7 +661,8 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
     for (size_t ci = 0; ci + 1 < starts.size() && status == RRTK_OK; ++ci) {
         const int p0 = starts[ci], m = starts[ci + 1] - starts[ci];
         PipeSlot &s = c->pipe[ci % kPipeSlots];
-        cudaStream_t st = s.stream;
+        cudaStream_t st = s.prep;                                                 // preparation first (see PipeSlot), then the plan stream
+        if (ci >= (size_t)kPipeSlots && !cuda_ok(cudaStreamWaitEvent(st, s.done, 0), "cudaStreamWaitEvent")) break;   // the slot's last chunk still reads these buffers
         const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
         const uint8_t *src = static_cast<const uint8_t *>(h_grids) + grid_bytes * w0;
         if (in_bits) {
@@ -669,6 +684,9 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
         }
         if (kind == RRTK_INFORMED && h_balls &&
             !cuda_ok(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(balls)")) break;
+        if (!cuda_ok(cudaEventRecord(s.ready, st), "cudaEventRecord")) break;
+        st = s.stream;
+        if (!cuda_ok(cudaStreamWaitEvent(st, s.ready, 0), "cudaStreamWaitEvent")) break;
         if (!rrtk_ok(rrtk_plan_batch(kind, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, r_rewire, r_goal,
                                      s.samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? s.balls.as<double>() : nullptr,
                                      s.pts.as<int16_t>(), s.cost.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(),
@@ -690,9 +708,13 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
                 ok = cuda_ok(cudaMemcpyAsync(h_ell_c + (size_t)p0 * rows1, s.ell.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(ell)");
         }
         if (ok) cuda_ok(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(stats)");
+        cuda_ok(cudaEventRecord(s.done, st), "cudaEventRecord");
     }
     for (PipeSlot &s : c->pipe)
-        if (s.stream) cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+        if (s.stream) {
+            cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
+            cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+        }
     return status;
 }
 
@@ -706,6 +728,39 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *c, int kind, const uint8_t *h_og, int nworlds
     RRTK_REQUIRE(kind != RRTK_INFORMED || h_ell_c, "rrtk_ctx_plan_worlds: informed plans need h_ell_c");
     return rrtk_ctx_plan_worlds2(c, kind, h_og, nworlds, W, H, h_plans, nplans, n, r_rewire, r_goal, h_samples, h_state, h_balls,
                                  RRTK_OUT_TREES, 0, h_pts, h_cost, h_parent, h_stats, h_ell_c, nullptr, nullptr, nullptr, nullptr, chunk_plans);
+}
+
+// np.random.default_rng(seed) -> PCG64 start state, on the host (rrt.py:85).  numpy's published seeding path: SeedSequence
+// (numpy/random/bit_generator.pyx: hashmix / mix over a 4-word pool, generate_state(4, uint64)) feeds
+// pcg_setseq_128_srandom_r (numpy/random/src/pcg64/pcg64.h).  h_state: {state_hi, state_lo, inc_hi, inc_lo} per seed.
+int rrtk_seed_states(const uint64_t *h_seeds, int nseeds, uint64_t *h_state)
+{
+    RRTK_REQUIRE(h_seeds && h_state && nseeds >= 0, "rrtk_seed_states: null pointer or negative count");
+    typedef unsigned __int128 u128;
+    const u128 mult = ((u128)0x2360ED051FC65DA4ull << 64) | 0x4385DF649FCCF645ull;
+    for (int i = 0; i < nseeds; ++i) {
+        const uint32_t ent[4] = {(uint32_t)h_seeds[i], (uint32_t)(h_seeds[i] >> 32), 0u, 0u};
+        uint32_t hc = 0x43B0D7E5u, pool[4];
+        auto hashmix = [&](uint32_t v) { v ^= hc; hc *= 0x931E8875u; v *= hc; return v ^ (v >> 16); };
+        auto mix = [](uint32_t x, uint32_t y) { const uint32_t r = 0xCA01F9DDu * x - 0x4973F715u * y; return r ^ (r >> 16); };
+        for (int k = 0; k < 4; ++k) pool[k] = hashmix(ent[k]);
+        for (int src = 0; src < 4; ++src)
+            for (int dst = 0; dst < 4; ++dst)
+                if (src != dst) pool[dst] = mix(pool[dst], hashmix(pool[src]));
+        uint32_t hb = 0x8B51F9DDu, w32[8];
+        for (int k = 0; k < 8; ++k) { uint32_t v = pool[k & 3] ^ hb; hb *= 0x58F38DEDu; v *= hb; w32[k] = v ^ (v >> 16); }
+        uint64_t w[4];
+        for (int k = 0; k < 4; ++k) w[k] = (uint64_t)w32[2 * k] | ((uint64_t)w32[2 * k + 1] << 32);
+        const u128 initstate = ((u128)w[0] << 64) | w[1], initseq = ((u128)w[2] << 64) | w[3];
+        const u128 inc = (initseq << 1) | 1u;
+        u128 st = 0;
+        st = st * mult + inc;
+        st += initstate;
+        st = st * mult + inc;
+        uint64_t *o = h_state + 4 * (size_t)i;
+        o[0] = (uint64_t)(st >> 64); o[1] = (uint64_t)st; o[2] = (uint64_t)(inc >> 64); o[3] = (uint64_t)inc;
+    }
+    return RRTK_OK;
 }
 
 // K0 on the host (include/rrtk.h: the tiled bit layout), for callers that keep their worlds packed

@@ -8,7 +8,8 @@ def test_seed_states_match_numpy():
     rng = np.random.default_rng(1)
     seeds = np.concatenate([[0, 1, 2, 2 ** 31 - 1, 2 ** 32 - 1, 2 ** 32, 2 ** 63 + 11],
                             rng.integers(0, 2 ** 62, size=200), np.arange(300)]).astype(np.uint64)
-    got = batch.seed_states(seeds)
+    got = batch.seed_states(seeds)                       # rrtk_seed_states (C, host)
+    assert np.array_equal(got, batch.seed_states_numpy(seeds))
     for s, g in zip(seeds, got):
         assert np.array_equal(g, _lib.pcg64_state_words(np.random.default_rng(int(s)))), int(s)
 
