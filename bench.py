@@ -925,6 +925,7 @@ def main():
     ap.add_argument("--no-informed", action="store_true", help="skip the cfg4 RRTStarInformed leg")
     ap.add_argument("--no-class-api", action="store_true", help="skip the cfg1 class-API latency leg")
     ap.add_argument("--dubins-only", action="store_true", help="run only the cfg5 Dubins RRT* leg (profiling aid)")
+    ap.add_argument("--informed-only", action="store_true", help="run only the cfg4 RRTStarInformed leg (profiling aid)")
     ap.add_argument("--dubins-plans", type=int, default=DUB_PLANS)
     ap.add_argument("--plan-only", action="store_true", help="device arm of the headline only (experiments): implies every --no-* flag")
     args = ap.parse_args()
@@ -937,6 +938,11 @@ def main():
         torch.cuda.set_device(0)
         from rrtplanner_b200 import peaks as onchip
         print(json.dumps(collision_microbench(0, args.steps, args.warmup, not args.no_cpu, 1965.0, onchip.measure(0))), flush=True)
+    elif args.informed_only:
+        import torch
+        torch.cuda.set_device(0)
+        from rrtplanner_b200 import peaks as onchip
+        print(json.dumps(informed_bench(0, args.steps, not args.no_cpu, onchip.measure(0))), flush=True)
     elif args.dubins_only:
         import torch
         torch.cuda.set_device(0)

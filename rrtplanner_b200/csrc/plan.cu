@@ -54,7 +54,9 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
     const long long side = W > H ? W : H;
     if (((2 * side * side) << s.sbits) > (1ll << 29)) return false;     // |key| and |key - threshold| stay below 2^31
     s.steps_max = (rows + 3) / 4;
-    int cap = kind == RRTK_INFORMED ? 512 : 256;
+    // radius-set list per owner warp: larger sets take the exact brute-force path.  448 rather than 512 entries for informed
+    // plans lets two blocks of cfg4 (n = 20000: an 80 KB tree) share an SM: 2.24 k instead of 1.68 k plans/s
+    int cap = env_int("RRTK_PLAN_CAP", kind == RRTK_INFORMED ? 448 : 256);
     const int need = (n + 1 + 31) & ~31;
     s.list_cap = kind == RRTK_STANDARD ? 0 : (cap < need ? cap : need);
     s.smem = (size_t)4 * 4 * T * s.steps_max;
