@@ -26,6 +26,7 @@ struct PlanParams {
     int sbits;            // key = (d2 - |q|^2) << sbits | row, row = vertex index / T
     int list_cap;         // uint16 entries per sample in the radius-set lists
     int hit_words;        // membership words per thread per sample (32 rows each)
+    int tail_bytes;       // storage of the last of them: 1, 2 or 4 bytes (a full tree fills only its first 8 / 16 / 32 rows)
     int steps_max;        // quads per thread that hold tree vertices: ceil(ceil((n + 1) / T) / 4)
 };
 

@@ -101,8 +101,23 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 
     const int npts = 4 * T * P.steps_max;
     uint32_t *s_pts = smem;                                               // npts words
-    uint32_t *s_hits = smem + npts;                                       // [HW][K][T] thread-private membership words
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_hits + (KIND == RRTK_STANDARD ? 0 : HW * K * T));   // [NW][cap]: one list per owner warp
+    // thread-private membership words: [HW - 1][K][T] full words, then the last word of every (sample, thread) stored in
+    // tail_bytes bytes -- a tree of n + 1 vertices fills only its first rows (8 of 32 for n = 5000, T = 128), and the 3 KB
+    // this saves are what lets an eighth plan fit on the SM
+    uint32_t *s_hits = smem + npts;
+    const int tailb = P.tail_bytes;                                       // 1, 2 or 4
+    uint8_t *s_tail = reinterpret_cast<uint8_t *>(s_hits + (HW - 1) * K * T);
+    uint16_t *s_list = reinterpret_cast<uint16_t *>(KIND == RRTK_STANDARD ? (uint8_t *)s_hits : s_tail + ((tailb * K * T + 3) & ~3));   // [NW][cap]: one list per owner warp
+    auto hit_store = [&](int w, int k, int t, uint32_t word) {            // word: left-aligned (row r of the word in bit 31 - r)
+        if (w < HW - 1 || tailb == 4) s_hits[(w * K + k) * T + t] = word;
+        else if (tailb == 1) s_tail[k * T + t] = (uint8_t)(word >> 24);
+        else reinterpret_cast<uint16_t *>(s_tail)[k * T + t] = (uint16_t)(word >> 16);
+    };
+    auto hit_load = [&](int w, int k, int t) -> uint32_t {
+        if (w < HW - 1 || tailb == 4) return s_hits[(w * K + k) * T + t];
+        if (tailb == 1) return (uint32_t)s_tail[k * T + t] << 24;
+        return (uint32_t)reinterpret_cast<uint16_t *>(s_tail)[k * T + t] << 16;
+    };
 
     const rrtk_plan_desc *dsc = P.plans + plan;
     const uint32_t *gbits = P.bits + (size_t)dsc->world * P.words_per_grid;
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 }
                 if (KIND != RRTK_STANDARD) {
 #pragma unroll
-                    for (int k = 0; k < K; ++k) s_hits[(w * K + k) * T + tid] = h[k] << (32 - nrow);   // 2 <= nrow <= 32
+                    for (int k = 0; k < K; ++k) hit_store(w, k, tid, h[k] << (32 - nrow));   // 2 <= nrow <= 32
                 }
             }
             fold_near(tid, thr, best, s_near);
@@ -301,9 +316,8 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                     // membership words of this sample: nwords rows of T thread-private words
                     int mine = 0;
                     for (int w = 0; w < nwords; ++w) {
-                        const uint32_t *hw = s_hits + (w * K + k) * T + lane;
 #pragma unroll
-                        for (int c = 0; c < T / 32; ++c) mine += __popc(hw[32 * c]);
+                        for (int c = 0; c < T / 32; ++c) mine += __popc(hit_load(w, k, 32 * c + lane));
                     }
                     total = __reduce_add_sync(RRTK_FULL, mine);
                     if (total <= cap) {
@@ -316,10 +330,9 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                         }
                         uint16_t *out = list + (incl - mine);
                         for (int w = 0; w < nwords; ++w) {
-                            const uint32_t *hw = s_hits + (w * K + k) * T + lane;
 #pragma unroll
                             for (int c = 0; c < T / 32; ++c) {
-                                uint32_t bits = hw[32 * c];
+                                uint32_t bits = hit_load(w, k, 32 * c + lane);
                                 const int vtop = (32 * w + 31) * T + 32 * c + lane;      // bit b of the word <-> row 32 w + 31 - b
                                 while (bits) {
                                     const int b = 31 - __clz(bits);

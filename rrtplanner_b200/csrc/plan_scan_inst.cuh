@@ -28,6 +28,46 @@ static int scan_launch_k(const PlanParams &P, int nplans, int T, size_t smem, cu
     return RRTK_ERR_INVALID;
 }
 
+// resident blocks per SM of the kernel that would run (registers, shared memory incl. the static part, threads): asked of the
+// runtime, not estimated
+template <int K, int T>
+static int scan_occupancy_kt(size_t smem)
+{
+    auto kern = plan_scan_kernel<RRTK_SCAN_KIND, K, T>;
+    int blocks = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kern, T, smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return blocks;
+}
+
+template <int K>
+static int scan_occupancy_k(int T, size_t smem)
+{
+    switch (T) {
+        case 64: return scan_occupancy_kt<K, 64>(smem);
+        case 128: return scan_occupancy_kt<K, 128>(smem);
+        case 160: return scan_occupancy_kt<K, 160>(smem);
+        case 256: return scan_occupancy_kt<K, 256>(smem);
+        case 512: return scan_occupancy_kt<K, 512>(smem);
+    }
+    return 0;
+}
+
+int RRTK_SCAN_OCC_FN(int T, int K, size_t smem)
+{
+    switch (K) {
+        case 4: return scan_occupancy_k<4>(T, smem);
+        case 8: return scan_occupancy_k<8>(T, smem);
+#ifdef RRTK_SCAN_K16
+        case 16: return scan_occupancy_k<16>(T, smem);
+#endif
+    }
+    return 0;
+}
+
 int RRTK_SCAN_FN(const PlanParams &P, int nplans, int T, int K, size_t smem, cudaStream_t st)
 {
     switch (K) {
