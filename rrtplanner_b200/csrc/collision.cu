@@ -15,7 +15,7 @@
 //     along x leaves x & 31 unchanged and moves one tile column, along y it leaves the bit position
 //     unchanged and moves one tile row, so the major-axis part of the word index advances by a
 //     constant per chunk and only the minor coordinate is re-derived (incrementally, with a carry).
-// Grids that fit shared memory are staged there once per block (SharedGrid); larger ones (2048^2 =
+// Grids that fit shared memory are staged there once per block with one TMA bulk copy (SharedGrid); larger ones (2048^2 =
 // 512 KB) are read through L1/L2 on the read-only path (GlobalGrid), where a chunk touches at most a
 // handful of 128-byte tiles whatever its direction.
 #include "common.cuh"
@@ -150,9 +150,30 @@ __global__ void collision_shared_kernel(const uint32_t *__restrict__ bits, int w
     extern __shared__ __align__(16) uint32_t s_dyn[];
     SegPre *s_pre = reinterpret_cast<SegPre *>(s_dyn);                      // blockDim.x entries
     uint32_t *s_grid = s_dyn + blockDim.x * (sizeof(SegPre) / 4);
-    for (int i = threadIdx.x; i < words / 4; i += blockDim.x)
-        reinterpret_cast<uint4 *>(s_grid)[i] = __ldg(reinterpret_cast<const uint4 *>(bits) + i);
+    // The grid comes in with one bulk asynchronous copy (TMA, cp.async.bulk: no registers, no per-thread loop): thread 0 arms
+    // an mbarrier with the byte count and issues the copy, everybody waits on the barrier's phase.  Both addresses and the size
+    // are multiples of 128 bytes (whole tiles of a cudaMalloc'd grid).
+    __shared__ __align__(8) unsigned long long s_bar;
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)words * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"((uint32_t)__cvta_generic_to_shared(s_grid)), "l"(bits), "r"(bytes), "r"(bar) : "memory");
+    }
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "GRID_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                 "@p bra GRID_DONE;\n"
+                 "bra GRID_WAIT;\n"
+                 "GRID_DONE:\n"
+                 "}" ::"r"(bar) : "memory");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const SharedGrid g{s_grid};
