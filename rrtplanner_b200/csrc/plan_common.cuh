@@ -46,6 +46,7 @@ struct SampleRec {
 struct RoundSummary {
     int j, consumed, flags;       // flags: 1 have_sol, 2 finished
     int vsol;
+    int kwant, pad;               // packed-key kernel: samples the next round should take (adaptive, see plan_scan.cuh)
     double csol;
     long long first_sol;
 };

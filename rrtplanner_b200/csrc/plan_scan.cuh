@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 #define WALK(ax_, ay_, bx_, by_) warp_first_hit(gg, TY, ax_, ay_, bx_, by_, lane)
 
     // block-uniform state, replicated in every thread (refreshed from s_sum after each round)
-    int j = 1, it0 = 0;
+    int j = 1, it0 = 0, kwant = 1;
     // The commit duty rotates over the warps: warp w of every resident block sits on scheduler w mod 4 of the SM, so a
     // fixed commit warp would load one scheduler with all the serial work of every block (-DRRTK_FIXED_COMMIT: warp 0).
     int cw = 0;
@@ -185,8 +185,12 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
         if (KIND != RRTK_INFORMED && j == n) break;                       // tree full: every later sample is rejected
         if (KIND == RRTK_INFORMED && have_sol && balls == nullptr) break; // probe run: stop at first solution
         const bool ellipse_mode = (KIND == RRTK_INFORMED) && have_sol;
-        // samples of this round: fewer while the tree is tiny (a new vertex would often be the nearest one)
-        const int kact = min(min(K, n - it0), 1 + (j >> 3));
+        // Samples of this round.  How many a round takes changes the speed, never the result (the commit replays them in order):
+        // the count doubles after every round that consumed all of its samples and halves after a round that was cut short (but
+        // not below 1 + j / 8) -- few while the tree is tiny and a new vertex is often the nearest one to the next sample, K once
+        // it has grown, and K as well for a plan whose tree does not grow at all (a walled-in start: 5000 one-sample rounds made such plans the
+        // stragglers of every batch, 19 M cycles against a mean of 13.7 M at 444 plans per launch).
+        const int kact = min(min(K, n - it0), kwant);
 
         // ---- scan: nearest + radius-set bits for K samples over vertices 0 .. j-1 ---------------
         const int rows = (j + T - 1) / T;
@@ -613,7 +617,8 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
             // stage the next round's samples
             const int itn = it0 + consumed;
             __syncwarp();                                                      // lane 0's tree writes -> all lanes
-            const int kact_next = min(min(K, n - itn), 1 + (jc >> 3));       // the next round's kact (same formula as above)
+            const int kwant_next = consumed < kact ? max(min(K, 1 + (jc >> 3)), max(1, kact >> 1)) : min(K, 2 * kact);
+            const int kact_next = min(min(K, n - itn), kwant_next);          // the next round's kact (same formula as above)
             if (lane == 0) s_next = NW;
             if (KIND == RRTK_INFORMED && hs && balls != nullptr) {
                 if (lane < K) {
@@ -641,6 +646,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
                 RoundSummary s;
                 s.j = jc; s.consumed = consumed; s.flags = (hs ? 1 : 0) | (finished ? 2 : 0);
                 s.vsol = vs; s.csol = cs; s.first_sol = fs;
+                s.kwant = kwant_next; s.pad = 0;
                 s_sum = s;
             }
             (void)cut;
@@ -658,6 +664,7 @@ __global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_
 #endif
             j = s.j;
             it0 += s.consumed;
+            kwant = s.kwant;
             have_sol = s.flags & 1;
             vsol = s.vsol; csol = s.csol; first_sol = s.first_sol;
             if (s.flags & 2) break;
