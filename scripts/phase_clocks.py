@@ -26,6 +26,3 @@ scan, owner, commit, ownwork, rounds = (st[:, names.index(k)].astype(np.float64)
 tot = scan + owner + commit
 print(f"P={P} T={T or 'default'} kernel {e0.elapsed_time(e1):.2f} ms; rounds/plan {rounds.mean():.0f}; cycles/round: scan {np.mean(scan/rounds):.0f} owner {np.mean(owner/rounds):.0f} (warp 0 busy {np.mean(ownwork/rounds):.0f}) commit {np.mean(commit/rounds):.0f}; total/plan {tot.mean()/1e6:.2f} Mcycles")
 print(f"   per-plan cycles: mean {tot.mean()/1e6:.2f}M  p50 {np.percentile(tot,50)/1e6:.2f}M  p90 {np.percentile(tot,90)/1e6:.2f}M  max {tot.max()/1e6:.2f}M; rounds p50 {np.percentile(rounds,50):.0f} max {rounds.max():.0f}; kernel = {e0.elapsed_time(e1)*1.965e3/1e3:.2f} Mcycles at 1965 MHz")
-sub = [st[:, names.index(k)].astype(np.float64) for k in ("j", "vgoal", "found", "checks", "cells", "nn_pairs", "accepted")]
-lab = ("set-up", "compaction", "walk finish", "costing", "candidate loop", "record", "commit replay (warp 0's turns only)")
-print("   warp 0, cycles/round: " + ", ".join(f"{l} {np.mean(v/rounds):.0f}" for l, v in zip(lab, sub)))
