@@ -49,6 +49,8 @@ R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
 NCU_DRAM_BYTES_PER_PLAN = (71402240.0 + 33531136.0) / 1036          # re-captured whenever the plan kernel changes
 NCU_DRAM_SOURCE = "profiles/r2_v3_plan_ncu.txt: 71.40 MB read + 33.53 MB written for 1036 plans"
+NCU_CFD_DRAM_BYTES = None                                          # filled from the ncu capture of the directional walk
+NCU_CFD_DRAM_SOURCE = "not captured yet"
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
 
 
@@ -280,21 +282,52 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
     e1.record(stream)
     torch.cuda.synchronize(dev)
     ms_cf = e0.elapsed_time(e1) / reps
-    out = {
-        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
-        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
-        "obstacle_fraction": float(db.og.float().mean().item()),
-        # the faster of the two kernels carries the leg's headline numbers; both are listed with their own roofline object
-        "kernel": "rrtk::collision_cf_kernel (thread per segment on a uint8 clearance field, cap %d; rrtk_collision_segments_cf)" % cap,
+    iso_field = {
+        "kernel": "rrtk::collision_cf_kernel (thread per segment on one uint8 Chebyshev clearance field, cap %d; rrtk_collision_segments_cf)" % cap,
         "segments_per_s": CC_NSEG / (ms_cf / 1e3), "cells_per_s": ncells / (ms_cf / 1e3), "ms_per_launch": ms_cf, "gpu_launches": reps,
         "field_build_ms": eb0.elapsed_time(eb1), "field_bytes": CC_SIZE * CC_SIZE,
         "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free2) and torch.equal(cells, cells2)),
         "roofline": roof("rrtk::collision_cf_kernel", ms_cf, 20984064.0,
                          "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                          "launch (profiles/r2_v3_cf_ncu.txt): 16 MB of segment records + the 4 MB field, once (the 5 MB of results stay in L2)"),
-        "note": "the clearance-field walk skips cells the field proves free, so it reads fewer bytes than the algorithmic 4 B x cells the "
-                "reference would test; what bounds it is the rate of scattered L1 reads (~1.08 cycles per lane-load per SM, "
-                "scripts/micro/scatter.cu), about 11 per segment",
+    }
+    # K1b on directional fields: one field per octant of the walk (8 bytes per cell), about half the reads per segment
+    cap8 = 255
+    clear8 = torch.empty((8, CC_SIZE, CC_SIZE), dtype=torch.uint8, device=dev)
+    eb0.record(stream)
+    _lib.check(L.rrtk_clearance_field_dir(db.bits.data_ptr(), 1, CC_SIZE, CC_SIZE, cap8, clear8.data_ptr(), stream.cuda_stream), "clearance_field_dir")
+    eb1.record(stream)
+    free3 = torch.empty_like(free)
+    cells3 = torch.empty_like(cells)
+
+    def launch_cfd():
+        _lib.check(L.rrtk_collision_segments_cfd(clear8.data_ptr(), CC_SIZE, CC_SIZE, segs.data_ptr(), None, CC_NSEG, free3.data_ptr(),
+                                                 cells3.data_ptr(), stream.cuda_stream), "collision_segments_cfd")
+
+    for _ in range(max(3, warmup)):
+        launch_cfd()
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(reps):
+        launch_cfd()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms_cfd = e0.elapsed_time(e1) / reps
+    out = {
+        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
+        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
+        "obstacle_fraction": float(db.og.float().mean().item()),
+        # the fastest of the three kernels carries the leg's headline numbers; each is listed with its own roofline object
+        "kernel": "rrtk::collision_cf_kernel (thread per segment on eight directional uint8 clearance fields, one per octant of the walk, cap %d; "
+                  "rrtk_clearance_field_dir + rrtk_collision_segments_cfd)" % cap8,
+        "segments_per_s": CC_NSEG / (ms_cfd / 1e3), "cells_per_s": ncells / (ms_cfd / 1e3), "ms_per_launch": ms_cfd, "gpu_launches": reps,
+        "field_build_ms": eb0.elapsed_time(eb1), "field_bytes": 8 * CC_SIZE * CC_SIZE,
+        "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free3) and torch.equal(cells, cells3)),
+        "roofline": roof("rrtk::collision_cf_kernel", ms_cfd, NCU_CFD_DRAM_BYTES, NCU_CFD_DRAM_SOURCE),
+        "note": "a clearance-field walk skips the cells the field proves free, so it reads far fewer bytes than the algorithmic 4 B x cells the "
+                "reference would test (about 5 scattered byte reads per segment here, 10 on the isotropic field); what bounds it is the rate of "
+                "scattered L1 reads (~1.08 cycles per lane-load per SM, scripts/micro/scatter.cu) and the slowest lane of each warp",
+        "isotropic_field_kernel": iso_field,
         "bit_grid_kernel": bit_grid,
     }
     if cpu:

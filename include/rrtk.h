@@ -144,6 +144,16 @@ int rrtk_clearance_field(const uint32_t *d_bits, int nworlds, int W, int H, int 
 int rrtk_collision_segments_cf(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world,
                                int64_t nseg, uint8_t *d_free, int32_t *d_cells, void *stream);
 
+/* Directional form of the same idea: eight fields per world, one per octant of a walk (which axis is the major one,
+ * sign of dx, sign of dy -- rrt.py:199-215 fixes all three for a segment).  The field of octant o holds, per cell, the
+ * depth (capped) of the obstacle-free cone the walk can reach from that cell, so obstacles beside or behind the walk do
+ * not shorten the step: about half the reads of the isotropic field on cfg2, at 8 bytes per cell.
+ *   o = 4 * (|dx| >= |dy|) + 2 * (dx > 0) + (dy > 0);   d_clear8[((w * 8 + o) * W + x) * H + y],  2 <= cap <= 255. */
+int rrtk_clearance_field_dir(const uint32_t *d_bits, int nworlds, int W, int H, int cap, uint8_t *d_clear8, void *stream);
+/* rrtk_collision_segments with identical outputs, walking the directional fields of rrtk_clearance_field_dir. */
+int rrtk_collision_segments_cfd(const uint8_t *d_clear8, int W, int H, const int32_t *d_segs, const int32_t *d_world,
+                                int64_t nseg, uint8_t *d_free, int32_t *d_cells, void *stream);
+
 /* ---- K2: RRT.near(points, x)[0] (rrt.py:131-155), batched, pinned tie rule (lowest index) ------- */
 /* d_pts: npts x (x, y) int32.  d_queries: nq x (x, y).  d_count (optional): query q only sees the
  * first d_count[q] points (the filled prefix of the tree); NULL = all npts.  d_idx[q] = nearest

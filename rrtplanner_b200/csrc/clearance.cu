@@ -97,14 +97,90 @@ int clearance_launch(const uint32_t *d_bits, int nworlds, int W, int H, int cap,
     return RRTK_OK;
 }
 
+// ---- directional clearance: one field per octant of the walk -------------------------------------------
+// The walk of a segment never turns: with (major axis, sign of dx, sign of dy) fixed, cell k + i lies i steps ahead on the
+// major axis and between 0 and i steps ahead on the minor axis.  So instead of the Chebyshev ball the field of an octant
+// keeps, per cell, the depth of the free *cone* ahead of it:
+//     D(c) = 0 on obstacles, else min(cap, 1 + min(D(c + major step), D(c + major step + minor step)))
+// (cells outside the grid count as free: the walk stays inside the bounding box of its end points).  D(cell k) = d > 0
+// proves cells k+1 .. k+d-1 free exactly like the isotropic field, but an obstacle beside or behind the walk no longer
+// shortens the step: on cfg2 a segment takes 4.9 reads instead of 10.1 (p99: 17 instead of 44), at 8 bytes per cell.
+// Octant o = 4 * (x is the major axis) + 2 * (dx > 0) + (dy > 0); layout clear8[(world * 8 + o) * W * H + x * H + y].
+//
+// Built by one sweep against the direction of the major axis: a thread keeps one minor coordinate and the block exchanges
+// the previous column through shared memory.  D saturates at cap, so a value depends on at most cap - 1 further minor
+// rows: stripes of the minor axis overlap by that much and need no exchange between blocks.
+constexpr int kDirThreadsMax = 1024;
+
+__global__ void __launch_bounds__(kDirThreadsMax) clearance_dir_kernel(const uint32_t *__restrict__ bits, int W, int H, int cap, int stripes, int rows_per,
+                                                                      int wide, uint8_t *__restrict__ clear8)
+{
+    __shared__ uint8_t s_col[2][kDirThreadsMax + 4];
+    const int tid = threadIdx.x;
+    const int stripe = blockIdx.x % stripes, oct = (blockIdx.x / stripes) & 7, world = blockIdx.x / (stripes * 8);
+    const bool xmajor = (oct & 4) != 0;
+    const bool maj_pos = xmajor ? (oct & 2) != 0 : (oct & 1) != 0, min_pos = xmajor ? (oct & 1) != 0 : (oct & 2) != 0;
+    const int nmaj = xmajor ? W : H, nmin = xmajor ? H : W;
+    const int TY = tiles_y(H);
+    if (stripe * rows_per >= nmin) return;                                     // block-uniform
+    const int u = stripe * rows_per + tid;                                     // minor coordinate, counted along the walk's minor direction
+    const bool inside = u < nmin;
+    const bool writes = inside && tid < rows_per;
+    const int m = min_pos ? u : nmin - 1 - u;
+    const uint32_t *g = bits + (size_t)world * grid_words(W, H);
+    uint8_t *field = clear8 + ((size_t)world * 8 + oct) * ((size_t)W * H);
+    s_col[0][tid] = (uint8_t)cap;
+    if (tid == 0) { s_col[0][blockDim.x] = (uint8_t)cap; s_col[1][blockDim.x] = (uint8_t)cap; }
+    __syncthreads();
+    int own = cap, cur = 0;
+    uint32_t acc = 0;
+    for (int v = nmaj - 1; v >= 0; --v) {
+        const int M = maj_pos ? v : nmaj - 1 - v;
+        int d = cap;
+        if (inside) {
+            const int x = xmajor ? M : m, y = xmajor ? m : M;
+            const bool occ = (g[word_index(x, y, TY)] >> (y & 31)) & 1u;
+            d = occ ? 0 : min(cap, 1 + min(own, (int)s_col[cur][tid + 1]));
+            if (writes) {
+                if (xmajor) field[(size_t)M * H + m] = (uint8_t)d;                  // threads <-> consecutive y: whole sectors
+                else if (!wide) field[(size_t)m * H + M] = (uint8_t)d;
+                else {                                                              // threads <-> x (stride H): four steps per store
+                    acc |= (uint32_t)d << (8 * (M & 3));
+                    if ((M & 3) == (maj_pos ? 0 : 3)) {
+                        *reinterpret_cast<uint32_t *>(field + (size_t)m * H + (M & ~3)) = acc;
+                        acc = 0;
+                    }
+                }
+            }
+        }
+        own = d;
+        s_col[cur ^ 1][tid] = (uint8_t)d;
+        cur ^= 1;
+        __syncthreads();
+    }
+}
+
+int clearance_dir_launch(const uint32_t *d_bits, int nworlds, int W, int H, int cap, uint8_t *d_clear8, cudaStream_t st)
+{
+    if ((size_t)W * H * nworlds == 0) return RRTK_OK;
+    const int nmin_max = W > H ? W : H;
+    const int threads = nmin_max >= kDirThreadsMax ? kDirThreadsMax : (nmin_max + 31) & ~31;
+    const int rows_per = nmin_max <= threads ? threads : threads - (cap - 1);     // one stripe sees the whole axis: no overlap needed
+    const int stripes = (nmin_max + rows_per - 1) / rows_per;
+    const int wide = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_clear8) & 3) == 0);
+    clearance_dir_kernel<<<(unsigned)((size_t)nworlds * 8 * stripes), threads, 0, st>>>(d_bits, W, H, cap, stripes, rows_per, wide, d_clear8);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
 // ---- the walk ---------------------------------------------------------------------------------------
 // A segment as the walk wants it, made lane-parallel (all 32 lanes busy) when the warp stages its pool and kept in shared
 // memory as two 16-byte words, so that a lane that draws a new segment only loads them:
 //   a = (base, step_k, step_q, major)      cell k of the walk lives at clear[base + k * step_k + q(k) * step_q]
-//   b = (minor, fp32 bits of ~1 / (2 major), world, result)        result: written when the walk is over
+//   b = (minor, fp32 bits of ~1 / (2 major), field, result)        field: which W x H field to read; result: written when the walk is over
 struct CfRec { int4 a, b; };
 
-__device__ __forceinline__ CfRec cf_prepare(int4 e, int world, int H)
+__device__ __forceinline__ CfRec cf_prepare(int4 e, int world, int H, int nf)
 {
     const int dx = e.z - e.x, dy = e.w - e.y;
     const int adx = abs(dx), ady = abs(dy);
@@ -115,7 +191,8 @@ __device__ __forceinline__ CfRec cf_prepare(int4 e, int world, int H)
     const int sxH = dx > 0 ? H : -H, sy = dy > 0 ? 1 : -1;                            // sx = +1 iff x0 < x1 (rrt.py:207-215)
     CfRec r;
     r.a = make_int4(e.x * H + e.y, xmajor ? sxH : sy, xmajor ? sy : sxH, major);
-    r.b = make_int4(minor, __float_as_int(inv), world, 0);
+    const int oct = (xmajor ? 4 : 0) | (dx > 0 ? 2 : 0) | (dy > 0 ? 1 : 0);      // which field of the world: nf = 1 (isotropic) or 8 (one per octant)
+    r.b = make_int4(minor, __float_as_int(inv), world * nf + (oct & (nf - 1)), 0);
     return r;
 }
 
@@ -134,7 +211,7 @@ constexpr int kCfThreads = 128;
 
 template <int kCfPerWarp>
 __global__ void __launch_bounds__(kCfThreads, RRTK_CF_MINB) collision_cf_kernel(const uint8_t *__restrict__ clear, size_t cells_per, int W, int H,
-                                                                  const int4 *__restrict__ segs, const int *__restrict__ world,
+                                                                  const int4 *__restrict__ segs, const int *__restrict__ world, int nf,
                                                                   int64_t nseg, uint8_t *__restrict__ free_out, int *__restrict__ cells_out)
 {
     __shared__ int4 s_a[kCfThreads / 32][kCfPerWarp];
@@ -147,7 +224,7 @@ __global__ void __launch_bounds__(kCfThreads, RRTK_CF_MINB) collision_cf_kernel(
     const int cnt = (int)min((int64_t)kCfPerWarp, nseg - first);
     int4 *ra = s_a[wib], *rb = s_b[wib];
     for (int i = lane; i < cnt; i += 32) {                                           // coalesced: 512 bytes per step
-        const CfRec r = cf_prepare(__ldg(segs + first + i), world ? __ldg(world + first + i) : 0, H);
+        const CfRec r = cf_prepare(__ldg(segs + first + i), world ? __ldg(world + first + i) : 0, H, nf);
         ra[i] = r.a; rb[i] = r.b;
     }
     __syncwarp();
@@ -204,16 +281,16 @@ __global__ void __launch_bounds__(kCfThreads, RRTK_CF_MINB) collision_cf_kernel(
 }
 
 template <int kPool>
-static void cf_launch_pool(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int64_t nseg,
+static void cf_launch_pool(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int nf, int64_t nseg,
                            uint8_t *d_free, int32_t *d_cells, cudaStream_t st)
 {
     const int64_t warps = (nseg + kPool - 1) / kPool;
     const int64_t blocks = (warps * 32 + kCfThreads - 1) / kCfThreads;
     collision_cf_kernel<kPool><<<(unsigned)blocks, kCfThreads, 0, st>>>(d_clear, (size_t)W * H, W, H, reinterpret_cast<const int4 *>(d_segs),
-                                                                      d_world, nseg, d_free, d_cells);
+                                                                      d_world, nf, nseg, d_free, d_cells);
 }
 
-int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int64_t nseg,
+int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_segs, const int32_t *d_world, int nf, int64_t nseg,
                         uint8_t *d_free, int32_t *d_cells, int sm_count, cudaStream_t st)
 {
     if (nseg == 0) return RRTK_OK;
@@ -222,10 +299,10 @@ int collision_cf_launch(const uint8_t *d_clear, int W, int H, const int32_t *d_s
     int64_t per = nseg / ((int64_t)sm_count * 128) + 1;
     const char *env = getenv("RRTK_CF_POOL");
     if (env && *env) per = atoi(env);
-    if (per > 128) cf_launch_pool<256>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
-    else if (per > 64) cf_launch_pool<128>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
-    else if (per > 32) cf_launch_pool<64>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
-    else cf_launch_pool<32>(d_clear, W, H, d_segs, d_world, nseg, d_free, d_cells, st);
+    if (per > 128) cf_launch_pool<256>(d_clear, W, H, d_segs, d_world, nf, nseg, d_free, d_cells, st);
+    else if (per > 64) cf_launch_pool<128>(d_clear, W, H, d_segs, d_world, nf, nseg, d_free, d_cells, st);
+    else if (per > 32) cf_launch_pool<64>(d_clear, W, H, d_segs, d_world, nf, nseg, d_free, d_cells, st);
+    else cf_launch_pool<32>(d_clear, W, H, d_segs, d_world, nf, nseg, d_free, d_cells, st);
     RRTK_CUDA(cudaGetLastError());
     return RRTK_OK;
 }

@@ -31,6 +31,12 @@ def test_cfg2_one_million_segments_against_the_oracle():
     free2, cells2 = torch.empty_like(free), torch.empty_like(cells)
     _lib.check(db.L.rrtk_collision_segments_cf(clear.data_ptr(), S, S, d_segs.data_ptr(), None, nseg, free2.data_ptr(), cells2.data_ptr(), st))
     assert torch.equal(free, free2) and torch.equal(cells, cells2)
+    # and so does the walk on the eight directional fields (32 MB)
+    clear8 = torch.empty((8, S, S), dtype=torch.uint8, device="cuda")
+    _lib.check(db.L.rrtk_clearance_field_dir(db.bits.data_ptr(), 1, S, S, 255, clear8.data_ptr(), st))
+    free2.zero_(); cells2.zero_()
+    _lib.check(db.L.rrtk_collision_segments_cfd(clear8.data_ptr(), S, S, d_segs.data_ptr(), None, nseg, free2.data_ptr(), cells2.data_ptr(), st))
+    assert torch.equal(free, free2) and torch.equal(cells, cells2)
     # reversing a free segment keeps it free only if the reversed walk is free too: verdicts of both directions vs the oracle
     rev = np.ascontiguousarray(segs[: 1 << 17][:, [2, 3, 0, 1]])
     d_rev = torch.from_numpy(rev).cuda()
