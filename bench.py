@@ -49,8 +49,9 @@ R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
 NCU_DRAM_BYTES_PER_PLAN = (71402240.0 + 33531136.0) / 1036          # re-captured whenever the plan kernel changes
 NCU_DRAM_SOURCE = "profiles/r2_v3_plan_ncu.txt: 71.40 MB read + 33.53 MB written for 1036 plans"
-NCU_CFD_DRAM_BYTES = None                                          # filled from the ncu capture of the directional walk
-NCU_CFD_DRAM_SOURCE = "not captured yet"
+NCU_CFD_DRAM_BYTES = 45535232.0 + 440064.0
+NCU_CFD_DRAM_SOURCE = ("profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                       "launch (profiles/r2_v4_cfd_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 29.5 MB of the 32 MB of fields, once")
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
 
 
@@ -258,6 +259,43 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
                          "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
                          "this launch (profiles/r2_v3_cc_ncu.txt): 16 MB of segment records + the 512 KB grid, once"),
     }
+    # K1 with the grid staged in shared memory (grids up to ~110 KB of bits: the planner-sized worlds), 512x512 here
+    S2 = 512
+    db2 = batch.DeviceBatch("standard", S2, S2, 8, device=local).gen_worlds([worlds.world_seed(0)])
+    segs2_h = np.random.default_rng(1).integers(0, S2, size=(CC_NSEG, 4)).astype(np.int32)
+    segs2 = torch.from_numpy(segs2_h).to(dev)
+    free_s, cells_s = torch.empty_like(free), torch.empty_like(cells)
+
+    def launch_shared():
+        _lib.check(L.rrtk_collision_segments(db2.bits.data_ptr(), S2, S2, segs2.data_ptr(), None, CC_NSEG, free_s.data_ptr(),
+                                             cells_s.data_ptr(), stream.cuda_stream), "collision_segments")
+
+    for _ in range(max(3, warmup)):
+        launch_shared()
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(reps):
+        launch_shared()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms_s = e0.elapsed_time(e1) / reps
+    ncells_s = int(cells_s.sum(dtype=torch.int64).item())
+    smem_peak = float(peaks["smem_read_GBps"])
+    shared_grid = {
+        "kernel": "rrtk::collision_shared_kernel (warp per segment, the 32 KB bit grid of one 512x512 world staged in shared memory by one "
+                  "cp.async.bulk per block)",
+        "workload": "%d random segments on one %dx%d world" % (CC_NSEG, S2, S2),
+        "segments_per_s": CC_NSEG / (ms_s / 1e3), "cells_per_s": ncells_s / (ms_s / 1e3), "ms_per_launch": ms_s, "gpu_launches": reps,
+        "mean_cells_per_segment": ncells_s / CC_NSEG,
+        "roofline": {"kernel": "rrtk::collision_shared_kernel", "bound": "smem", "achieved": 4.0 * ncells_s / (ms_s / 1e3) / 1e9, "peak": smem_peak,
+                     "unit": "GB/s", "frac": 4.0 * ncells_s / (ms_s / 1e3) / 1e9 / smem_peak, "traffic": None,
+                     "bytes_model": "4 B (one grid word) x cells the reference's walk tests", "peak_source": "measured in this run: rrtk_peak_smem_read"},
+    }
+    if cpu:
+        from oracle import c_oracle                            # checker only
+        m2 = 1 << 16
+        wf2, wc2 = c_oracle.collision_batch(db2.og[0].cpu().numpy(), segs2_h[:m2])
+        shared_grid["matches_oracle"] = bool(np.array_equal(free_s[:m2].cpu().numpy().astype(bool), wf2) and np.array_equal(cells_s[:m2].cpu().numpy(), wc2))
     # K1b: same outputs from the clearance field (built once per grid, outside the timed region like the packing)
     cap = 128
     clear = torch.empty((CC_SIZE, CC_SIZE), dtype=torch.uint8, device=dev)
@@ -329,6 +367,7 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
                 "scattered L1 reads (~1.08 cycles per lane-load per SM, scripts/micro/scatter.cu) and the slowest lane of each warp",
         "isotropic_field_kernel": iso_field,
         "bit_grid_kernel": bit_grid,
+        "shared_grid_kernel": shared_grid,
     }
     if cpu:
         from oracle import c_oracle                            # checker + CPU baseline only
@@ -567,11 +606,35 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
             r_host = ctx.plan2(db.cfg, desc_h, N_ITER, states=batch.seed_states(ids), heads=heads_h, out=out_pin)
             dt = time.perf_counter() - t0
             t_best = dt if t_best is None else min(t_best, dt)
+        # the pipelined form: packed grids, descriptors, PCG64 states and headings up; path records + statistics down
+        cap = PATH_CAP
+        bits_pin = torch.empty(tuple(db.bits.shape), dtype=db.bits.dtype, pin_memory=True)
+        bits_pin.copy_(db.bits)
+        torch.cuda.synchronize(dev)
+        bits_host = bits_pin.numpy().view(np.uint32).reshape(plans, -1)
+        out2 = {k: torch.empty(shape, dtype=dt, pin_memory=True).numpy() for k, shape, dt in (
+            ("stats", (plans, _lib.STAT_COUNT), torch.int64), ("path", (plans, cap), torch.int32), ("xy", (plans, cap, 2), torch.int16),
+            ("path_head", (plans, cap), torch.uint8), ("len", (plans,), torch.int32), ("path_cost", (plans,), torch.float64))}
+        states_h = batch.seed_states(ids)
+        t_pipe = None
+        for rep in range(3):
+            t0 = time.perf_counter()
+            r2 = ctx.plan2_worlds(db.cfg, bits_host, W, H, desc_h, N_ITER, states=states_h, heads=heads_h, bits=True, trees=False, paths=True,
+                                  path_cap=cap, out=out2)
+            dt = time.perf_counter() - t0
+            t_pipe = dt if t_pipe is None or rep == 1 else min(t_pipe, dt)        # the first call allocates the pipeline's buffers
         ctx.close()
-        rec["e2e"] = {"value": plans / t_best, "unit": "plans/s", "api": "rrtk_ctx_set_grids + rrtk_ctx_plan2 (seed mode), pinned host buffers, not pipelined",
-                      "h2d_bytes_per_step": int(plans * (W * H + 64 + 32 + (N_ITER if model == "dubins" else 0))),
-                      "d2h_bytes_per_step": int(plans * ((N_ITER + 1) * 25 + _lib.STAT_COUNT * 8)),
-                      "matches_device_arm": bool(np.array_equal(r_host[4], db.out["parent"].cpu().numpy()))}
+        st_dev = db.out["stats"].cpu().numpy()
+        rec["e2e"] = {"value": plans / t_pipe, "unit": "plans/s",
+                      "api": "rrtk_ctx_plan2_worlds (packed grids in, seed mode, path records out; chunks of one plan per SM on 8 pipeline slots), pinned host buffers",
+                      "h2d_bytes_per_step": int(plans * (bits_host.shape[1] * 4 + 64 + 32 + (N_ITER if model == "dubins" else 0))),
+                      "d2h_bytes_per_step": int(plans * (cap * 9 + 12 + _lib.STAT_COUNT * 8)),
+                      "matches_device_arm": bool(np.array_equal(r2["stats"][:, :3], st_dev[:, :3])),
+                      "trees_mode": {"value": plans / t_best, "unit": "plans/s",
+                                     "api": "rrtk_ctx_set_grids + rrtk_ctx_plan2 (uint8 grids up, every tree down), not pipelined",
+                                     "h2d_bytes_per_step": int(plans * (W * H + 64 + 32 + (N_ITER if model == "dubins" else 0))),
+                                     "d2h_bytes_per_step": int(plans * ((N_ITER + 1) * 25 + _lib.STAT_COUNT * 8)),
+                                     "matches_device_arm": bool(np.array_equal(r_host[4], db.out["parent"].cpu().numpy()))}}
         out["dubins_rrtstar" if model == "dubins" else "euclid_rrtstar_with_rewire"] = rec
         keep[model] = (db, starts, goals, hs)
     if cpu and world == 1:

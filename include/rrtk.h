@@ -260,6 +260,10 @@ int rrtk_extract_paths_xy(const int32_t *d_parent, const int16_t *d_pts, const d
  *   loop         rrt.py:498-548 with nearest / within Euclidean on (x, y); rewire != 0 adds, for every member vn
  *                of the radius set in ascending order with  cost[vnew] + len(vnew -> vn) < cost[vn]  and a free
  *                edge: parent[vn] = vnew and the costs of vn's subtree recomputed from the edge lengths
+ *   informed     (cfg.informed, RRTStarInformed.plan rrt.py:690-748 with a rewire that fires): once a vertex within
+ *                r_goal of the goal exists, the (x, y) of iteration i is the ellipse point (rrt.py:589-625, rotation in
+ *                rrtk_plan_desc.rot) for c = cost of the cheapest solution vertex (first one on ties, rrt.py:627-633;
+ *                costs as lowered by every rewire so far) + its distance to the goal, and unit-disc draw balls[i]
  */
 typedef enum { RRTK_MODEL_EUCLID = 0, RRTK_MODEL_DUBINS = 1 } rrtk_model;
 
@@ -274,7 +278,13 @@ typedef struct {
     const void *dubins_table; /* DUBINS, optional (NULL = none): DEVICE memo made by rrtk_dubins_table_build for the same
                                 nheadings and rho; edges whose |dx|, |dy| <= table_radius are looked up instead of evaluated */
     int32_t table_radius;
-    int32_t reserved;
+    int32_t informed;        /* 1: the informed sampling rule of rrt.py:690-701,744-745 on top of the loop (below) */
+    double r_goal;           /* informed: accepted vertices closer than this to the goal (Euclidean, strict) are solution vertices */
+    const double *balls;     /* informed: nplans x n x (x, y) unit-disc draws (rrt.py:579-587), row i used by iteration i; NULL = probe
+                                run that stops at the first solution vertex.  DEVICE memory for rrtk_plan2_batch, HOST memory for
+                                rrtk_ctx_plan2 / rrtk_ctx_plan2_worlds (the call uploads it) */
+    double *ell_c;           /* informed, optional output: nplans x (n + 1), entry j = the budget c of the last ellipse sample drawn
+                                while the tree had j vertices (rrt.py:701), NaN elsewhere.  DEVICE / HOST as for balls */
 } rrtk_plan2_cfg;
 
 /* statistics slots rrtk_plan2_batch writes (RRTK_STAT_COUNT int64 per plan; J / VGOAL / FOUND / CHECKS as above) */
@@ -284,7 +294,9 @@ enum {
     RRTK_STAT2_PROPAGATED,     /* descendant costs recomputed after rewires */
     RRTK_STAT2_RING_MEMBERS,   /* sum over accepted iterations of |within(r_rewire)| */
     RRTK_STAT2_LEN_EVALS,      /* edge lengths evaluated on the device (parallel form) */
-    RRTK_STAT2_OVERFLOW        /* 1: a radius set exceeded the kernel's 1024-entry list; the plan is INVALID */
+    RRTK_STAT2_OVERFLOW,       /* 1: a radius set exceeded the kernel's 1024-entry list; the plan is INVALID */
+    RRTK_STAT2_ELL_ITERS,      /* informed: iterations whose sample came from the ellipse */
+    RRTK_STAT2_FIRST_SOL       /* informed: iteration that accepted the first solution vertex, -1 = none */
 };
 
 /* bytes of device scratch rrtk_plan2_batch needs for nplans plans of n iterations */
@@ -410,6 +422,17 @@ int rrtk_ctx_near_order_f64(rrtk_ctx *ctx, const double *h_pts, int npts, double
 int rrtk_ctx_plan2(rrtk_ctx *ctx, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc *h_plans, int nplans, int n,
                    const int16_t *h_samples, const uint64_t *h_state, const uint8_t *h_heads, int16_t *h_pts,
                    uint8_t *h_head, double *h_cost, double *h_elen, int32_t *h_parent, int64_t *h_stats);
+/* rrtk_ctx_plan2 with the worlds in the same call, chunked and pipelined like rrtk_ctx_plan_worlds2 (same flags, same
+ * ordering rule for plans, same meaning of h_grids / h_path / h_xy / h_len / h_path_cost; set_og + plan of
+ * rrt.py:261-272,498-548 for a batch of K8 plans).  RRTK_OUT_TREES additionally fills h_head and h_elen; h_path_head
+ * (optional, RRTK_OUT_PATHS) receives nplans x path_cap uint8 headings of the path vertices (255 past the end), which a
+ * Dubins path needs beside its points.  chunk_plans <= 0: one plan per SM and chunk. */
+int rrtk_ctx_plan2_worlds(rrtk_ctx *ctx, const rrtk_plan2_cfg *cfg, const void *h_grids, int nworlds, int W, int H,
+                          const rrtk_plan_desc *h_plans, int nplans, int n, const int16_t *h_samples,
+                          const uint64_t *h_state, const uint8_t *h_heads, int flags, int path_cap, int16_t *h_pts,
+                          uint8_t *h_head, double *h_cost, double *h_elen, int32_t *h_parent, int64_t *h_stats,
+                          int32_t *h_path, int16_t *h_xy, uint8_t *h_path_head, int32_t *h_len, double *h_path_cost,
+                          int chunk_plans);
 int rrtk_ctx_dubins_paths(rrtk_ctx *ctx, const int32_t *h_q, int64_t nq, int nheadings, double rho, int32_t *h_word,
                           double *h_tpq, double *h_len);
 int rrtk_ctx_dubins_collision(rrtk_ctx *ctx, int world, const int32_t *h_q, int64_t nq, int nheadings, double rho,

@@ -40,6 +40,14 @@
  *   and cm = cbest + len(xnew -> vn) < cost[vn] and free(xnew -> vn):  parent[vn] = vnew,
  *   elen[vn] = len, cost[vn] = cm, and every descendant d of vn gets cost[d] = cost[parent[d]] + elen[d].
  * Goal connection: ascending (cost[v] + len(v -> goal), v), first free one; none -> vgoal = 0.
+ * Informed sampling (orc2_plan_informed; the sampling rule of rrt.py:690-701,744-745 on top of the loop above):
+ *   a vertex accepted within Euclidean distance r_goal of the goal (strict) joins vsoln.  While vsoln is
+ *   empty iteration i takes sample i.  Otherwise vb = the first minimum of cost over vsoln in the order the
+ *   vertices joined (rrt.py:627-633; costs as they stand NOW, i.e. after every rewire so far),
+ *   c = cost[vb] + |x_vb - x_goal|, and the (x, y) of iteration i is the ellipse point of rrt.py:589-625
+ *   for c and the unit-disc draw balls[i] (rotation given by the caller), clamped to the grid and truncated;
+ *   the heading stays that of sample i.  ell_c[j] = c for the running j (rrt.py:701).  balls == NULL is the
+ *   probe: the plan stops after the iteration that puts the first vertex into vsoln.
  */
 #include <math.h>
 #include <stdint.h>
@@ -49,7 +57,8 @@
 #define MODEL_EUCLID 0
 #define MODEL_DUBINS 1
 
-enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROPAGATED, S2_RING, S2_LEN_EVALS, S2_OVERFLOW, S2_COUNT = 12 };
+enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROPAGATED, S2_RING, S2_LEN_EVALS, S2_OVERFLOW, S2_ELL_ITERS,
+       S2_FIRST_SOL, S2_COUNT = 12 };
 
 /* ---- deterministic elementary functions (part of the specification) ------------------------------ */
 #define DM_PI 3.14159265358979323846
@@ -391,9 +400,29 @@ static int cand2_cmp(const void *a, const void *b)
  * (INT32_MIN unfilled), head int32 (-1 unfilled), cost, elen (length of the edge from the parent;
  * 0 for the root, +inf unfilled), parent.
  */
-int orc2_plan(int model, int star, int rewire, const uint8_t *og, int W, int H, int n, double r_rewire, int NH, double rho,
-              double ds, const int32_t *start, const int32_t *goal, const int32_t *samples, int32_t *pts, int32_t *head,
-              double *cost, double *elen, int32_t *parent, int64_t *stats)
+/* rrt.py:589-599 + 615-625: the informed ellipse point for budget c and unit-disc draw ball (same operation order as
+ * oracle/rrt_oracle.c:ellipse_point and the device's ellipse_sample) */
+static void ellipse_xy(int W, int H, const double rot[4], const int32_t *s, const int32_t *g, double c, const double *ball, int *ox, int *oy)
+{
+    const double cx = (double)(s[0] + g[0]) / 2.0, cy = (double)(s[1] + g[1]) / 2.0;
+    const double r1 = c / 2.0;
+    const int64_t ddx = (int64_t)s[0] - g[0], ddy = (int64_t)s[1] - g[1];
+    const double d2 = (double)(ddx * ddx + ddy * ddy);
+    const double r2 = sqrt(fabs(c * c - d2)) / 2.0;
+    const double m00 = rot[0] * r1, m01 = rot[1] * r2, m10 = rot[2] * r1, m11 = rot[3] * r2;
+    const double x = (m00 * ball[0] + m01 * ball[1]) + cx;
+    const double y = (m10 * ball[0] + m11 * ball[1]) + cy;
+    double lx = (x < (double)(W - 1)) ? x : (double)(W - 1);
+    double ly = (y < (double)(H - 1)) ? y : (double)(H - 1);
+    lx = (lx > 0.0) ? lx : 0.0;
+    ly = (ly > 0.0) ? ly : 0.0;
+    *ox = (int)lx; *oy = (int)ly;
+}
+
+static int plan_core(int model, int star, int rewire, const uint8_t *og, int W, int H, int n, double r_rewire, int NH, double rho,
+                     double ds, const int32_t *start, const int32_t *goal, const int32_t *samples, int32_t *pts, int32_t *head,
+                     double *cost, double *elen, int32_t *parent, int64_t *stats, int informed, double r_goal, const double *rot,
+                     const double *balls, double *ell_c)
 {
     uint8_t *seen = calloc((size_t)W * H, 1);
     int32_t *ring = malloc(sizeof(int32_t) * (size_t)(n + 1));
@@ -401,19 +430,33 @@ int orc2_plan(int model, int star, int rewire, const uint8_t *og, int W, int H, 
     int32_t *next = malloc(sizeof(int32_t) * (size_t)(n + 1));
     int32_t *queue = malloc(sizeof(int32_t) * (size_t)(n + 1));
     cand2_t *cands = malloc(sizeof(cand2_t) * (size_t)(n + 1));
-    if (!seen || !ring || !first || !next || !queue || !cands) return -1;
+    int32_t *vsoln = malloc(sizeof(int32_t) * (size_t)(n + 1));
+    int nsol = 0;
+    if (!seen || !ring || !first || !next || !queue || !cands || !vsoln) return -1;
+    if (informed && ell_c) for (int i = 0; i <= n; ++i) ell_c[i] = NAN;
     for (int i = 0; i <= n; ++i) {
         pts[2 * i] = pts[2 * i + 1] = INT32_MIN; head[i] = -1;
         cost[i] = INFINITY; elen[i] = INFINITY; parent[i] = -1; first[i] = -1; next[i] = -1;
     }
     memset(stats, 0, sizeof(int64_t) * S2_COUNT);
+    stats[S2_FIRST_SOL] = -1;
     world_t w = {model, NH, W, H, rho, ds, og, stats};
     pts[0] = start[0]; pts[1] = start[1]; head[0] = start[2]; cost[0] = 0.0; elen[0] = 0.0;
     int j = 1;
     const double rr = r_rewire * r_rewire;
 
     for (int i = 0; i < n; ++i) {
-        const int x = samples[3 * i], y = samples[3 * i + 1], h = samples[3 * i + 2];
+        int x = samples[3 * i], y = samples[3 * i + 1];
+        const int h = samples[3 * i + 2];
+        if (informed && nsol > 0) {
+            if (!balls) break;                                       /* probe */
+            int vb = vsoln[0];
+            for (int k = 1; k < nsol; ++k) if (cost[vsoln[k]] < cost[vb]) vb = vsoln[k];
+            const double c = cost[vb] + euclid(pts, vb, goal[0], goal[1]);
+            ellipse_xy(W, H, rot, start, goal, c, balls + 2 * i, &x, &y);
+            if (ell_c) ell_c[j] = c;
+            stats[S2_ELL_ITERS]++;
+        }
         int vnear = 0;
         int64_t bd = INT64_MAX;
         for (int v = 0; v < j; ++v) {
@@ -476,6 +519,10 @@ int orc2_plan(int model, int star, int rewire, const uint8_t *og, int W, int H, 
             }
         }
         stats[S2_ACCEPTED]++;
+        if (informed && euclid(pts, j, goal[0], goal[1]) < r_goal) {
+            vsoln[nsol++] = j;
+            if (nsol == 1) stats[S2_FIRST_SOL] = i;
+        }
         ++j;
     }
 
@@ -497,6 +544,25 @@ int orc2_plan(int model, int star, int rewire, const uint8_t *og, int W, int H, 
         }
     }
     stats[S2_J] = j; stats[S2_VGOAL] = vgoal; stats[S2_FOUND] = found;
-    free(seen); free(ring); free(first); free(next); free(queue); free(cands);
+    free(seen); free(ring); free(first); free(next); free(queue); free(cands); free(vsoln);
     return 0;
+}
+
+int orc2_plan(int model, int star, int rewire, const uint8_t *og, int W, int H, int n, double r_rewire, int NH, double rho,
+              double ds, const int32_t *start, const int32_t *goal, const int32_t *samples, int32_t *pts, int32_t *head,
+              double *cost, double *elen, int32_t *parent, int64_t *stats)
+{
+    return plan_core(model, star, rewire, og, W, H, n, r_rewire, NH, rho, ds, start, goal, samples, pts, head, cost, elen, parent, stats,
+                     0, 0.0, NULL, NULL, NULL);
+}
+
+/* the same loop with the informed sampling rule; rot: 2 x 2 row-major rotation (rrt.py:601-613, computed by the caller),
+ * balls: n x 2 unit-disc draws or NULL (probe), ell_c: n + 1 doubles (NaN where no ellipse sample was drawn) or NULL */
+int orc2_plan_informed(int model, int star, int rewire, const uint8_t *og, int W, int H, int n, double r_rewire, int NH, double rho,
+                       double ds, const int32_t *start, const int32_t *goal, const int32_t *samples, int32_t *pts, int32_t *head,
+                       double *cost, double *elen, int32_t *parent, int64_t *stats, double r_goal, const double *rot,
+                       const double *balls, double *ell_c)
+{
+    return plan_core(model, star, rewire, og, W, H, n, r_rewire, NH, rho, ds, start, goal, samples, pts, head, cost, elen, parent, stats,
+                     1, r_goal, rot, balls, ell_c);
 }

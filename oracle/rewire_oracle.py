@@ -18,7 +18,7 @@ _OUT = os.path.join(_HERE, "_build", "liboracle2.so")
 
 MODELS = {"euclid": 0, "dubins": 1}
 ST_NAMES = ("j", "vgoal", "found", "checks", "accepted", "rewires", "propagated", "ring_members", "len_evals", "overflow",
-            "reserved0", "reserved1")
+            "ell_iters", "first_solution_iter")
 WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
 _lib = None
 
@@ -48,6 +48,8 @@ def lib():
         L.orc2_math.argtypes = [vp, vp, lg, vp, vp, vp]
         L.orc2_plan.restype = i
         L.orc2_plan.argtypes = [i, i, i, vp, i, i, i, d, i, d, d] + [vp] * 9
+        L.orc2_plan_informed.restype = i
+        L.orc2_plan_informed.argtypes = [i, i, i, vp, i, i, i, d, i, d, d] + [vp] * 9 + [d, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -104,9 +106,10 @@ def dubins_points(q, nh, rho, s):
     return out
 
 
-def plan(model, og, n, start, goal, samples, star=True, rewire=True, r_rewire=0.0, nh=16, rho=1.0, ds=1.0):
+def plan(model, og, n, start, goal, samples, star=True, rewire=True, r_rewire=0.0, nh=16, rho=1.0, ds=1.0, informed=None):
     """start / goal: (x, y, h); samples: (n, 3) (x, y, h) (h ignored by the Euclidean model).
-    Returns dict(pts (n+1,2) int32, head, cost, elen, parent, stats dict)."""
+    ``informed``: None, or dict(r_goal, rot (2, 2), balls (n, 2) or None for the probe) -- the informed sampling rule.
+    Returns dict(pts (n+1,2) int32, head, cost, elen, parent, stats dict[, ell (n+1)])."""
     g = _u8(og)
     s = np.ascontiguousarray(samples, dtype=np.int32)
     assert s.shape == (n, 3), s.shape
@@ -117,9 +120,19 @@ def plan(model, og, n, start, goal, samples, star=True, rewire=True, r_rewire=0.
     cost, elen = np.empty(n + 1), np.empty(n + 1)
     par = np.empty(n + 1, dtype=np.int32)
     stats = np.zeros(len(ST_NAMES), dtype=np.int64)
-    rc = lib().orc2_plan(MODELS[model], int(bool(star)), int(bool(rewire)), _p(g), g.shape[0], g.shape[1], n, float(r_rewire),
-                         int(nh), float(rho), float(ds), _p(st), _p(gl), _p(s), _p(pts), _p(head), _p(cost), _p(elen), _p(par),
-                         _p(stats))
+    args = (MODELS[model], int(bool(star)), int(bool(rewire)), _p(g), g.shape[0], g.shape[1], n, float(r_rewire),
+            int(nh), float(rho), float(ds), _p(st), _p(gl), _p(s), _p(pts), _p(head), _p(cost), _p(elen), _p(par), _p(stats))
+    ell = None
+    if informed is None:
+        rc = lib().orc2_plan(*args)
+    else:
+        rot = np.ascontiguousarray(informed["rot"], dtype=np.float64).reshape(4)
+        balls = None if informed.get("balls") is None else np.ascontiguousarray(informed["balls"], dtype=np.float64).reshape(n, 2)
+        ell = np.empty(n + 1)
+        rc = lib().orc2_plan_informed(*args, float(informed["r_goal"]), _p(rot), _p(balls), _p(ell))
     if rc:
         raise MemoryError("orc2_plan")
-    return dict(pts=pts, head=head, cost=cost, elen=elen, parent=par, stats=dict(zip(ST_NAMES, (int(v) for v in stats))))
+    out = dict(pts=pts, head=head, cost=cost, elen=elen, parent=par, stats=dict(zip(ST_NAMES, (int(v) for v in stats))))
+    if ell is not None:
+        out["ell"] = ell
+    return out

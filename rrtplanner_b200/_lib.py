@@ -20,18 +20,22 @@ STAT_COUNT = len(STAT_NAMES)
 
 MODEL_EUCLID, MODEL_DUBINS = 0, 1
 STAT2_NAMES = ("j", "vgoal", "found", "checks", "accepted", "rewires", "propagated", "ring_members", "len_evals", "overflow",
-               "reserved0", "reserved1")
+               "ell_iters", "first_solution_iter")
 DUBINS_WORDS = ("LSL", "RSR", "LSR", "RSL", "RLR", "LRL")
-# numpy mirror of rrtk_plan2_cfg (56 bytes)
+# numpy mirror of rrtk_plan2_cfg (80 bytes)
 PLAN2_CFG = np.dtype([("model", "<i4"), ("star", "<i4"), ("rewire", "<i4"), ("nheadings", "<i4"), ("r_rewire", "<f8"),
-                      ("rho", "<f8"), ("ds", "<f8"), ("dubins_table", "<u8"), ("table_radius", "<i4"), ("reserved", "<i4")], align=True)
-assert PLAN2_CFG.itemsize == 56
+                      ("rho", "<f8"), ("ds", "<f8"), ("dubins_table", "<u8"), ("table_radius", "<i4"), ("informed", "<i4"),
+                      ("r_goal", "<f8"), ("balls", "<u8"), ("ell_c", "<u8")], align=True)
+assert PLAN2_CFG.itemsize == 80
 
 
-def plan2_cfg(model, star, rewire, r_rewire=0.0, nheadings=1, rho=1.0, ds=1.0) -> np.ndarray:
+def plan2_cfg(model, star, rewire, r_rewire=0.0, nheadings=1, rho=1.0, ds=1.0, informed=False, r_goal=0.0) -> np.ndarray:
+    """``informed``: the informed sampling rule; the ``balls`` / ``ell_c`` pointers are filled in by the caller that owns the
+    arrays (Context.plan2 / plan2_worlds: host arrays; DeviceBatch2: device tensors)."""
     c = np.zeros(1, dtype=PLAN2_CFG)
     c["model"], c["star"], c["rewire"], c["nheadings"] = int(model), int(bool(star)), int(bool(rewire)), int(nheadings)
     c["r_rewire"], c["rho"], c["ds"] = float(r_rewire), float(rho), float(ds)
+    c["informed"], c["r_goal"] = int(bool(informed)), float(r_goal)
     return c
 
 
@@ -108,6 +112,7 @@ SIGNATURES = {
     "rrtk_dubins_collision": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _d, _d, _vp, _vp]),
     "rrtk_dubins_sample": (_i, [_vp, _i64, _i, _d, _d, _i, _vp, _vp, _vp]),
     "rrtk_ctx_plan2": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rrtk_ctx_plan2_worlds": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i] + [_vp] * 11 + [_i]),
     "rrtk_ctx_dubins_paths": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _vp]),
     "rrtk_ctx_dubins_collision": (_i, [_vp, _i, _vp, _i64, _i, _d, _d, _vp]),
     "rrtk_ctx_dubins_sample": (_i, [_vp, _vp, _i64, _i, _d, _d, _i, _vp, _vp]),
@@ -310,12 +315,21 @@ class Context:
         return out
 
     # -- K8: rewire / Dubins planners, Dubins primitive ---------------------------------------
-    def plan2(self, cfg, desc, n, samples=None, states=None, heads=None, out=None):
+    def plan2(self, cfg, desc, n, samples=None, states=None, heads=None, out=None, balls=None):
         """rrtk_ctx_plan2: returns (pts, head, cost, elen, parent, stats); desc["reserved"][:, :2] = start / goal heading.
-        ``out``: optional preallocated host arrays in that order (e.g. pinned)."""
+        ``out``: optional preallocated host arrays in that order (e.g. pinned).  With ``cfg["informed"]`` set, ``balls`` is the
+        (nplans, n, 2) array of unit-disc draws (None = probe run) and a seventh array, the (nplans, n + 1) ellipse budgets, is
+        appended to the result."""
         nplans = desc.shape[0]
         desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
-        cfg = np.ascontiguousarray(cfg, dtype=PLAN2_CFG)
+        cfg = np.ascontiguousarray(cfg, dtype=PLAN2_CFG).copy()
+        ell = None
+        if int(cfg["informed"][0]):
+            if balls is not None:
+                balls = np.ascontiguousarray(balls, dtype=np.float64)
+                assert balls.shape == (nplans, n, 2), balls.shape
+            ell = np.empty((nplans, n + 1), dtype=np.float64)
+            cfg["balls"], cfg["ell_c"] = (0 if balls is None else balls.ctypes.data), ell.ctypes.data
         if out is not None:
             pts, head, cost, elen, parent, stats = out
             assert pts.shape == (nplans, n + 1, 2) and pts.dtype == np.int16 and head.dtype == np.uint8
@@ -338,7 +352,48 @@ class Context:
             assert heads.shape == (nplans, n), heads.shape
         check(lib().rrtk_ctx_plan2(self._h, ptr(cfg), ptr(desc), nplans, n, ptr(samples), ptr(states), ptr(heads), ptr(pts), ptr(head),
                                    ptr(cost), ptr(elen), ptr(parent), ptr(stats)), "rrtk_ctx_plan2")
+        if ell is not None:
+            return pts, head, cost, elen, parent, stats, ell
         return pts, head, cost, elen, parent, stats
+
+    def plan2_worlds(self, cfg, grids, W, H, desc, n, samples=None, states=None, heads=None, bits=False, trees=False, paths=True,
+                     path_cap=256, out=None, chunk=0, balls=None):
+        """rrtk_ctx_plan2_worlds: K8 plans with their worlds in one pipelined call.  ``grids`` as for plan_worlds2.  Returns a
+        dict with ``stats`` and, as requested, the trees (``pts``, ``head``, ``cost``, ``elen``, ``parent``) and / or the path
+        records (``path``, ``xy``, ``path_head``, ``len``, ``path_cost``); informed plans (``cfg["informed"]``, ``balls`` as for
+        plan2) also return ``ell``."""
+        grids = np.ascontiguousarray(grids, dtype=np.uint32 if bits else np.uint8)
+        nw = grids.shape[0]
+        nplans = desc.shape[0]
+        desc = np.ascontiguousarray(desc, dtype=PLAN_DESC)
+        cfg = np.ascontiguousarray(cfg, dtype=PLAN2_CFG).copy()
+        out = dict(out or {})
+        def buf(name, shape, dtype):
+            if name not in out:
+                out[name] = np.empty(shape, dtype=dtype)
+            return out[name]
+        buf("stats", (nplans, STAT_COUNT), np.int64)
+        if int(cfg["informed"][0]):
+            if balls is not None:
+                balls = np.ascontiguousarray(balls, dtype=np.float64)
+                assert balls.shape == (nplans, n, 2), balls.shape
+            cfg["balls"], cfg["ell_c"] = (0 if balls is None else balls.ctypes.data), buf("ell", (nplans, n + 1), np.float64).ctypes.data
+        flags = (1 if bits else 0) | (2 if trees else 0) | (4 if paths else 0)
+        if trees:
+            buf("pts", (nplans, n + 1, 2), np.int16); buf("head", (nplans, n + 1), np.uint8); buf("cost", (nplans, n + 1), np.float64)
+            buf("elen", (nplans, n + 1), np.float64); buf("parent", (nplans, n + 1), np.int32)
+        if paths:
+            buf("path", (nplans, path_cap), np.int32); buf("xy", (nplans, path_cap, 2), np.int16); buf("path_head", (nplans, path_cap), np.uint8)
+            buf("len", (nplans,), np.int32); buf("path_cost", (nplans,), np.float64)
+        samples = None if samples is None else np.ascontiguousarray(samples, dtype=np.int16)
+        states = None if states is None else np.ascontiguousarray(states, dtype=np.uint64)
+        heads = None if heads is None else np.ascontiguousarray(heads, dtype=np.uint8)
+        g = out.get
+        check(lib().rrtk_ctx_plan2_worlds(self._h, ptr(cfg), ptr(grids), nw, W, H, ptr(desc), nplans, n, ptr(samples), ptr(states), ptr(heads),
+                                          flags, int(path_cap), ptr(g("pts")), ptr(g("head")), ptr(g("cost")), ptr(g("elen")), ptr(g("parent")),
+                                          ptr(out["stats"]), ptr(g("path")), ptr(g("xy")), ptr(g("path_head")), ptr(g("len")), ptr(g("path_cost")),
+                                          int(chunk)), "rrtk_ctx_plan2_worlds")
+        return out
 
     def dubins_paths(self, q, nheadings, rho):
         """q: (nq, 6) (x0, y0, h0, x1, y1, h1) -> (word, tpq, length)."""

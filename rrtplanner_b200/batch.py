@@ -386,10 +386,12 @@ class DeviceBatch2(DeviceBatch):
     """HBM-resident batch of K8 plans (RRT* with a firing rewire, Dubins RRT / RRT*; include/rrtk.h rrtk_plan2_batch)."""
 
     def __init__(self, model, W: int, H: int, n: int, r_rewire=0.0, star=True, rewire=True, nheadings=16, rho=6.0, ds=1.0,
-                 device=None, threads: int = 0, use_table: bool = True):
+                 device=None, threads: int = 0, use_table: bool = True, informed: bool = False, r_goal: float = 0.0):
         super().__init__("star" if star else "standard", W, H, n, r_rewire=r_rewire, device=device, threads=threads)
         m = {"euclid": _lib.MODEL_EUCLID, "dubins": _lib.MODEL_DUBINS}[model] if isinstance(model, str) else int(model)
-        self.cfg = _lib.plan2_cfg(m, star, rewire, r_rewire, nheadings if m == _lib.MODEL_DUBINS else 1, rho, ds)
+        self.cfg = _lib.plan2_cfg(m, star, rewire, r_rewire, nheadings if m == _lib.MODEL_DUBINS else 1, rho, ds, informed, r_goal)
+        self.informed = bool(informed)
+        self.balls2 = None
         self.nheadings = int(self.cfg["nheadings"][0])
         self.heads = None
         self.scratch = None
@@ -415,6 +417,19 @@ class DeviceBatch2(DeviceBatch):
                         cost=self._empty((P, n + 1), t.float64), elen=self._empty((P, n + 1), t.float64),
                         parent=self._empty((P, n + 1), t.int32), stats=self._empty((P, _lib.STAT_COUNT), t.int64))
         self.scratch = self._empty((int(self.L.rrtk_plan2_scratch_bytes(P, n)),), t.uint8)
+        if self.informed:
+            self.out["ell"] = self._empty((P, n + 1), t.float64)
+            self.cfg["ell_c"] = self.out["ell"].data_ptr()
+            self.cfg["balls"] = 0                          # probe until set_balls_host
+        return self
+
+    def set_balls_host(self, balls: np.ndarray):
+        """Informed plans: (nplans, n, 2) unit-disc draws, row i used by iteration i (rrt.py:579-587); the descriptors carry the
+        rotation (make_desc(..., rots=...)).  Without this call an informed batch runs as the probe (stops at the first solution)."""
+        b = np.ascontiguousarray(balls, dtype=np.float64)
+        assert self.informed and b.shape == (self.nplans, self.n, 2), b.shape
+        self.balls2 = self.torch.from_numpy(b).to(self.dev)
+        self.cfg["balls"] = self.balls2.data_ptr()
         return self
 
     def set_heads_host(self, heads: np.ndarray):

@@ -49,6 +49,7 @@ int plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, in
                 const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int plan_footprint(int, int, int, int, int, int, int, int *, int *);
 int paths_launch(const int32_t *, const int64_t *, int, int, int, int32_t *, int32_t *, cudaStream_t);
+int path_heads_launch(const int32_t *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
 int paths_xy_launch(const int32_t *, const int16_t *, const double *, const int64_t *, int, int, int, int32_t *, int16_t *, int32_t *,
                     double *, cudaStream_t);
 int plan2_launch(const rrtk_plan2_cfg &, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, const int16_t *, const uint8_t *,
@@ -130,6 +131,7 @@ struct PipeSlot {
     cudaEvent_t ready = nullptr, done = nullptr;
     DevBuf og, bits, rowcum, plans, samples, state, balls, pts, cost, parent, stats, ell;
     DevBuf path, xy, len, pcost;                // path records (RRTK_OUT_PATHS)
+    DevBuf heads, head_out, elen, scratch2, phead;   // K8 chunks (rrtk_ctx_plan2_worlds)
     std::vector<rrtk_plan_desc> desc;
 };
 constexpr int kPipeSlots = 8;
@@ -962,6 +964,7 @@ static int check_plan2_cfg(const rrtk_plan2_cfg *cfg)
     RRTK_REQUIRE(cfg, "rrtk_plan2: null configuration");
     RRTK_REQUIRE(cfg->model == RRTK_MODEL_EUCLID || cfg->model == RRTK_MODEL_DUBINS, "rrtk_plan2: unknown model");
     RRTK_REQUIRE(cfg->r_rewire == cfg->r_rewire, "rrtk_plan2: NaN radius");
+    RRTK_REQUIRE(!cfg->informed || cfg->r_goal == cfg->r_goal, "rrtk_plan2: NaN goal radius");
     RRTK_REQUIRE(!cfg->dubins_table || (cfg->table_radius >= 1 && cfg->table_radius <= 1024), "rrtk_plan2: table_radius out of range");
     if (cfg->model == RRTK_MODEL_DUBINS) {
         RRTK_REQUIRE(cfg->nheadings >= 1 && cfg->nheadings <= 255, "rrtk_plan2: need 1 <= nheadings <= 255");
@@ -1049,6 +1052,25 @@ int rrtk_dubins_sample(const int32_t *d_q, int64_t nq, int nheadings, double rho
     return dubins_walk_launch(nullptr, 1, 1, d_q, nullptr, nq, nheadings, rho, ds, nullptr, cap, d_xyth, d_count, (cudaStream_t)stream);
 }
 
+// memo of the Dubins primitive over the rewire radius, kept in the context while (radius, headings, rho) stay the same
+static int ctx_dubins_memo(rrtk_ctx *c, rrtk_plan2_cfg *use, cudaStream_t st)
+{
+    if (!(use->model == RRTK_MODEL_DUBINS && use->star && !use->dubins_table && use->r_rewire >= 1.0 && use->r_rewire <= 1024.0)) return RRTK_OK;
+    const int R = (int)ceil(use->r_rewire);
+    const size_t bytes = dubins_table_bytes(R, use->nheadings);
+    if (bytes > ((size_t)256 << 20)) return RRTK_OK;
+    if (c->dt_R != R || c->dt_NH != use->nheadings || c->dt_rho != use->rho || !c->dtable.p) {
+        RRTK_CUDA(cudaStreamSynchronize(st));
+        RRTK_TRY(c->dtable.reserve(bytes));
+        RRTK_TRY(rrtk_dubins_table_build(R, use->nheadings, use->rho, c->dtable.p, st));
+        RRTK_CUDA(cudaStreamSynchronize(st));
+        c->dt_R = R; c->dt_NH = use->nheadings; c->dt_rho = use->rho;
+    }
+    use->dubins_table = c->dtable.p;
+    use->table_radius = R;
+    return RRTK_OK;
+}
+
 int rrtk_ctx_plan2(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc *h_plans, int nplans, int n, const int16_t *h_samples,
                    const uint64_t *h_state, const uint8_t *h_heads, int16_t *h_pts, uint8_t *h_head, double *h_cost, double *h_elen,
                    int32_t *h_parent, int64_t *h_stats)
@@ -1113,20 +1135,19 @@ int rrtk_ctx_plan2(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc 
     }
     if (h_heads) RRTK_CUDA(cudaMemcpyAsync(c->heads.p, h_heads, total, cudaMemcpyHostToDevice, st));
     rrtk_plan2_cfg use = *cfg;
-    if (dub && cfg->star && !cfg->dubins_table && cfg->r_rewire >= 1.0 && cfg->r_rewire <= 1024.0) {
-        // memo of the primitive over the rewire radius, kept in the context while (radius, headings, rho) stay the same
-        const int R = (int)ceil(cfg->r_rewire);
-        const size_t bytes = dubins_table_bytes(R, cfg->nheadings);
-        if (bytes <= ((size_t)256 << 20)) {
-            if (c->dt_R != R || c->dt_NH != cfg->nheadings || c->dt_rho != cfg->rho || !c->dtable.p) {
-                RRTK_CUDA(cudaStreamSynchronize(st));
-                RRTK_TRY(c->dtable.reserve(bytes));
-                RRTK_TRY(rrtk_dubins_table_build(R, cfg->nheadings, cfg->rho, c->dtable.p, st));
-                c->dt_R = R; c->dt_NH = cfg->nheadings; c->dt_rho = cfg->rho;
-            }
-            use.dubins_table = c->dtable.p;
-            use.table_radius = R;
-        }
+    RRTK_TRY(ctx_dubins_memo(c, &use, st));
+    // informed: the unit-disc draws and the ellipse budgets are host arrays in this form of the call
+    const double *h_balls = cfg->informed ? cfg->balls : nullptr;
+    double *h_ell = cfg->informed ? cfg->ell_c : nullptr;
+    use.balls = nullptr; use.ell_c = nullptr;
+    if (h_balls) {
+        RRTK_TRY(c->balls.reserve(total * 16));
+        RRTK_CUDA(cudaMemcpyAsync(c->balls.p, h_balls, total * 16, cudaMemcpyHostToDevice, st));
+        use.balls = c->balls.as<double>();
+    }
+    if (h_ell) {
+        RRTK_TRY(c->ell.reserve(rows * 8));
+        use.ell_c = c->ell.as<double>();
     }
     cfg = &use;
     RRTK_TRY(rrtk_plan2_batch(cfg, c->bits.as<uint32_t>(), c->W, c->H, c->plans.as<rrtk_plan_desc>(), nplans, n, c->samples.as<int16_t>(),
@@ -1139,7 +1160,186 @@ int rrtk_ctx_plan2(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const rrtk_plan_desc 
     RRTK_CUDA(cudaMemcpyAsync(h_elen, c->elen.p, rows * 8, cudaMemcpyDeviceToHost, st));
     RRTK_CUDA(cudaMemcpyAsync(h_parent, c->parent.p, rows * 4, cudaMemcpyDeviceToHost, st));
     RRTK_CUDA(cudaMemcpyAsync(h_stats, c->stats.p, (size_t)nplans * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st));
+    if (h_ell) RRTK_CUDA(cudaMemcpyAsync(h_ell, c->ell.p, rows * 8, cudaMemcpyDeviceToHost, st));
     RRTK_CUDA(cudaStreamSynchronize(st));
+    for (int p = 0; p < nplans; ++p)
+        if (h_stats[(size_t)p * RRTK_STAT_COUNT + RRTK_STAT2_OVERFLOW]) {
+            set_error("plan %d: a rewire-radius set exceeded the kernel's list (1024 vertices); reduce r_rewire", p);
+            return RRTK_ERR_CAPACITY;
+        }
+    return RRTK_OK;
+}
+
+// K8 from host buffers with the worlds in the same call, chunked and pipelined like rrtk_ctx_plan_worlds2
+int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_grids, int nworlds, int W, int H, const rrtk_plan_desc *h_plans,
+                          int nplans, int n, const int16_t *h_samples, const uint64_t *h_state, const uint8_t *h_heads, int flags, int path_cap,
+                          int16_t *h_pts, uint8_t *h_head, double *h_cost, double *h_elen, int32_t *h_parent, int64_t *h_stats, int32_t *h_path,
+                          int16_t *h_xy, uint8_t *h_path_head, int32_t *h_len, double *h_path_cost, int chunk_plans)
+{
+    const bool in_bits = flags & RRTK_IN_BITS, out_trees = flags & RRTK_OUT_TREES, out_paths = flags & RRTK_OUT_PATHS;
+    RRTK_TRY(check_plan2_cfg(cfg));
+    RRTK_REQUIRE(c && h_grids && h_plans && h_stats, "rrtk_ctx_plan2_worlds: null pointer");
+    RRTK_REQUIRE(!out_trees || (h_pts && h_head && h_cost && h_elen && h_parent),
+                 "rrtk_ctx_plan2_worlds: RRTK_OUT_TREES needs h_pts, h_head, h_cost, h_elen, h_parent");
+    RRTK_REQUIRE(!out_paths || (h_path && h_xy && h_len && h_path_cost && path_cap >= 1),
+                 "rrtk_ctx_plan2_worlds: RRTK_OUT_PATHS needs h_path, h_xy, h_len, h_path_cost and path_cap >= 1");
+    RRTK_REQUIRE((h_samples != nullptr) != (h_state != nullptr), "rrtk_ctx_plan2_worlds: pass exactly one of h_samples / h_state");
+    RRTK_REQUIRE(nworlds >= 1 && nplans >= 0 && n >= 1 && n <= 65534, "rrtk_ctx_plan2_worlds: need nworlds >= 1, nplans >= 0, 1 <= n <= 65534");
+    RRTK_TRY(check_grid_dims(W, H, 16384));
+    if (nplans == 0) return RRTK_OK;
+    const bool dub = cfg->model == RRTK_MODEL_DUBINS;
+    for (int p = 0; p < nplans; ++p) {
+        const rrtk_plan_desc &d = h_plans[p];
+        if (d.world < 0 || d.world >= nworlds || d.start_x < 0 || d.start_x >= W || d.goal_x < 0 || d.goal_x >= W ||
+            d.start_y < 0 || d.start_y >= H || d.goal_y < 0 || d.goal_y >= H) {
+            set_error("plan %d: world index or start/goal outside the grid", p);
+            return RRTK_ERR_INVALID;
+        }
+        if (p && d.world < h_plans[p - 1].world) {
+            set_error("rrtk_ctx_plan2_worlds: plans must be ordered by world index (plan %d)", p);
+            return RRTK_ERR_INVALID;
+        }
+        if (dub && (d.reserved[0] < 0 || d.reserved[0] >= cfg->nheadings || d.reserved[1] < 0 || d.reserved[1] >= cfg->nheadings)) {
+            set_error("plan %d: start / goal heading outside [0, %d)", p, cfg->nheadings);
+            return RRTK_ERR_INVALID;
+        }
+    }
+    const size_t total = (size_t)nplans * n;
+    if (h_samples)
+        for (size_t i = 0; i < total; ++i) {
+            const int x = h_samples[2 * i], y = h_samples[2 * i + 1];
+            if (x < 0 || x >= W || y < 0 || y >= H) {
+                set_error("sample %zu of plan %zu lies outside the grid", i % n, i / n);
+                return RRTK_ERR_INVALID;
+            }
+        }
+    if (dub && h_heads)
+        for (size_t i = 0; i < total; ++i)
+            if (h_heads[i] >= cfg->nheadings) {
+                set_error("heading of sample %zu of plan %zu outside [0, %d)", i % n, i / n, cfg->nheadings);
+                return RRTK_ERR_INVALID;
+            }
+    DevInfo *di;
+    RRTK_TRY(dev_info(&di));
+    if (chunk_plans <= 0) {
+        // a plan of this kernel runs for tens of milliseconds: one block per SM and chunk keeps every copy hidden behind the
+        // plans of the chunks before it, and the first chunk is on the device after 1/16 of the uploads
+        chunk_plans = di->sms;
+    }
+    rrtk_plan2_cfg use = *cfg;
+    RRTK_TRY(ctx_dubins_memo(c, &use, c->stream));
+    const double *h_balls = cfg->informed ? cfg->balls : nullptr;      // host arrays in this form of the call
+    double *h_ell = cfg->informed ? cfg->ell_c : nullptr;
+    use.balls = nullptr; use.ell_c = nullptr;
+    const size_t cells = (size_t)W * H, words = grid_words(W, H), rows1 = (size_t)n + 1;
+    const size_t grid_bytes = in_bits ? words * 4 : cells;
+    std::vector<int> starts;
+    for (int p0 = 0; p0 < nplans; p0 += chunk_plans) starts.push_back(p0);
+    starts.push_back(nplans);
+    size_t max_m = 0, max_nw = 0;
+    for (size_t k = 0; k + 1 < starts.size(); ++k) {
+        const size_t m = (size_t)(starts[k + 1] - starts[k]);
+        const size_t nw = (size_t)(h_plans[starts[k + 1] - 1].world - h_plans[starts[k]].world + 1);
+        max_m = m > max_m ? m : max_m;
+        max_nw = nw > max_nw ? nw : max_nw;
+    }
+    int status = RRTK_OK;
+    auto cuda_ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && status == RRTK_OK) status = cuda_fail(e, what);
+        return e == cudaSuccess;
+    };
+    auto rrtk_ok = [&](int rc) {
+        if (rc != RRTK_OK && status == RRTK_OK) status = rc;
+        return rc == RRTK_OK;
+    };
+    const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
+    for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
+        PipeSlot &s = c->pipe[k];
+        if (!s.stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags") ||
+                !cuda_ok(cudaStreamCreateWithPriority(&s.prep, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority") ||
+                !cuda_ok(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming), "cudaEventCreateWithFlags") ||
+                !cuda_ok(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreateWithFlags")) break;
+        }
+        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+        cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
+        bool ok = rrtk_ok(s.bits.reserve(words * 4 * max_nw)) && rrtk_ok(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw)) &&
+                  rrtk_ok(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m)) && rrtk_ok(s.samples.reserve(max_m * n * 4)) &&
+                  rrtk_ok(s.state.reserve(max_m * 32)) && rrtk_ok(s.heads.reserve(max_m * n)) && rrtk_ok(s.pts.reserve(rows1 * max_m * 4)) &&
+                  rrtk_ok(s.head_out.reserve(rows1 * max_m)) && rrtk_ok(s.cost.reserve(rows1 * max_m * 8)) &&
+                  rrtk_ok(s.elen.reserve(rows1 * max_m * 8)) && rrtk_ok(s.parent.reserve(rows1 * max_m * 4)) &&
+                  rrtk_ok(s.stats.reserve(max_m * RRTK_STAT_COUNT * 8)) && rrtk_ok(s.scratch2.reserve(plan2_scratch_bytes((int)max_m, n)));
+        if (ok && !in_bits) ok = rrtk_ok(s.og.reserve(cells * max_nw));
+        if (ok && h_balls) ok = rrtk_ok(s.balls.reserve(max_m * n * 16));
+        if (ok && h_ell) ok = rrtk_ok(s.ell.reserve(rows1 * max_m * 8));
+        if (ok && out_paths)
+            ok = rrtk_ok(s.path.reserve(max_m * path_cap * 4)) && rrtk_ok(s.xy.reserve(max_m * path_cap * 4)) &&
+                 rrtk_ok(s.phead.reserve(max_m * path_cap)) && rrtk_ok(s.len.reserve(max_m * 4)) && rrtk_ok(s.pcost.reserve(max_m * 8));
+    }
+    for (size_t ci = 0; ci + 1 < starts.size() && status == RRTK_OK; ++ci) {
+        const int p0 = starts[ci], m = starts[ci + 1] - starts[ci];
+        PipeSlot &s = c->pipe[ci % kPipeSlots];
+        cudaStream_t st = s.prep;
+        if (ci >= (size_t)kPipeSlots && !cuda_ok(cudaStreamWaitEvent(st, s.done, 0), "cudaStreamWaitEvent")) break;
+        const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
+        const uint8_t *src = static_cast<const uint8_t *>(h_grids) + grid_bytes * w0;
+        if (in_bits) {
+            if (!cuda_ok(cudaMemcpyAsync(s.bits.p, src, grid_bytes * nw, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(bits)")) break;
+        } else {
+            if (!cuda_ok(cudaMemcpyAsync(s.og.p, src, grid_bytes * nw, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(og)")) break;
+            if (!rrtk_ok(pack_launch(s.og.as<uint8_t>(), nw, W, H, s.bits.as<uint32_t>(), st))) break;
+        }
+        s.desc.assign(h_plans + p0, h_plans + p0 + m);
+        for (rrtk_plan_desc &d : s.desc) d.world -= w0;
+        if (!cuda_ok(cudaMemcpyAsync(s.plans.p, s.desc.data(), sizeof(rrtk_plan_desc) * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(plans)")) break;
+        if (h_samples) {
+            if (!cuda_ok(cudaMemcpyAsync(s.samples.p, h_samples + (size_t)p0 * n * 2, (size_t)m * n * 4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(samples)")) break;
+        } else {
+            if (!rrtk_ok(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st))) break;
+            if (!cuda_ok(cudaMemcpyAsync(s.state.p, h_state + (size_t)p0 * 4, (size_t)m * 32, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(state)")) break;
+            if (!rrtk_ok(sample_streams_launch(s.bits.as<uint32_t>(), s.rowcum.as<int32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m,
+                                               s.state.as<uint64_t>(), n, s.samples.as<int16_t>(), di->optin, st))) break;
+        }
+        if (h_heads && !cuda_ok(cudaMemcpyAsync(s.heads.p, h_heads + (size_t)p0 * n, (size_t)m * n, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(heads)")) break;
+        if (h_balls && !cuda_ok(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(balls)")) break;
+        if (!cuda_ok(cudaEventRecord(s.ready, st), "cudaEventRecord")) break;
+        st = s.stream;
+        if (!cuda_ok(cudaStreamWaitEvent(st, s.ready, 0), "cudaStreamWaitEvent")) break;
+        use.balls = h_balls ? s.balls.as<double>() : nullptr;
+        use.ell_c = h_ell ? s.ell.as<double>() : nullptr;
+        if (!rrtk_ok(rrtk_plan2_batch(&use, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, s.samples.as<int16_t>(),
+                                      h_heads ? s.heads.as<uint8_t>() : nullptr, s.pts.as<int16_t>(), s.head_out.as<uint8_t>(), s.cost.as<double>(),
+                                      s.elen.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(), s.scratch2.p, 0, st))) break;
+        bool ok = true;
+        if (out_paths) {
+            ok = rrtk_ok(paths_xy_launch(s.parent.as<int32_t>(), s.pts.as<int16_t>(), s.cost.as<double>(), s.stats.as<int64_t>(), m, n, path_cap,
+                                         s.path.as<int32_t>(), s.xy.as<int16_t>(), s.len.as<int32_t>(), s.pcost.as<double>(), st)) &&
+                 cuda_ok(cudaMemcpyAsync(h_path + (size_t)p0 * path_cap, s.path.p, (size_t)m * path_cap * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(path)") &&
+                 cuda_ok(cudaMemcpyAsync(h_xy + (size_t)p0 * path_cap * 2, s.xy.p, (size_t)m * path_cap * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(xy)") &&
+                 cuda_ok(cudaMemcpyAsync(h_len + p0, s.len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(len)") &&
+                 cuda_ok(cudaMemcpyAsync(h_path_cost + p0, s.pcost.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(path_cost)");
+            if (ok && h_path_head)
+                ok = rrtk_ok(path_heads_launch(s.path.as<int32_t>(), s.head_out.as<uint8_t>(), m, n, path_cap, s.phead.as<uint8_t>(), st)) &&
+                     cuda_ok(cudaMemcpyAsync(h_path_head + (size_t)p0 * path_cap, s.phead.p, (size_t)m * path_cap, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(path_head)");
+        }
+        if (ok && out_trees)
+            ok = cuda_ok(cudaMemcpyAsync(h_pts + (size_t)p0 * rows1 * 2, s.pts.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(pts)") &&
+                 cuda_ok(cudaMemcpyAsync(h_head + (size_t)p0 * rows1, s.head_out.p, rows1 * m, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(head)") &&
+                 cuda_ok(cudaMemcpyAsync(h_cost + (size_t)p0 * rows1, s.cost.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(cost)") &&
+                 cuda_ok(cudaMemcpyAsync(h_elen + (size_t)p0 * rows1, s.elen.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(elen)") &&
+                 cuda_ok(cudaMemcpyAsync(h_parent + (size_t)p0 * rows1, s.parent.p, rows1 * m * 4, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(parent)");
+        if (ok && h_ell) ok = cuda_ok(cudaMemcpyAsync(h_ell + (size_t)p0 * rows1, s.ell.p, rows1 * m * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(ell)");
+        if (ok) cuda_ok(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(stats)");
+        cuda_ok(cudaEventRecord(s.done, st), "cudaEventRecord");
+    }
+    for (PipeSlot &s : c->pipe)
+        if (s.stream) {
+            cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
+            cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+        }
+    if (status != RRTK_OK) return status;
     for (int p = 0; p < nplans; ++p)
         if (h_stats[(size_t)p * RRTK_STAT_COUNT + RRTK_STAT2_OVERFLOW]) {
             set_error("plan %d: a rewire-radius set exceeded the kernel's list (1024 vertices); reduce r_rewire", p);

@@ -187,6 +187,24 @@ int paths_xy_launch(const int32_t *d_parent, const int16_t *d_pts, const double 
     return RRTK_OK;
 }
 
+// headings of the path vertices (K8 trees): what a caller needs beside the points to re-draw a Dubins path
+__global__ void path_heads_kernel(const int *path, const uint8_t *head, int nplans, int n, int cap, uint8_t *out)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)nplans * cap) return;
+    const int v = path[i];
+    out[i] = v < 0 ? (uint8_t)255 : head[(i / cap) * (size_t)(n + 1) + v];
+}
+
+int path_heads_launch(const int32_t *d_path, const uint8_t *d_head, int nplans, int n, int cap, uint8_t *d_out, cudaStream_t st)
+{
+    const size_t total = (size_t)nplans * cap;
+    if (total == 0) return RRTK_OK;
+    path_heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_path, d_head, nplans, n, cap, d_out);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
 int paths_launch(const int32_t *d_parent, const int64_t *d_stats, int nplans, int n, int cap, int32_t *d_path,
                  int32_t *d_len, cudaStream_t st)
 {

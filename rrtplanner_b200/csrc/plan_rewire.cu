@@ -18,10 +18,16 @@
 //   G  apply     warp 0, ascending vertex order, re-testing against costs already lowered this round; the rewired
 //                subtree's costs are recomputed breadth-first over child lists kept in shared memory
 // The goal connection evaluates every vertex, prunes with a shared 64-bit minimum and breaks ties by index.
+//
+// Informed sampling (cfg.informed, the rule of rrt.py:690-701,744-745 on top of this loop): accepted vertices within r_goal
+// of the goal join a list; while it is non-empty the (x, y) of a round is the ellipse point for c = cost of the list's
+// cheapest vertex + its distance to the goal.  A rewire can lower that cost, so warp 0 re-reads the list at the end of every
+// accepted round (one sample per round is exactly what this needs); rejected rounds change nothing and reuse c.
 #include <math_constants.h>
 #include <cstdio>
 
 #include "dubins.cuh"
+#include "plan_common.cuh"      // ellipse_sample
 
 #ifndef RRTK_K8_BLOCK_THREADS
 #define RRTK_K8_BLOCK_THREADS 768        // resident threads per SM the register allocation is bounded for
@@ -29,7 +35,7 @@
 
 namespace rrtk {
 
-enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROPAGATED, S2_RING, S2_LEN_EVALS, S2_OVERFLOW };
+enum { S2_J = 0, S2_VGOAL, S2_FOUND, S2_CHECKS, S2_ACCEPTED, S2_REWIRES, S2_PROPAGATED, S2_RING, S2_LEN_EVALS, S2_OVERFLOW, S2_ELL_ITERS, S2_FIRST_SOL };
 
 struct Plan2Params {
     const uint32_t *bits;
@@ -50,6 +56,11 @@ struct Plan2Params {
     long long *stats;
     double *gcost;          // scratch: (n + 1) doubles per plan
     uint16_t *queue;        // scratch: (n + 1) vertex ids per plan
+    uint16_t *sol;          // scratch: (n + 1) vertex ids per plan: the solution vertices of an informed plan, in the order they joined
+    int informed;
+    double r_goal;
+    const double2 *balls;   // informed: n unit-disc draws per plan (NULL = probe: stop at the first solution vertex)
+    double *ell_c;          // informed, optional: (n + 1) per plan, the budget the last ellipse sample drawn at that j used
     int ring_cap;
     // optional memo of the Dubins primitive (rrtk_dubins_table_build): shortest path for every displacement in
     // [-tR, tR]^2 and every heading pair, entry ((dx + tR) * (2 tR + 1) + dy + tR) * NH * NH + h0 * NH + h1
@@ -164,6 +175,8 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
     __shared__ int s_accept, s_tail;
     __shared__ double s_c0, s_l0;
     __shared__ long long s_stat[10];
+    __shared__ int s_nsol, s_first;             // informed: solution vertices so far, iteration that accepted the first one
+    __shared__ double s_cb;                     // informed: budget c of the ellipse the next sample is drawn from (s_nsol > 0)
 
     const rrtk_plan_desc pd = P.plans[plan];
     const uint32_t *bits = P.bits + (size_t)pd.world * P.words_per_grid;
@@ -176,12 +189,16 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
     int *parent = P.parent + (size_t)plan * (n + 1);
     double *gcost = P.gcost + (size_t)plan * (n + 1);
     uint16_t *queue = P.queue + (size_t)plan * (n + 1);
+    uint16_t *sol = P.sol + (size_t)plan * (n + 1);
+    const double2 *balls = (P.informed && P.balls) ? P.balls + (size_t)plan * n : nullptr;
+    double *ell_c = (P.informed && P.ell_c) ? P.ell_c + (size_t)plan * (n + 1) : nullptr;
 
     // ---- initialise ---------------------------------------------------------------------------------
     for (int v = tid; v <= n; v += T) {
         spts[v] = RRTK_FAR_VERTEX; shead[v] = 255; first[v] = kNil; next[v] = kNil;
         o_pts[v] = make_short2(-32768, -32768); o_head[v] = 255;
         cost[v] = CUDART_INF; elen[v] = CUDART_INF; parent[v] = -1;
+        if (ell_c) ell_c[v] = CUDART_NAN;
     }
     if (MODEL == RRTK_MODEL_DUBINS) {
         const double dth = DM_TWO_PI / (double)P.NH;
@@ -192,6 +209,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
         }
     }
     if (tid < 10) s_stat[tid] = 0;
+    if (tid == 0) { s_nsol = 0; s_first = -1; s_cb = 0.0; }
     __syncthreads();
     const int start_h = MODEL == RRTK_MODEL_DUBINS ? pd.reserved[0] : 0;
     const int goal_h = MODEL == RRTK_MODEL_DUBINS ? pd.reserved[1] : 0;
@@ -204,6 +222,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
 
     int j = 1;
     long long my_checks = 0, my_lens = 0;      // per-thread counters, reduced at the end
+    long long ell_iters = 0;                   // informed: rounds whose sample came from the ellipse (the same in every thread)
     // -DRRTK_K8_CLOCKS (experiment builds): cycles thread 0 spends up to the barrier that ends each phase, printed for plan 0
 #ifdef RRTK_K8_CLOCKS
     long long clk_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, clk_last = clock64(), clk_rounds = 0;
@@ -223,7 +242,14 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
 
     for (int it = 0; it < n; ++it) {
         const short2 sm = samples[it];
-        const int qx = sm.x, qy = sm.y;
+        int qx = sm.x, qy = sm.y;
+        if (P.informed && s_nsol > 0) {          // uniform: the list and the budget only change before a round's last barrier
+            if (!balls) break;                    // probe run
+            const double c = s_cb;
+            ellipse_sample(P.W, P.H, pd.rot, pd.start_x, pd.start_y, pd.goal_x, pd.goal_y, c, balls[it], qx, qy);   // rrt.py:699-700
+            if (tid == 0 && ell_c) ell_c[j] = c;                                                                     // rrt.py:701
+            ++ell_iters;
+        }
         const int qh = (MODEL == RRTK_MODEL_DUBINS && heads) ? heads[it] : 0;
         const uint32_t pnew = pack_xy(qx, qy);
 
@@ -433,6 +459,11 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             if (wslot < 0) elen[j] = s_l0;
             next[j] = first[vbest]; first[vbest] = (uint16_t)j;
             s_stat[S2_ACCEPTED] += 1; s_stat[S2_RING] += m;
+            if (P.informed && __dsqrt_rn((double)dist2(pnew, pd.goal_x, pd.goal_y)) < P.r_goal) {      // rrt.py:744-745
+                if (s_nsol == 0) s_first = it;
+                sol[s_nsol] = (uint16_t)j;
+                s_nsol = s_nsol + 1;
+            }
         }
         if (both) {
             for (int i = tid; i < m; i += T) {
@@ -512,6 +543,27 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 }
             }
         }
+        if (P.informed && warp == 0) {
+            // least_cost over the solution vertices (rrt.py:627-633: first minimum in list order) with the costs as they stand after
+            // this round's rewires, + that vertex's distance to the goal (rrt.py:697-698): the budget of the next ellipse
+            __syncwarp();
+            const int ns = s_nsol;
+            if (ns > 0) {
+                double bc = CUDART_INF;
+                int bk = 0x7fffffff;
+                for (int k = lane; k < ns; k += 32) {
+                    const double c = cost[sol[k]];
+                    if (c < bc) { bc = c; bk = k; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double oc = __shfl_xor_sync(RRTK_FULL, bc, o);
+                    const int ok = __shfl_xor_sync(RRTK_FULL, bk, o);
+                    if (oc < bc || (oc == bc && ok < bk)) { bc = oc; bk = ok; }
+                }
+                if (lane == 0) s_cb = __dadd_rn(bc, __dsqrt_rn((double)dist2(spts[sol[bk]], pd.goal_x, pd.goal_y)));
+            }
+        }
         ++j;
         __syncthreads();
         K8_CLK(9);
@@ -581,6 +633,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
         long long *st = P.stats + (size_t)plan * RRTK_STAT_COUNT;
         for (int k = 0; k < RRTK_STAT_COUNT; ++k) st[k] = k < 10 ? s_stat[k] : 0;
         st[S2_J] = j; st[S2_VGOAL] = vgoal; st[S2_FOUND] = found;
+        st[S2_ELL_ITERS] = ell_iters; st[S2_FIRST_SOL] = s_first;
     }
 }
 
@@ -607,7 +660,7 @@ static int plan2_ring_cap(int n)
 
 size_t plan2_scratch_bytes(int nplans, int n)
 {
-    return (size_t)nplans * (n + 1) * (sizeof(double) + sizeof(uint16_t)) + 16;
+    return (size_t)nplans * (n + 1) * (sizeof(double) + 2 * sizeof(uint16_t)) + 16;
 }
 
 template <int MODEL, int T>
@@ -654,6 +707,11 @@ int plan2_launch(const rrtk_plan2_cfg &cfg, const uint32_t *d_bits, int W, int H
     uintptr_t s = (reinterpret_cast<uintptr_t>(d_scratch) + 15) & ~(uintptr_t)15;
     P.gcost = reinterpret_cast<double *>(s);
     P.queue = reinterpret_cast<uint16_t *>(P.gcost + (size_t)nplans * (n + 1));
+    P.sol = P.queue + (size_t)nplans * (n + 1);
+    P.informed = cfg.informed != 0;
+    P.r_goal = cfg.r_goal;
+    P.balls = reinterpret_cast<const double2 *>(cfg.balls);
+    P.ell_c = cfg.ell_c;
     P.tlen = nullptr; P.ttpq = nullptr; P.tword = nullptr; P.tR = 0;
     if (cfg.model == RRTK_MODEL_DUBINS && cfg.dubins_table && cfg.table_radius > 0) {
         const size_t N = dubins_table_entries(cfg.table_radius, cfg.nheadings);

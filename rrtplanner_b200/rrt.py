@@ -365,16 +365,39 @@ class RRTStar(RRT):
 
 
 class RRTStarInformed(RRT):
-    """Informed RRT* (rrt.py:562-758)."""
+    """Informed RRT* (rrt.py:562-758).
+
+    ``rewire`` (keyword-only, not in the reference) as for :class:`RRTStar`: ``"reference"`` keeps the reference's rewire
+    block, which never fires; ``"rrtstar"`` runs the loop with the rewire that fires (kernel K8 with the informed sampling
+    rule; specification oracle/rewire_oracle.c:orc2_plan_informed).  With the rewire off that kernel reproduces the
+    reference's informed trees bit for bit (tests/test_gpu_rewire.py), so the sampling rule itself is pinned."""
 
     _KIND = _lib.KIND_INFORMED
 
     def __init__(self, og: np.ndarray, n: int, r_rewire: float, r_goal: float, costfn: callable = None,
-                 pbar: bool = True, seed: int = 0):
+                 pbar: bool = True, seed: int = 0, *, rewire: str = "reference"):
         super().__init__(og, n, costfn=costfn, pbar=pbar, seed=seed)
         self.r_rewire = r_rewire
         self.r_goal = r_goal
         self.ellipses = {}
+        if rewire not in ("reference", "rrtstar"):
+            raise ValueError("rewire must be 'reference' or 'rrtstar'")
+        self.rewire = rewire               # as for RRTStar: "rrtstar" = the rewire that fires (kernel K8), not in the reference
+
+    def _launch(self, ctx, desc, samples, balls=None):
+        """One launch of the plan (balls=None: the probe that stops at the first solution vertex):
+        (pts, cost, parent, stats, ell, iteration of the first solution vertex)."""
+        if self.rewire == "rrtstar":
+            cfg = _lib.plan2_cfg(_lib.MODEL_EUCLID, True, True, self.r_rewire, informed=True, r_goal=self.r_goal)
+            pts, _, cost, _, parent, stats, ell = ctx.plan2(cfg, desc, self.n, samples=samples, balls=balls)
+            self.last_stats = dict(zip(_lib.STAT2_NAMES, (int(v) for v in stats[0])))
+            return pts, cost, parent, stats, ell, int(stats[0][_lib.STAT2_NAMES.index("first_solution_iter")])
+        if balls is None:
+            pts, cost, parent, stats, ell = ctx.plan(self._KIND, desc, self.n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples)
+        else:
+            pts, cost, parent, stats, ell = ctx.plan(self._KIND, desc, self.n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples,
+                                                     balls=balls)
+        return pts, cost, parent, stats, ell, int(stats[0][5])
 
     # ---- sampler pieces, host-side mirrors of rrt.py:579-651 (the device evaluates the same
     #      formulas inside the plan kernel; these serve callers and the ellipse records) ---------
@@ -462,16 +485,14 @@ class RRTStarInformed(RRT):
                 if r2norm(x - xgoal) < self.r_goal:
                     # the probe sees iterations 0 .. drawn-1 only (later rows repeat the last sample: duplicates)
                     samples[0, drawn:] = x
-                    _, _, _, st, _ = ctx.plan(self._KIND, desc, n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples)
-                    f = int(st[0][5])
+                    f = self._launch(ctx, desc, samples)[5]
                     if 0 <= f < drawn:
                         first = f
         else:
             nfree = self.free.shape[0]
             probe_gen = copy.deepcopy(self.rand_gen)
             samples = self.free[probe_gen.integers(0, nfree, size=n)].astype(np.int16)[None]
-            _, _, _, st, _ = ctx.plan(self._KIND, desc, n, r_rewire=self.r_rewire, r_goal=self.r_goal, samples=samples)
-            first = int(st[0][5])
+            first = self._launch(ctx, desc, samples)[5]
             # advance the real generator by exactly the free-space draws the reference consumes
             self.rand_gen.integers(0, nfree, size=n if first < 0 else first + 1)
         balls = np.zeros((1, n, 2))
@@ -480,9 +501,11 @@ class RRTStarInformed(RRT):
             desc = self._desc(xstart, xgoal, rot)
             for i in range(first + 1, n):
                 balls[0, i] = self.unitball()
-        pts, cost, parent, stats, ell = ctx.plan(self._KIND, desc, n, r_rewire=self.r_rewire, r_goal=self.r_goal,
-                                                 samples=samples, balls=balls)
+        pts, cost, parent, stats, ell, _ = self._launch(ctx, desc, samples, balls)
         for jj in np.flatnonzero(~np.isnan(ell[0])):
             self.ellipses[int(jj)] = self.get_ellipse_for_plt(xstart, xgoal, ell[0][jj])   # rrt.py:701
         self._tick()
-        return self._finish(pts[0], cost[0], parent[0], stats[0])
+        T, gv = self._finish(pts[0], cost[0], parent[0], stats[0])
+        if self.rewire == "rrtstar":
+            self.last_stats = dict(zip(_lib.STAT2_NAMES, (int(v) for v in stats[0])))
+        return T, gv

@@ -120,7 +120,8 @@ int main(void) {
     printf("rrtk_plan2_cfg %zu\n", sizeof(rrtk_plan2_cfg));
     F(rrtk_plan2_cfg, model); F(rrtk_plan2_cfg, star); F(rrtk_plan2_cfg, rewire); F(rrtk_plan2_cfg, nheadings);
     F(rrtk_plan2_cfg, r_rewire); F(rrtk_plan2_cfg, rho); F(rrtk_plan2_cfg, ds); F(rrtk_plan2_cfg, dubins_table);
-    F(rrtk_plan2_cfg, table_radius); F(rrtk_plan2_cfg, reserved);
+    F(rrtk_plan2_cfg, table_radius); F(rrtk_plan2_cfg, informed); F(rrtk_plan2_cfg, r_goal); F(rrtk_plan2_cfg, balls);
+    F(rrtk_plan2_cfg, ell_c);
     printf("RRTK_STAT_COUNT %d\n", (int)RRTK_STAT_COUNT);
     return 0;
 }

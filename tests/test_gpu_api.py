@@ -164,6 +164,45 @@ def test_subclass_injection_reproduces_the_golden_trees(golden_plan):
         assert state["ball"] == 0
 
 
+def test_informed_planner_with_the_firing_rewire_matches_the_specification():
+    """RRTStarInformed(..., rewire="rrtstar") through the class API == oracle/rewire_oracle.c driven with the draws the
+    reference's loop would take from the planner's generator (free-space draws up to the first solution vertex, then two
+    uniforms per iteration)."""
+    from oracle import rewire_oracle as R2
+    from oracle import rrt_oracle as O
+    og = R.worlds.perlin_occupancygrid(120, 96, seed=33).astype(np.uint8)
+    n, r, r_goal, seed = 1200, 25.0, 8.0, 5
+    free = np.argwhere(og == 0)
+    xs, xg = R.worlds.start_goal(og, 1)
+    p = R.RRTStarInformed(og, n, r, r_goal, pbar=False, seed=seed, rewire="rrtstar")
+    T, gv = p.plan(xs, xg)
+    gen = np.random.default_rng(seed)
+    probe_gen = np.random.default_rng(seed)
+    smp = np.concatenate([free[probe_gen.integers(0, len(free), size=n)], np.zeros((n, 1), dtype=np.int64)], axis=1)
+    rot = O.ellipse_rotation(xs, xg)
+    kw = dict(star=True, rewire=True, r_rewire=r)
+    first = R2.plan("euclid", og, n, [*xs, 0], [*xg, 0], smp, informed=dict(r_goal=r_goal, rot=rot, balls=None), **kw)["stats"]["first_solution_iter"]
+    assert first >= 0
+    gen.integers(0, len(free), size=first + 1)
+    balls = np.zeros((n, 2))
+    for i in range(first + 1, n):
+        u = gen.uniform(0, 1)
+        a = 2 * np.pi * gen.uniform(0, 1)
+        balls[i] = [np.sqrt(u) * np.cos(a), np.sqrt(u) * np.sin(a)]
+    want = R2.plan("euclid", og, n, [*xs, 0], [*xg, 0], smp, informed=dict(r_goal=r_goal, rot=rot, balls=balls), **kw)
+    st = want["stats"]
+    assert st["rewires"] > 10 and st["ell_iters"] == n - 1 - first
+    assert p.last_stats["j"] == st["j"] and p.last_stats["rewires"] == st["rewires"] and p.last_stats["first_solution_iter"] == first
+    j = st["j"]
+    for v in range(1, j):
+        assert np.array_equal(T.nodes[v]["pt"], want["pts"][v])
+        (par, _, attr), = T.in_edges(v, data=True)
+        assert par == want["parent"][v] and attr["cost"] == want["cost"][v]
+    assert sorted(p.ellipses) == [int(k) for k in np.flatnonzero(~np.isnan(want["ell"]))]
+    # the planner's generator was advanced exactly as the reference's loop would have advanced it
+    assert p.rand_gen.uniform(0, 1) == gen.uniform(0, 1)
+
+
 def test_static_collisionfree_sees_in_place_edits():
     """The static wrapper keeps the last grid on the device between calls, validated by content."""
     og = np.zeros((40, 60), dtype=np.int64)

@@ -111,6 +111,73 @@ def test_euclid_without_rewire_reproduces_the_reference_trees(ctx, path):
     assert np.array_equal(par[1:top].astype(np.int64), g["parents"][1:top])
 
 
+def _run_informed(ctx, model, og, n, start, goal, smp, rewire, r, r_goal, rot, balls, nh=16, rho=1.0, ds=1.0):
+    ctx.set_grids((og != 0).astype(np.uint8)[None])
+    cfg = _lib.plan2_cfg(_lib.MODEL_DUBINS if model == "dubins" else _lib.MODEL_EUCLID, True, rewire, r, nh, rho, ds, informed=True, r_goal=r_goal)
+    d = _desc(start, goal)
+    d["rot"][0] = np.asarray(rot, dtype=np.float64).reshape(4)
+    pts, head, cost, elen, par, st, ell = ctx.plan2(cfg, d, n, samples=smp[None, :, :2].astype(np.int16), heads=smp[None, :, 2].astype(np.uint8),
+                                                    balls=None if balls is None else balls[None])
+    return (pts[0], head[0], cost[0], elen[0], par[0], dict(zip(_lib.STAT2_NAMES, (int(v) for v in st[0])))), ell[0]
+
+
+@pytest.mark.parametrize("path", [p for p in golden_plans() if "informed" in p], ids=lambda p: p.split("plan_")[-1][:-4])
+def test_informed_without_rewire_reproduces_the_reference_trees(ctx, path):
+    """K8 with the informed sampling rule and the rewire off == the RRTStarInformed trees of the real reference (pinned)."""
+    from oracle import rrt_oracle as O
+    g = load_plan(path)
+    n = g["n"]
+    smp = np.concatenate([g["samples"], np.zeros((n, 1), dtype=np.int64)], axis=1)
+    rot = O.ellipse_rotation(g["xstart"], g["xgoal"])
+    (pts, head, cost, elen, par, st), ell = _run_informed(ctx, "euclid", g["og"], n, [*g["xstart"], 0], [*g["xgoal"], 0], smp, False,
+                                                          float(g["r_rewire"]), float(g["r_goal"]), rot, g["balls"])
+    found = bool(st["found"])
+    top = st["j"] + (1 if found else 0)
+    assert int(g["vgoal"]) == (st["vgoal"] if found else 0)
+    assert np.array_equal(pts[:top].astype(np.int64), g["points"][:top])
+    assert np.array_equal(cost[:top].view(np.int64), g["vcosts"][:top].view(np.int64))
+    assert np.array_equal(par[1:top].astype(np.int64), g["parents"][1:top])
+    assert [int(k) for k in np.flatnonzero(~np.isnan(ell))] == [int(k) for k in g["ell_keys"]]
+
+
+INFORMED_CASES = [
+    # model, W, H, n, r, r_goal, rewire, nh, rho, world seed
+    ("euclid", 96, 96, 900, 20.0, 8.0, True, 1, 1.0, 21),
+    ("euclid", 200, 160, 2500, 30.0, 5.0, True, 1, 1.0, 22),
+    ("euclid", 128, 128, 1500, 25.0, 40.0, True, 1, 1.0, 23),          # a goal region of ~5000 cells: a long solution list
+    ("dubins", 96, 96, 700, 20.0, 8.0, True, 16, 3.0, 21),
+    ("dubins", 128, 128, 1200, 30.0, 6.0, False, 16, 4.0, 24),
+]
+
+
+@pytest.mark.parametrize("case", INFORMED_CASES, ids=lambda c: f"{c[0]}_{c[1]}x{c[2]}_n{c[3]}_rg{c[5]:g}_rw{int(c[6])}")
+def test_informed_plans_bit_exact_against_the_specification(ctx, case):
+    from oracle import rrt_oracle as O
+    model, W, H, n, r, r_goal, rewire, nh, rho, seed = case
+    og = worlds.perlin_occupancygrid(W, H, seed=seed).astype(np.uint8)
+    free = np.argwhere(og == 0)
+    rng = np.random.default_rng(seed)
+    smp = np.concatenate([free[rng.integers(0, len(free), n)], rng.integers(0, nh, (n, 1))], axis=1)
+    start, goal = [*free[7], 1 % nh], [*free[-7], 3 % nh]
+    u, a = rng.uniform(0, 1, n), 2 * np.pi * rng.uniform(0, 1, n)
+    balls = np.stack([np.sqrt(u) * np.cos(a), np.sqrt(u) * np.sin(a)], axis=1)
+    rot = O.ellipse_rotation(np.array(start[:2]), np.array(goal[:2]))
+    inf = dict(r_goal=r_goal, rot=rot, balls=balls)
+    want = R.plan(model, og, n, start, goal, smp, star=True, rewire=rewire, r_rewire=r, nh=nh, rho=rho, ds=1.0, informed=inf)
+    got, ell = _run_informed(ctx, model, og, n, start, goal, smp, rewire, r, r_goal, rot, balls, nh, rho, 1.0)
+    _compare(got, want, model)
+    assert got[5]["ell_iters"] == want["stats"]["ell_iters"] and got[5]["first_solution_iter"] == want["stats"]["first_solution_iter"]
+    assert want["stats"]["first_solution_iter"] >= 0 and want["stats"]["ell_iters"] > n // 4
+    assert np.array_equal(np.isnan(ell), np.isnan(want["ell"]))
+    k = ~np.isnan(ell)
+    assert np.array_equal(ell[k].view(np.int64), want["ell"][k].view(np.int64))
+    # probe: stops at the first solution vertex, same prefix of the tree
+    probe, _ = _run_informed(ctx, model, og, n, start, goal, smp, rewire, r, r_goal, rot, None, nh, rho, 1.0)
+    wp = R.plan(model, og, n, start, goal, smp, star=True, rewire=rewire, r_rewire=r, nh=nh, rho=rho, ds=1.0, informed=dict(inf, balls=None))
+    _compare(probe, wp, model)
+    assert probe[5]["first_solution_iter"] == want["stats"]["first_solution_iter"] and probe[5]["ell_iters"] == 0
+
+
 CASES = [
     # model, W, H, n, r, star, rewire, nh, rho, ds, world seed
     ("euclid", 96, 96, 600, 20.0, True, True, 1, 1.0, 1.0, 7),
@@ -179,6 +246,54 @@ def test_several_plans_in_one_launch(ctx):
     for p in range(nplans):
         want = R.plan("dubins", ogs[p], n, starts[p], goals[p], smp[p], star=True, rewire=True, r_rewire=25.0, nh=nh, rho=4.0, ds=1.0)
         _compare((pts[p], head[p], cost[p], elen[p], par[p], dict(zip(_lib.STAT2_NAMES, (int(v) for v in st[p])))), want, "dubins")
+
+
+@pytest.mark.parametrize("bits", [False, True])
+def test_pipelined_worlds_call_equals_the_resident_call(ctx, bits):
+    """rrtk_ctx_plan2_worlds (worlds + plans in, trees + path records out, several chunks) == rrtk_ctx_set_grids + rrtk_ctx_plan2."""
+    W = H = 96
+    n, nh, nplans = 300, 8, 11
+    ogs = np.stack([worlds.perlin_occupancygrid(W, H, seed=40 + w).astype(np.uint8) for w in range(nplans)])
+    desc = np.zeros(nplans, dtype=_lib.PLAN_DESC)
+    smp = np.zeros((nplans, n, 2), dtype=np.int16)
+    hd = np.zeros((nplans, n), dtype=np.uint8)
+    for p in range(nplans):
+        free = np.argwhere(ogs[p] == 0)
+        rng = np.random.default_rng(300 + p)
+        smp[p] = free[rng.integers(0, len(free), n)]
+        hd[p] = rng.integers(0, nh, n)
+        desc[p]["world"] = p
+        desc[p]["start_x"], desc[p]["start_y"], desc[p]["goal_x"], desc[p]["goal_y"] = *free[2], *free[-2]
+        desc[p]["reserved"][0], desc[p]["reserved"][1] = p % nh, (5 * p) % nh
+    cfg = _lib.plan2_cfg(_lib.MODEL_DUBINS, True, True, 20.0, nh, 3.0, 1.0)
+    ctx.set_grids(ogs)
+    pts, head, cost, elen, par, st = ctx.plan2(cfg, desc, n, samples=smp, heads=hd)
+    grids = _lib.pack_grids_host(ogs) if bits else ogs
+    cap = 64
+    got = ctx.plan2_worlds(cfg, grids, W, H, desc, n, samples=smp, heads=hd, bits=bits, trees=True, paths=True, path_cap=cap, chunk=4)
+    assert np.array_equal(got["pts"], pts) and np.array_equal(got["head"], head) and np.array_equal(got["parent"], par)
+    assert np.array_equal(got["cost"].view(np.int64), cost.view(np.int64)) and np.array_equal(got["elen"].view(np.int64), elen.view(np.int64))
+    names = list(_lib.STAT2_NAMES)
+    keep = [i for i, nm in enumerate(names) if nm != "checks"]       # edge tests saved by the goal connection's pruning depend on timing
+    assert np.array_equal(got["stats"][:, keep], st[:, keep])
+    for p in range(nplans):
+        v = int(st[p, names.index("vgoal")])
+        chain = [v]
+        while chain[-1] > 0:
+            chain.append(int(par[p, chain[-1]]))
+        chain = chain[::-1]
+        assert got["len"][p] == len(chain)
+        if len(chain) <= cap:
+            assert list(got["path"][p, :len(chain)]) == chain and (got["path"][p, len(chain):] == -1).all()
+            assert np.array_equal(got["xy"][p, :len(chain)], pts[p, chain]) and np.array_equal(got["path_head"][p, :len(chain)], head[p, chain])
+            assert (got["path_head"][p, len(chain):] == 255).all()
+        assert got["path_cost"][p].view(np.int64) == cost[p, v].view(np.int64)
+    # paths only, seeds instead of sample arrays, default chunking: same statistics as the resident seed-mode call
+    from rrtplanner_b200 import batch
+    states = batch.seed_states(np.arange(nplans) + 7)
+    want = ctx.plan2(cfg, desc, n, states=states, heads=hd)
+    got2 = ctx.plan2_worlds(cfg, grids, W, H, desc, n, states=states, heads=hd, bits=bits, trees=False, paths=True, path_cap=cap)
+    assert np.array_equal(got2["stats"][:, keep], want[5][:, keep])
 
 
 def test_bad_arguments_raise(ctx):
