@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <vector>
 
 #include "common.cuh"
@@ -123,18 +124,22 @@ struct DevBuf {
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
-// one stage of the chunked upload / plan / download pipeline of rrtk_ctx_plan_worlds
+// One stage of the chunked upload / plan / download pipeline of rrtk_ctx_plan_worlds2 / rrtk_ctx_plan2_worlds.
+// Streams: ONE preparation stream for all chunks (uploads, packing, free-space index, sampler) and ONE output stream
+// (path extraction, downloads), both of the highest priority so that their short kernels get SM resources ahead of the
+// pending plan blocks (a plan kernel leaves no free registers on an SM it fills), plus one plan stream per slot.  That is
+// 2 + kPipeSlots streams: with the context's own stream they fit the 8 hardware queues of a default CUDA context
+// (CUDA_DEVICE_MAX_CONNECTIONS), where streams that share a queue serialise behind each other -- with 16 streams a chunk's
+// plan kernel waited for the chunk four before it to finish entirely (RRTK_PIPE_TRACE=1 prints the time stamps).
 struct PipeSlot {
-    cudaStream_t stream = nullptr;              // plan kernel, path extraction, downloads
-    cudaStream_t prep = nullptr;                // uploads, packing, free-space index, sampler: highest priority, so that the next chunk's
-                                                // (short) preparation kernels get SM slots ahead of the pending plan blocks of the running chunks
-    cudaEvent_t ready = nullptr, done = nullptr;
+    cudaStream_t stream = nullptr;              // the chunk's plan kernel
+    cudaEvent_t ready = nullptr, planned = nullptr, done = nullptr;   // inputs on the device / plan kernel finished / outputs on the host
     DevBuf og, bits, rowcum, plans, samples, state, balls, pts, cost, parent, stats, ell;
     DevBuf path, xy, len, pcost;                // path records (RRTK_OUT_PATHS)
     DevBuf heads, head_out, elen, scratch2, phead;   // K8 chunks (rrtk_ctx_plan2_worlds)
     std::vector<rrtk_plan_desc> desc;
 };
-constexpr int kPipeSlots = 8;
+constexpr int kPipeSlots = 5;
 
 struct rrtk_ctx {
     cudaStream_t stream = nullptr;
@@ -149,6 +154,7 @@ struct rrtk_ctx {
     int dt_R = 0, dt_NH = 0;
     double dt_rho = 0.0;
     PipeSlot pipe[kPipeSlots];
+    cudaStream_t pipe_prep = nullptr, pipe_post = nullptr;
 };
 
 extern "C" {
@@ -430,10 +436,12 @@ int rrtk_destroy(rrtk_ctx *c)
         DevBuf *pb[] = {&p.og, &p.bits, &p.rowcum, &p.plans, &p.samples, &p.state, &p.balls, &p.pts, &p.cost, &p.parent, &p.stats, &p.ell};
         for (DevBuf *b : pb) b->release();
         if (p.stream) cudaStreamDestroy(p.stream);
-        if (p.prep) cudaStreamDestroy(p.prep);
         if (p.ready) cudaEventDestroy(p.ready);
+        if (p.planned) cudaEventDestroy(p.planned);
         if (p.done) cudaEventDestroy(p.done);
     }
+    if (c->pipe_prep) cudaStreamDestroy(c->pipe_prep);
+    if (c->pipe_post) cudaStreamDestroy(c->pipe_post);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return RRTK_OK;
@@ -568,6 +576,37 @@ int rrtk_ctx_plan(rrtk_ctx *c, int kind, const rrtk_plan_desc *h_plans, int npla
 // one chunk overlap the kernels of its neighbours.  Plans must be ordered by world index.
 // flags: RRTK_IN_BITS (h_grids = tiled bit grids, 1/8 of the bytes), RRTK_OUT_TREES, RRTK_OUT_PATHS (path records of
 // path_cap entries per plan); statistics always come back.
+// streams and events of one pipeline slot (and the two shared streams), created on first use; every pipelined call drains all of
+// them before it returns, so the slot's buffers may be regrown right after this
+static int pipe_slot_init(rrtk_ctx *c, PipeSlot &s)
+{
+    if (!c->pipe_prep) {
+        int lo = 0, hi = 0;
+        RRTK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));                    // hi = numerically lowest = greatest priority
+        RRTK_CUDA(cudaStreamCreateWithPriority(&c->pipe_prep, cudaStreamNonBlocking, hi));
+        RRTK_CUDA(cudaStreamCreateWithPriority(&c->pipe_post, cudaStreamNonBlocking, hi));
+    }
+    if (!s.stream) {
+        RRTK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        RRTK_CUDA(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming));
+        RRTK_CUDA(cudaEventCreateWithFlags(&s.planned, cudaEventDisableTiming));
+        RRTK_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    return RRTK_OK;
+}
+
+static void pipe_drain(rrtk_ctx *c, int *status)
+{
+    auto sync = [&](cudaStream_t st) {
+        if (!st) return;
+        const cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess && *status == RRTK_OK) *status = cuda_fail(e, "cudaStreamSynchronize");
+    };
+    sync(c->pipe_prep);
+    for (PipeSlot &s : c->pipe) sync(s.stream);
+    sync(c->pipe_post);
+}
+
 int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworlds, int W, int H, const rrtk_plan_desc *h_plans,
                           int nplans, int n, double r_rewire, double r_goal, const int16_t *h_samples, const uint64_t *h_state,
                           const double *h_balls, int flags, int path_cap, int16_t *h_pts, double *h_cost, int32_t *h_parent,
@@ -659,16 +698,7 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
     const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
     for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
         PipeSlot &s = c->pipe[k];
-        if (!s.stream) {
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);                          // hi = numerically lowest = greatest priority
-            if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags") ||
-                !cuda_ok(cudaStreamCreateWithPriority(&s.prep, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority") ||
-                !cuda_ok(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming), "cudaEventCreateWithFlags") ||
-                !cuda_ok(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreateWithFlags")) break;
-        }
-        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");       // buffers may be regrown below
-        cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
+        if (!rrtk_ok(pipe_slot_init(c, s))) break;
         bool ok = rrtk_ok(s.bits.reserve(words * 4 * max_nw)) && rrtk_ok(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw)) &&
                   rrtk_ok(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m)) && rrtk_ok(s.samples.reserve(max_m * n * 4)) &&
                   rrtk_ok(s.state.reserve(max_m * 32)) && rrtk_ok(s.pts.reserve(rows1 * max_m * 4)) &&
@@ -680,10 +710,24 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
             ok = rrtk_ok(s.path.reserve(max_m * path_cap * 4)) && rrtk_ok(s.xy.reserve(max_m * path_cap * 4)) &&
                  rrtk_ok(s.len.reserve(max_m * 4)) && rrtk_ok(s.pcost.reserve(max_m * 8));
     }
+    // RRTK_PIPE_TRACE=1 (diagnosis): device-side time stamps of every chunk's stages, printed to stderr after the call
+    const bool trace = getenv("RRTK_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto stamp = [&](cudaStream_t on) {
+        if (!trace) return;
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, on);
+        tev.push_back(e);
+    };
+    const auto host_t0 = std::chrono::steady_clock::now();
+    std::vector<double> host_ms;
     for (size_t ci = 0; ci + 1 < starts.size() && status == RRTK_OK; ++ci) {
         const int p0 = starts[ci], m = starts[ci + 1] - starts[ci];
         PipeSlot &s = c->pipe[ci % kPipeSlots];
-        cudaStream_t st = s.prep;                                                 // preparation first (see PipeSlot), then the plan stream
+        cudaStream_t st = c->pipe_prep;                                           // preparation first (see PipeSlot), then the plan stream
+        if (trace) host_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count());
+        stamp(st);                                                                // [0] preparation of the chunk begins
         if (ci >= (size_t)kPipeSlots && !cuda_ok(cudaStreamWaitEvent(st, s.done, 0), "cudaStreamWaitEvent")) break;   // the slot's last chunk still reads these buffers
         const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
         const uint8_t *src = static_cast<const uint8_t *>(h_grids) + grid_bytes * w0;
@@ -707,12 +751,18 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
         if (kind == RRTK_INFORMED && h_balls &&
             !cuda_ok(cudaMemcpyAsync(s.balls.p, h_balls + (size_t)p0 * n * 2, (size_t)m * n * 16, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(balls)")) break;
         if (!cuda_ok(cudaEventRecord(s.ready, st), "cudaEventRecord")) break;
+        stamp(st);                                                                // [1] inputs ready
         st = s.stream;
         if (!cuda_ok(cudaStreamWaitEvent(st, s.ready, 0), "cudaStreamWaitEvent")) break;
+        stamp(st);                                                                // [2] plan stream free and inputs ready
         if (!rrtk_ok(rrtk_plan_batch(kind, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, r_rewire, r_goal,
                                      s.samples.as<int16_t>(), (kind == RRTK_INFORMED && h_balls) ? s.balls.as<double>() : nullptr,
                                      s.pts.as<int16_t>(), s.cost.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(),
                                      s.ell.as<double>(), 0, st))) break;
+        stamp(st);                                                                // [3] plan kernel done
+        if (!cuda_ok(cudaEventRecord(s.planned, st), "cudaEventRecord")) break;
+        st = c->pipe_post;                                                        // outputs: extraction and downloads, high priority
+        if (!cuda_ok(cudaStreamWaitEvent(st, s.planned, 0), "cudaStreamWaitEvent")) break;
         bool ok = true;
         if (out_paths) {
             ok = rrtk_ok(paths_xy_launch(s.parent.as<int32_t>(), s.pts.as<int16_t>(), s.cost.as<double>(), s.stats.as<int64_t>(), m, n, path_cap,
@@ -731,12 +781,20 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
         }
         if (ok) cuda_ok(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(stats)");
         cuda_ok(cudaEventRecord(s.done, st), "cudaEventRecord");
+        stamp(st);                                                                // [4] results on the host
     }
-    for (PipeSlot &s : c->pipe)
-        if (s.stream) {
-            cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
-            cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
+    pipe_drain(c, &status);
+    if (trace && status == RRTK_OK && tev.size() == 5 * (starts.size() - 1)) {
+        const double host_end = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count();
+        fprintf(stderr, "rrtk pipe trace (ms after the first chunk's preparation began; host = when the host enqueued the chunk; call returned at host %.2f)\n", host_end);
+        for (size_t ci = 0; ci + 1 < starts.size(); ++ci) {
+            float t[5];
+            for (int k = 0; k < 5; ++k) cudaEventElapsedTime(&t[k], tev[0], tev[5 * ci + k]);
+            fprintf(stderr, "  chunk %2zu plans %5d..%5d host %6.2f | prep %6.2f ready %6.2f | plan start %6.2f end %6.2f | out %6.2f\n", ci, starts[ci],
+                    starts[ci + 1], host_ms[ci], t[0], t[1], t[2], t[3], t[4]);
         }
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
     return status;
 }
 
@@ -1255,16 +1313,7 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
     const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
     for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
         PipeSlot &s = c->pipe[k];
-        if (!s.stream) {
-            int lo = 0, hi = 0;
-            cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            if (!cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "cudaStreamCreateWithFlags") ||
-                !cuda_ok(cudaStreamCreateWithPriority(&s.prep, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority") ||
-                !cuda_ok(cudaEventCreateWithFlags(&s.ready, cudaEventDisableTiming), "cudaEventCreateWithFlags") ||
-                !cuda_ok(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming), "cudaEventCreateWithFlags")) break;
-        }
-        cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
-        cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
+        if (!rrtk_ok(pipe_slot_init(c, s))) break;
         bool ok = rrtk_ok(s.bits.reserve(words * 4 * max_nw)) && rrtk_ok(s.rowcum.reserve((size_t)(W + 1) * 4 * max_nw)) &&
                   rrtk_ok(s.plans.reserve(sizeof(rrtk_plan_desc) * max_m)) && rrtk_ok(s.samples.reserve(max_m * n * 4)) &&
                   rrtk_ok(s.state.reserve(max_m * 32)) && rrtk_ok(s.heads.reserve(max_m * n)) && rrtk_ok(s.pts.reserve(rows1 * max_m * 4)) &&
@@ -1281,7 +1330,7 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
     for (size_t ci = 0; ci + 1 < starts.size() && status == RRTK_OK; ++ci) {
         const int p0 = starts[ci], m = starts[ci + 1] - starts[ci];
         PipeSlot &s = c->pipe[ci % kPipeSlots];
-        cudaStream_t st = s.prep;
+        cudaStream_t st = c->pipe_prep;
         if (ci >= (size_t)kPipeSlots && !cuda_ok(cudaStreamWaitEvent(st, s.done, 0), "cudaStreamWaitEvent")) break;
         const int w0 = h_plans[p0].world, w1 = h_plans[p0 + m - 1].world, nw = w1 - w0 + 1;
         const uint8_t *src = static_cast<const uint8_t *>(h_grids) + grid_bytes * w0;
@@ -1312,6 +1361,9 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
         if (!rrtk_ok(rrtk_plan2_batch(&use, s.bits.as<uint32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m, n, s.samples.as<int16_t>(),
                                       h_heads ? s.heads.as<uint8_t>() : nullptr, s.pts.as<int16_t>(), s.head_out.as<uint8_t>(), s.cost.as<double>(),
                                       s.elen.as<double>(), s.parent.as<int32_t>(), s.stats.as<int64_t>(), s.scratch2.p, 0, st))) break;
+        if (!cuda_ok(cudaEventRecord(s.planned, st), "cudaEventRecord")) break;
+        st = c->pipe_post;
+        if (!cuda_ok(cudaStreamWaitEvent(st, s.planned, 0), "cudaStreamWaitEvent")) break;
         bool ok = true;
         if (out_paths) {
             ok = rrtk_ok(paths_xy_launch(s.parent.as<int32_t>(), s.pts.as<int16_t>(), s.cost.as<double>(), s.stats.as<int64_t>(), m, n, path_cap,
@@ -1334,11 +1386,7 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
         if (ok) cuda_ok(cudaMemcpyAsync(h_stats + (size_t)p0 * RRTK_STAT_COUNT, s.stats.p, (size_t)m * RRTK_STAT_COUNT * 8, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(stats)");
         cuda_ok(cudaEventRecord(s.done, st), "cudaEventRecord");
     }
-    for (PipeSlot &s : c->pipe)
-        if (s.stream) {
-            cuda_ok(cudaStreamSynchronize(s.prep), "cudaStreamSynchronize");
-            cuda_ok(cudaStreamSynchronize(s.stream), "cudaStreamSynchronize");
-        }
+    pipe_drain(c, &status);
     if (status != RRTK_OK) return status;
     for (int p = 0; p < nplans; ++p)
         if (h_stats[(size_t)p * RRTK_STAT_COUNT + RRTK_STAT2_OVERFLOW]) {
