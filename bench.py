@@ -626,7 +626,7 @@ def dubins_bench(local: int, steps: int, cpu: bool, plans: int = DUB_PLANS, thre
         ctx.close()
         st_dev = db.out["stats"].cpu().numpy()
         rec["e2e"] = {"value": plans / t_pipe, "unit": "plans/s",
-                      "api": "rrtk_ctx_plan2_worlds (packed grids in, seed mode, path records out; chunks of one plan per SM on 8 pipeline slots), pinned host buffers",
+                      "api": "rrtk_ctx_plan2_worlds (packed grids in, seed mode, path records out; chunks of one plan per SM, five plan streams), pinned host buffers",
                       "h2d_bytes_per_step": int(plans * (bits_host.shape[1] * 4 + 64 + 32 + (N_ITER if model == "dubins" else 0))),
                       "d2h_bytes_per_step": int(plans * (cap * 9 + 12 + _lib.STAT_COUNT * 8)),
                       "matches_device_arm": bool(np.array_equal(r2["stats"][:, :3], st_dev[:, :3])),
@@ -950,7 +950,7 @@ def gpu_arm(args):
                "plans_per_step_per_gpu": Pe, "ms_per_step": 1000 * dt_paths / args.steps,
                "api": "rrtk_ctx_plan_worlds2(RRTK_IN_BITS | RRTK_OUT_PATHS) via rrtplanner_b200._lib.Context.plan_worlds2: tiled bit grids, plan "
                       "descriptors and PCG64 states up; path record (ids + points, cap %d; length; cost) and statistics of every plan down; "
-                      "chunks of %d plans on 8 rotating streams, pinned host buffers" % (PATH_CAP, args.e2e_chunk or 4 * sms),
+                      "chunks of %d plans on five plan streams between one preparation and one output stream, pinned host buffers" % (PATH_CAP, args.e2e_chunk or 4 * sms),
                "matches_device_arm": bool(same_paths), "host_packer_matches_device_packer": packer_ok,
                "trees_mode": {"value": Pe * world * args.steps / dt_trees, "unit": "plans/s", "ms_per_step": 1000 * dt_trees / args.steps,
                               "h2d_bytes_per_step": int(Pe * (W * H + 64 + 32)),
