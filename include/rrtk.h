@@ -361,9 +361,11 @@ int rrtk_ctx_plan(rrtk_ctx *ctx, int kind, const rrtk_plan_desc *h_plans, int np
                   int64_t *h_stats, double *h_ell_c);
 
 /* rrtk_ctx_set_grids + rrtk_ctx_plan in one call, pipelined: plans (ordered by world index) are
- * processed in chunks of chunk_plans (0 = two plan blocks per SM, the first chunk one per SM) on rotating streams, so the upload of one chunk's
- * grids and the download of another's trees overlap the kernels; give pinned host buffers for the
- * copies to be asynchronous.  The worlds are not kept in the context afterwards. */
+ * processed in chunks of chunk_plans (0 = two plan blocks per SM, the first chunk one per SM) on rotating plan streams
+ * between one preparation and one output stream, so the upload of one chunk's grids and the download of another's trees
+ * overlap the kernels; give pinned host buffers for the copies to be asynchronous.  The worlds are not kept in the
+ * context afterwards.  Seed mode (h_state) on a world without a free cell is an error as in rrtk_ctx_plan
+ * (RRTK_ERR_INVALID; found on the device, so reported when the call returns: the outputs then mean nothing). */
 int rrtk_ctx_plan_worlds(rrtk_ctx *ctx, int kind, const uint8_t *h_og, int nworlds, int W, int H,
                          const rrtk_plan_desc *h_plans, int nplans, int n, double r_rewire, double r_goal,
                          const int16_t *h_samples, const uint64_t *h_state, const double *h_balls,
@@ -379,7 +381,7 @@ int rrtk_ctx_plan_worlds(rrtk_ctx *ctx, int kind, const uint8_t *h_og, int nworl
  *                   plan in h_path / h_xy, h_len, h_path_cost): ~2 KB per plan instead of 16 B per tree row
  * h_stats always comes back.  Output pointers of a mode that is not requested may be NULL.  On an error after the first
  * copy was enqueued the call drains every stream before it returns, so no transfer is still writing into the caller's
- * buffers. */
+ * buffers.  RRTK_PIPE_TRACE=1 in the environment prints the device time stamps of every chunk's stages to stderr. */
 #define RRTK_IN_BITS 1
 #define RRTK_OUT_TREES 2
 #define RRTK_OUT_PATHS 4

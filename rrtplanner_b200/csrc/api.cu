@@ -155,6 +155,8 @@ struct rrtk_ctx {
     double dt_rho = 0.0;
     PipeSlot pipe[kPipeSlots];
     cudaStream_t pipe_prep = nullptr, pipe_post = nullptr;
+    int32_t *pin_nfree = nullptr;               // pinned: free cells per world of a pipelined call (seed mode checks them)
+    size_t pin_nfree_cap = 0;
 };
 
 extern "C" {
@@ -440,6 +442,7 @@ int rrtk_destroy(rrtk_ctx *c)
         if (p.planned) cudaEventDestroy(p.planned);
         if (p.done) cudaEventDestroy(p.done);
     }
+    if (c->pin_nfree) cudaFreeHost(c->pin_nfree);
     if (c->pipe_prep) cudaStreamDestroy(c->pipe_prep);
     if (c->pipe_post) cudaStreamDestroy(c->pipe_post);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -595,6 +598,27 @@ static int pipe_slot_init(rrtk_ctx *c, PipeSlot &s)
     return RRTK_OK;
 }
 
+static int pipe_nfree_reserve(rrtk_ctx *c, size_t nworlds)
+{
+    if (nworlds <= c->pin_nfree_cap) return RRTK_OK;
+    if (c->pin_nfree) cudaFreeHost(c->pin_nfree);
+    c->pin_nfree = nullptr; c->pin_nfree_cap = 0;
+    RRTK_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c->pin_nfree), nworlds * sizeof(int32_t), cudaHostAllocDefault));
+    c->pin_nfree_cap = nworlds;
+    return RRTK_OK;
+}
+
+// seed mode draws free[choice(nfree)] (rrt.py:240): the results of a plan on a world without a free cell mean nothing
+static int pipe_require_free_cells(const rrtk_ctx *c, const rrtk_plan_desc *h_plans, int nplans, const char *who)
+{
+    for (int p = 0; p < nplans; ++p)
+        if (c->pin_nfree[h_plans[p].world] <= 0) {
+            set_error("%s: world %d of plan %d has no free cell to sample", who, h_plans[p].world, p);
+            return RRTK_ERR_INVALID;
+        }
+    return RRTK_OK;
+}
+
 static void pipe_drain(rrtk_ctx *c, int *status)
 {
     auto sync = [&](cudaStream_t st) {
@@ -695,6 +719,7 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
         if (rc != RRTK_OK && status == RRTK_OK) status = rc;
         return rc == RRTK_OK;
     };
+    if (h_state) RRTK_TRY(pipe_nfree_reserve(c, (size_t)nworlds));
     const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
     for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
         PipeSlot &s = c->pipe[k];
@@ -738,6 +763,8 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
             if (!rrtk_ok(pack_launch(s.og.as<uint8_t>(), nw, W, H, s.bits.as<uint32_t>(), st))) break;
         }
         if (!rrtk_ok(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st))) break;
+        if (h_state && !cuda_ok(cudaMemcpy2DAsync(c->pin_nfree + w0, 4, s.rowcum.as<int32_t>() + W, (size_t)(W + 1) * 4, 4, nw, cudaMemcpyDeviceToHost, st),
+                                "cudaMemcpy2DAsync(nfree)")) break;
         s.desc.assign(h_plans + p0, h_plans + p0 + m);
         for (rrtk_plan_desc &d : s.desc) d.world -= w0;
         if (!cuda_ok(cudaMemcpyAsync(s.plans.p, s.desc.data(), sizeof(rrtk_plan_desc) * m, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(plans)")) break;
@@ -795,6 +822,7 @@ int rrtk_ctx_plan_worlds2(rrtk_ctx *c, int kind, const void *h_grids, int nworld
         }
     }
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    if (status == RRTK_OK && h_state) status = pipe_require_free_cells(c, h_plans, nplans, "rrtk_ctx_plan_worlds2");
     return status;
 }
 
@@ -1310,6 +1338,7 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
         if (rc != RRTK_OK && status == RRTK_OK) status = rc;
         return rc == RRTK_OK;
     };
+    if (h_state) RRTK_TRY(pipe_nfree_reserve(c, (size_t)nworlds));
     const size_t nslots = starts.size() - 1 < (size_t)kPipeSlots ? starts.size() - 1 : (size_t)kPipeSlots;
     for (size_t k = 0; k < nslots && status == RRTK_OK; ++k) {
         PipeSlot &s = c->pipe[k];
@@ -1347,6 +1376,8 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
             if (!cuda_ok(cudaMemcpyAsync(s.samples.p, h_samples + (size_t)p0 * n * 2, (size_t)m * n * 4, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(samples)")) break;
         } else {
             if (!rrtk_ok(free_rows_launch(s.bits.as<uint32_t>(), nw, W, H, s.rowcum.as<int32_t>(), st))) break;
+            if (!cuda_ok(cudaMemcpy2DAsync(c->pin_nfree + w0, 4, s.rowcum.as<int32_t>() + W, (size_t)(W + 1) * 4, 4, nw, cudaMemcpyDeviceToHost, st),
+                           "cudaMemcpy2DAsync(nfree)")) break;
             if (!cuda_ok(cudaMemcpyAsync(s.state.p, h_state + (size_t)p0 * 4, (size_t)m * 32, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(state)")) break;
             if (!rrtk_ok(sample_streams_launch(s.bits.as<uint32_t>(), s.rowcum.as<int32_t>(), W, H, s.plans.as<rrtk_plan_desc>(), m,
                                                s.state.as<uint64_t>(), n, s.samples.as<int16_t>(), di->optin, st))) break;
@@ -1388,6 +1419,7 @@ int rrtk_ctx_plan2_worlds(rrtk_ctx *c, const rrtk_plan2_cfg *cfg, const void *h_
     }
     pipe_drain(c, &status);
     if (status != RRTK_OK) return status;
+    if (h_state) RRTK_TRY(pipe_require_free_cells(c, h_plans, nplans, "rrtk_ctx_plan2_worlds"));
     for (int p = 0; p < nplans; ++p)
         if (h_stats[(size_t)p * RRTK_STAT_COUNT + RRTK_STAT2_OVERFLOW]) {
             set_error("plan %d: a rewire-radius set exceeded the kernel's list (1024 vertices); reduce r_rewire", p);

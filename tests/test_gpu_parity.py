@@ -645,3 +645,11 @@ def test_world_without_free_cells_cannot_be_sampled(ctx):
     db.set_plans(batch.make_desc([0], [[1, 1]], [[2, 2]]))
     with pytest.raises(ValueError, match="no free cell"):
         db.seed_samples([5])
+    # the pipelined calls find out on the device (the free-cell index is built there) and report after the call
+    desc2 = batch.make_desc([0, 1], [[1, 1], [3, 4]], [[2, 2], [3, 4]])
+    with pytest.raises(ValueError, match="no free cell"):
+        ctx.plan_worlds2(1, full, 40, 40, desc2, 10, 5.0, states=batch.seed_states([5, 6]))
+    ctx.plan_worlds2(1, full, 40, 40, desc2[1:], 10, 5.0, states=batch.seed_states([6]))          # world 1 alone is fine
+    ctx.plan_worlds2(1, full, 40, 40, desc2, 4, 5.0, samples=np.zeros((2, 4, 2), dtype=np.int16))  # explicit streams stay legal
+    with pytest.raises(ValueError, match="no free cell"):
+        ctx.plan2_worlds(_lib.plan2_cfg(_lib.MODEL_EUCLID, True, True, 5.0), full, 40, 40, desc2, 10, states=batch.seed_states([5, 6]))
