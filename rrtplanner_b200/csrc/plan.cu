@@ -11,18 +11,18 @@
 
 namespace rrtk {
 
-int scan_launch_standard(const PlanParams &, int, int, int, size_t, cudaStream_t);
-int scan_launch_star(const PlanParams &, int, int, int, size_t, cudaStream_t);
-int scan_launch_informed(const PlanParams &, int, int, int, size_t, cudaStream_t);
-int scan_occupancy_standard(int, int, size_t);
-int scan_occupancy_star(int, int, size_t);
-int scan_occupancy_informed(int, int, size_t);
+int scan_launch_standard(const PlanParams &, int, int, int, int, size_t, cudaStream_t);
+int scan_launch_star(const PlanParams &, int, int, int, int, size_t, cudaStream_t);
+int scan_launch_informed(const PlanParams &, int, int, int, int, size_t, cudaStream_t);
+int scan_occupancy_standard(int, int, int, size_t);
+int scan_occupancy_star(int, int, int, size_t);
+int scan_occupancy_informed(int, int, int, size_t);
 int wide_plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
                      const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int wide_plan_footprint(int, int, int, int, int, int, int, int *, int *);
 
 struct ScanShape {
-    int T, K, hit_words, tail_bytes, sbits, steps_max, list_cap, blocks_per_sm;
+    int T, K, hit_words, tail_bytes, sbits, steps_max, list_cap, blocks_per_sm, two_per_sm;
     size_t smem;
 };
 
@@ -69,14 +69,18 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
         s.smem += (size_t)4 * (s.hit_words - 1) * s.K * T + (((size_t)s.tail_bytes * s.K * T + 3) & ~(size_t)3) + (size_t)2 * (T / 32) * s.list_cap;   // membership words, one list per warp
     s.smem = (s.smem + 15) & ~(size_t)15;
     if (s.smem > (size_t)optin - 2048) return false;
+    // 256-thread blocks whose shared memory admits at most two per SM run the build that is bounded for two (128 registers)
+    s.two_per_sm = (T == 256 && (size_t)sm_smem / (s.smem + 2048) <= 2) ? 1 : 0;
     // resident blocks per SM: asked of the runtime for the kernel that will run (no device -> the static estimate)
-    int b = kind == RRTK_STANDARD ? scan_occupancy_standard(T, s.K, s.smem) : kind == RRTK_STAR ? scan_occupancy_star(T, s.K, s.smem)
-                                                                                                : scan_occupancy_informed(T, s.K, s.smem);
+    int b = kind == RRTK_STANDARD ? scan_occupancy_standard(T, s.K, s.two_per_sm, s.smem)
+            : kind == RRTK_STAR   ? scan_occupancy_star(T, s.K, s.two_per_sm, s.smem)
+                                  : scan_occupancy_informed(T, s.K, s.two_per_sm, s.smem);
     if (b <= 0) {
         const int by_smem = (int)((size_t)sm_smem / (s.smem + 1024 + 1024));   // + static + per-block reservation
         const int by_threads = 2048 / T;
         b = by_smem < by_threads ? by_smem : by_threads;
-        const int by_regs = 65536 / (T * (65536 / (T * scan_min_blocks(T)) / 8 * 8));
+        const int mb = s.two_per_sm ? 2 : scan_min_blocks(T);
+        const int by_regs = 65536 / (T * (65536 / (T * mb) / 8 * 8));
         if (b > by_regs) b = by_regs;
     }
     s.blocks_per_sm = b < 1 ? 1 : (b > 32 ? 32 : b);
@@ -129,9 +133,9 @@ int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_
     P.tail_bytes = s.tail_bytes;
     P.steps_max = s.steps_max;
     switch (kind) {
-        case RRTK_STANDARD: return scan_launch_standard(P, nplans, s.T, s.K, s.smem, st);
-        case RRTK_STAR: return scan_launch_star(P, nplans, s.T, s.K, s.smem, st);
-        default: return scan_launch_informed(P, nplans, s.T, s.K, s.smem, st);
+        case RRTK_STANDARD: return scan_launch_standard(P, nplans, s.T, s.K, s.two_per_sm, s.smem, st);
+        case RRTK_STAR: return scan_launch_star(P, nplans, s.T, s.K, s.two_per_sm, s.smem, st);
+        default: return scan_launch_informed(P, nplans, s.T, s.K, s.two_per_sm, s.smem, st);
     }
 }
 

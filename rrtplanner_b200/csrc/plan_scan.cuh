@@ -73,8 +73,11 @@ struct ScanCfg {
     static constexpr int kMinBlocks = (T <= 64) ? 12 : (T <= 128) ? RRTK_MINB128 : (T <= 160) ? 5 : (T <= 256) ? RRTK_MINB256 : 1;
 };
 
-template <int KIND, int K, int T>
-__global__ void __launch_bounds__(T, ScanCfg<KIND, K, T>::kMinBlocks) plan_scan_kernel(PlanParams P)
+// MB: resident blocks per SM the registers are bounded for.  Blocks of 256 threads come in two builds: 3 per SM (80 registers) and,
+// for trees so large that shared memory admits only two blocks anyway (cfg4: n = 20000), 2 per SM with 128 registers -- the
+// informed kernel spills at 80 (cfg4: 2.27 k -> 2.63 k plans/s).
+template <int KIND, int K, int T, int MB = ScanCfg<KIND, K, T>::kMinBlocks>
+__global__ void __launch_bounds__(T, MB) plan_scan_kernel(PlanParams P)
 {
     constexpr int NW = T / 32;
     static_assert(T % 32 == 0 && K <= 16 && K >= 1, "block shape");
