@@ -126,7 +126,10 @@ __device__ __forceinline__ void pcg_jump(Pcg64 &g, unsigned long long delta)
     g.hi = st.hi; g.lo = st.lo;
 }
 
-constexpr int kSampleThreads = 128;
+#ifndef RRTK_SAMPLE_THREADS
+#define RRTK_SAMPLE_THREADS 256
+#endif
+constexpr int kSampleThreads = RRTK_SAMPLE_THREADS;
 constexpr int kRawSlack = 62;          // raw 32-bit values generated beyond n; more rejections than that -> sequential path
 
 // one block per plan: the generator's raw outputs in parallel slices, Lemire's rejection as a compaction, then
