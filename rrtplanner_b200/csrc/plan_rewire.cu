@@ -138,7 +138,8 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
     return v;
 }
 
-template <int MODEL, int T>
+// INF: the informed sampling rule, compiled in only where it is asked for (the plain planners keep their registers)
+template <int MODEL, int T, bool INF>
 __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kernel(Plan2Params P)
 {
     constexpr int NW = T / 32;
@@ -190,15 +191,16 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
     double *gcost = P.gcost + (size_t)plan * (n + 1);
     uint16_t *queue = P.queue + (size_t)plan * (n + 1);
     uint16_t *sol = P.sol + (size_t)plan * (n + 1);
-    const double2 *balls = (P.informed && P.balls) ? P.balls + (size_t)plan * n : nullptr;
-    double *ell_c = (P.informed && P.ell_c) ? P.ell_c + (size_t)plan * (n + 1) : nullptr;
+    const double2 *balls = (INF && P.balls) ? P.balls + (size_t)plan * n : nullptr;
+    double *ell_c = (INF && P.ell_c) ? P.ell_c + (size_t)plan * (n + 1) : nullptr;
+    const double rot[4] = {INF ? pd.rot[0] : 0.0, INF ? pd.rot[1] : 0.0, INF ? pd.rot[2] : 0.0, INF ? pd.rot[3] : 0.0};
 
     // ---- initialise ---------------------------------------------------------------------------------
     for (int v = tid; v <= n; v += T) {
         spts[v] = RRTK_FAR_VERTEX; shead[v] = 255; first[v] = kNil; next[v] = kNil;
         o_pts[v] = make_short2(-32768, -32768); o_head[v] = 255;
         cost[v] = CUDART_INF; elen[v] = CUDART_INF; parent[v] = -1;
-        if (ell_c) ell_c[v] = CUDART_NAN;
+        if (INF && ell_c) ell_c[v] = CUDART_NAN;
     }
     if (MODEL == RRTK_MODEL_DUBINS) {
         const double dth = DM_TWO_PI / (double)P.NH;
@@ -243,10 +245,10 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
     for (int it = 0; it < n; ++it) {
         const short2 sm = samples[it];
         int qx = sm.x, qy = sm.y;
-        if (P.informed && s_nsol > 0) {          // uniform: the list and the budget only change before a round's last barrier
+        if (INF && s_nsol > 0) {                 // uniform: the list and the budget only change before a round's last barrier
             if (!balls) break;                    // probe run
             const double c = s_cb;
-            ellipse_sample(P.W, P.H, pd.rot, pd.start_x, pd.start_y, pd.goal_x, pd.goal_y, c, balls[it], qx, qy);   // rrt.py:699-700
+            ellipse_sample(P.W, P.H, rot, pd.start_x, pd.start_y, pd.goal_x, pd.goal_y, c, balls[it], qx, qy);   // rrt.py:699-700
             if (tid == 0 && ell_c) ell_c[j] = c;                                                                     // rrt.py:701
             ++ell_iters;
         }
@@ -459,7 +461,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
             if (wslot < 0) elen[j] = s_l0;
             next[j] = first[vbest]; first[vbest] = (uint16_t)j;
             s_stat[S2_ACCEPTED] += 1; s_stat[S2_RING] += m;
-            if (P.informed && __dsqrt_rn((double)dist2(pnew, pd.goal_x, pd.goal_y)) < P.r_goal) {      // rrt.py:744-745
+            if (INF && __dsqrt_rn((double)dist2(pnew, pd.goal_x, pd.goal_y)) < P.r_goal) {      // rrt.py:744-745
                 if (s_nsol == 0) s_first = it;
                 sol[s_nsol] = (uint16_t)j;
                 s_nsol = s_nsol + 1;
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(T, RRTK_K8_BLOCK_THREADS / T) plan_rewire_kern
                 }
             }
         }
-        if (P.informed && warp == 0) {
+        if (INF && warp == 0) {
             // least_cost over the solution vertices (rrt.py:627-633: first minimum in list order) with the costs as they stand after
             // this round's rewires, + that vertex's distance to the goal (rrt.py:697-698): the budget of the next ellipse
             __syncwarp();
@@ -663,13 +665,19 @@ size_t plan2_scratch_bytes(int nplans, int n)
     return (size_t)nplans * (n + 1) * (sizeof(double) + 2 * sizeof(uint16_t)) + 16;
 }
 
+template <int MODEL, int T, bool INF>
+static int plan2_launch_ti(const Plan2Params &P, int nplans, size_t smem, cudaStream_t st)
+{
+    RRTK_CUDA(cudaFuncSetAttribute(plan_rewire_kernel<MODEL, T, INF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    plan_rewire_kernel<MODEL, T, INF><<<nplans, T, smem, st>>>(P);
+    RRTK_CUDA(cudaGetLastError());
+    return RRTK_OK;
+}
+
 template <int MODEL, int T>
 static int plan2_launch_t(const Plan2Params &P, int nplans, size_t smem, cudaStream_t st)
 {
-    RRTK_CUDA(cudaFuncSetAttribute(plan_rewire_kernel<MODEL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    plan_rewire_kernel<MODEL, T><<<nplans, T, smem, st>>>(P);
-    RRTK_CUDA(cudaGetLastError());
-    return RRTK_OK;
+    return P.informed ? plan2_launch_ti<MODEL, T, true>(P, nplans, smem, st) : plan2_launch_ti<MODEL, T, false>(P, nplans, smem, st);
 }
 
 int plan2_footprint(int n, int threads, int optin, int sm_smem, int *smem_bytes, int *blocks_per_sm)
