@@ -17,6 +17,8 @@ int scan_launch_informed(const PlanParams &, int, int, int, int, size_t, cudaStr
 int scan_occupancy_standard(int, int, int, size_t);
 int scan_occupancy_star(int, int, int, size_t);
 int scan_occupancy_informed(int, int, int, size_t);
+int grid_launch(int, const PlanParams &, int, size_t, cudaStream_t);
+int grid_occupancy(int, size_t);
 int wide_plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
                      const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int wide_plan_footprint(int, int, int, int, int, int, int, int *, int *);
@@ -37,6 +39,62 @@ static int env_int(const char *name, int dflt)
 #define RRTK_MINB128 7
 #endif
 static int scan_min_blocks(int T) { return T <= 64 ? 12 : T <= 128 ? RRTK_MINB128 : T <= 160 ? 5 : T <= 256 ? 3 : 1; }
+
+// ---- the bucket form (plan_grid.cuh): RRTStandard / RRTStar whose tree entries fit one word ---------------------------------
+struct GridShape {
+    int xb, yb, bshift, bshy, nbx, nby, rad, list_cap, blocks_per_sm;
+    uint32_t near_ok2;
+    size_t smem;
+};
+
+static int bits_for(int v) { int b = 0; while ((1 << b) <= v) ++b; return b; }   // bits that hold 0 .. v
+
+static bool grid_shape(int kind, int W, int H, int n, double r_rewire, int threads, int optin, int sm_smem, GridShape *out)
+{
+    const char *impl = getenv("RRTK_PLAN_IMPL");
+    if (impl && (impl[0] == 'w' || impl[0] == 's')) return false;
+#ifndef RRTK_GRID_DEFAULT
+    if (!(impl && impl[0] == 'g')) return false;                               // opt-in: RRTK_PLAN_IMPL=grid
+#endif
+    if (kind != RRTK_STANDARD && kind != RRTK_STAR) return false;
+    if (threads != 0 && threads != 128) return false;
+    if (env_int("RRTK_PLAN_K", 8) != 8 || env_int("RRTK_PLAN_T", 0) != 0) return false;
+    if (n < 2048 || n >= 5120) {                                               // the range plan_scan.cuh runs with 128 threads
+        if (!(impl && impl[0] == 'g' && n <= 60000)) return false;              // forced (tests): any size that fits
+    }
+    GridShape g;
+    g.xb = bits_for(W - 1); g.yb = bits_for(H - 1);
+    const int ib = 32 - g.xb - g.yb;
+    if (ib < 1 || ib > 31 || (long long)n >= (1ll << ib) - 1) return false;    // ids 0 .. n, all ones = an empty slot
+    // buckets: 32 cells in x (a sample reads ~4 runs of slots), 4 cells in y (a run covers just the y range it needs);
+    // coarser while there would be more than 2048 of them (cfg3: 16 x 128)
+    g.bshift = env_int("RRTK_GRID_BSX", 5); g.bshy = env_int("RRTK_GRID_BSY", 2);
+    for (;;) {
+        g.nbx = (W + (1 << g.bshift) - 1) >> g.bshift; g.nby = (H + (1 << g.bshy) - 1) >> g.bshy;
+        if (g.nbx * g.nby <= 2048) break;
+        if (g.bshy < g.bshift) ++g.bshy; else ++g.bshift;
+    }
+    if (g.nbx * g.nby + 1 > n) return false;                                   // the prologue's counters live in the entry array
+    const double r = kind == RRTK_STAR ? (r_rewire > 0.0 ? r_rewire : 0.0) : 0.0;
+    double rad = ceil(r);
+    if (rad < (double)(1 << g.bshift)) rad = (double)(1 << g.bshift);          // near: look at least one x bucket around
+    if (rad > 32768.0) rad = 32768.0;
+    g.rad = (int)rad;
+    g.near_ok2 = (uint32_t)(rad * rad);
+    int cap = env_int("RRTK_PLAN_CAP", 256);
+    const int need = (n + 1 + 31) & ~31;
+    g.list_cap = kind == RRTK_STANDARD ? 0 : (cap < need ? cap : need);
+    g.smem = (size_t)4 * ((n + 1 + 31) & ~31) + (size_t)4 * 4 * g.list_cap + (((size_t)2 * (g.nbx * g.nby + 1) + 15) & ~(size_t)15);
+    if (g.smem > (size_t)optin - 4096) return false;
+    int b = grid_occupancy(kind, g.smem);
+    if (b <= 0) {
+        b = (int)((size_t)sm_smem / (g.smem + 3072));
+        if (b > 7) b = 7;
+    }
+    g.blocks_per_sm = b < 1 ? 1 : b;
+    *out = g;
+    return true;
+}
 
 static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, int sm_smem, ScanShape *out)
 {
@@ -90,6 +148,12 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
 
 int plan_footprint(int kind, int W, int H, int n, int threads, int optin, int sm_smem, int *smem_bytes, int *blocks_per_sm)
 {
+    GridShape g;
+    if (grid_shape(kind, W, H, n, 0.0, threads, optin, sm_smem, &g)) {
+        if (smem_bytes) *smem_bytes = (int)g.smem;
+        if (blocks_per_sm) *blocks_per_sm = g.blocks_per_sm;
+        return RRTK_OK;
+    }
     ScanShape s;
     if (!scan_shape(kind, W, H, n, threads, optin, sm_smem, &s))
         return wide_plan_footprint(kind, W, H, n, threads == 160 || threads == 512 ? 0 : threads, optin, sm_smem, smem_bytes, blocks_per_sm);
@@ -107,8 +171,10 @@ int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_
         set_error("unknown planner kind %d", kind);
         return RRTK_ERR_INVALID;
     }
+    GridShape g;
+    const bool use_grid = grid_shape(kind, W, H, n, r_rewire, threads, optin, sm_smem, &g);
     ScanShape s;
-    if (!scan_shape(kind, W, H, n, threads, optin, sm_smem, &s))
+    if (!use_grid && !scan_shape(kind, W, H, n, threads, optin, sm_smem, &s))
         return wide_plan_launch(kind, d_bits, W, H, d_plans, nplans, n, r_rewire, r_goal, d_samples, d_balls, d_pts, d_cost,
                                 d_parent, d_stats, d_ell_c, threads == 160 || threads == 512 ? 0 : threads, optin, sm_smem, st);
     PlanParams P;
@@ -127,6 +193,13 @@ int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_
     P.parent = d_parent;
     P.stats = reinterpret_cast<long long *>(d_stats);
     P.ell_c = d_ell_c;
+    if (use_grid) {
+        P.sbits = 0; P.hit_words = 0; P.tail_bytes = 0; P.steps_max = 0;
+        P.list_cap = g.list_cap;
+        P.g_xb = g.xb; P.g_yb = g.yb; P.g_bshift = g.bshift; P.g_bshy = g.bshy; P.g_nbx = g.nbx; P.g_nby = g.nby; P.g_rad = g.rad; P.g_near_ok2 = g.near_ok2;
+        return grid_launch(kind, P, nplans, g.smem, st);
+    }
+    P.g_xb = P.g_yb = P.g_bshift = P.g_bshy = P.g_nbx = P.g_nby = P.g_rad = 0; P.g_near_ok2 = 0;
     P.sbits = s.sbits;
     P.list_cap = s.list_cap;
     P.hit_words = s.hit_words;

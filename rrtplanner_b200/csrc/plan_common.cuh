@@ -28,6 +28,12 @@ struct PlanParams {
     int hit_words;        // membership words per thread per sample (32 rows each)
     int tail_bytes;       // storage of the last of them: 1, 2 or 4 bytes (a full tree fills only its first 8 / 16 / 32 rows)
     int steps_max;        // quads per thread that hold tree vertices: ceil(ceil((n + 1) / T) / 4)
+    // bucket kernel only (plan_grid.cuh)
+    int g_xb, g_yb;       // bits of x and y in a tree entry  id << (xb + yb) | y << xb | x
+    int g_bshift, g_bshy; // buckets of 2^bshift x 2^bshy cells (x-major order: the buckets of one x form a run of slots)
+    int g_nbx, g_nby;     // buckets per axis
+    int g_rad;            // a sample reads the buckets that hold every cell within rad of it on both axes, rad >= r_rewire
+    uint32_t g_near_ok2;  // rad^2: a nearest vertex at most this far away is the nearest of the whole tree
 };
 
 // what the owner warp of a sample hands to the commit phase
