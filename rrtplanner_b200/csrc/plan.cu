@@ -1,10 +1,15 @@
 // K7 dispatch: which plan kernel runs a batch, with what block shape and shared-memory budget.
 //
-// Default: the packed-key scan kernel (plan_scan.cuh).  Its keys hold (d2 - |q|^2) * 2^sbits + row
-// in 32 bits, so it takes grids up to 2896 / 2048 / 1448 cells a side (1 / 2 / 3-4 membership words
-// per thread, i.e. n up to 32 / 64 / 128 vertices per thread); anything larger -- up to the
-// 16384-cell limit of the packed vertex format -- runs on the 32-bit-distance kernel of plan_wide.cu.
-// RRTK_PLAN_IMPL=wide|scan, RRTK_PLAN_K=<samples per round> override the choice for experiments.
+// 1. RRTStandard / RRTStar with 2048 <= n < 5120 whose tree entries fit one word (bits(W-1) + bits(H-1) + bits(n+1) <= 32,
+//    cfg3: 9 + 9 + 13): the bucket kernel (plan_grid.cuh) -- the tree in shared memory in bucket order of the samples,
+//    near / within from the buckets around a sample, 16 samples per round, 128 threads.
+// 2. Otherwise the packed-key scan kernel (plan_scan.cuh): brute-force scan over the whole tree.  Its keys hold
+//    (d2 - |q|^2) * 2^sbits + row in 32 bits, so it takes grids up to 2896 / 2048 / 1448 cells a side (1 / 2 / 3-4
+//    membership words per thread, i.e. n up to 32 / 64 / 128 vertices per thread).
+// 3. Anything larger -- up to the 16384-cell limit of the packed vertex format -- runs on the 32-bit-distance kernel of
+//    plan_wide.cu.
+// RRTK_PLAN_IMPL=grid|scan|wide, RRTK_PLAN_K / RRTK_GRID_K=<samples per round> override the choice for experiments and tests
+// (grid: forced for any size that fits).
 #include <cstdlib>
 
 #include "plan_common.cuh"
@@ -17,8 +22,8 @@ int scan_launch_informed(const PlanParams &, int, int, int, int, size_t, cudaStr
 int scan_occupancy_standard(int, int, int, size_t);
 int scan_occupancy_star(int, int, int, size_t);
 int scan_occupancy_informed(int, int, int, size_t);
-int grid_launch(int, const PlanParams &, int, size_t, cudaStream_t);
-int grid_occupancy(int, size_t);
+int grid_launch(int, int, const PlanParams &, int, size_t, cudaStream_t);
+int grid_occupancy(int, int, size_t);
 int wide_plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
                      const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int wide_plan_footprint(int, int, int, int, int, int, int, int *, int *);
@@ -42,7 +47,7 @@ static int scan_min_blocks(int T) { return T <= 64 ? 12 : T <= 128 ? RRTK_MINB12
 
 // ---- the bucket form (plan_grid.cuh): RRTStandard / RRTStar whose tree entries fit one word ---------------------------------
 struct GridShape {
-    int xb, yb, bshift, bshy, nbx, nby, rad, list_cap, blocks_per_sm;
+    int xb, yb, bshift, bshy, nbx, nby, rad, list_cap, blocks_per_sm, K;
     uint32_t near_ok2;
     size_t smem;
 };
@@ -53,16 +58,18 @@ static bool grid_shape(int kind, int W, int H, int n, double r_rewire, int threa
 {
     const char *impl = getenv("RRTK_PLAN_IMPL");
     if (impl && (impl[0] == 'w' || impl[0] == 's')) return false;
-#ifndef RRTK_GRID_DEFAULT
-    if (!(impl && impl[0] == 'g')) return false;                               // opt-in: RRTK_PLAN_IMPL=grid
+#ifdef RRTK_GRID_OPT_IN
+    if (!(impl && impl[0] == 'g')) return false;                               // experiment builds: only with RRTK_PLAN_IMPL=grid
 #endif
     if (kind != RRTK_STANDARD && kind != RRTK_STAR) return false;
     if (threads != 0 && threads != 128) return false;
-    if (env_int("RRTK_PLAN_K", 8) != 8 || env_int("RRTK_PLAN_T", 0) != 0) return false;
+    if (env_int("RRTK_PLAN_T", 0) != 0) return false;
     if (n < 2048 || n >= 5120) {                                               // the range plan_scan.cuh runs with 128 threads
         if (!(impl && impl[0] == 'g' && n <= 60000)) return false;              // forced (tests): any size that fits
     }
     GridShape g;
+    g.K = env_int("RRTK_GRID_K", 16);                                          // measured on cfg3: 100.4 k plans/s against 99.2 k with 8
+    if (g.K != 8 && g.K != 16) return false;
     g.xb = bits_for(W - 1); g.yb = bits_for(H - 1);
     const int ib = 32 - g.xb - g.yb;
     if (ib < 1 || ib > 31 || (long long)n >= (1ll << ib) - 1) return false;    // ids 0 .. n, all ones = an empty slot
@@ -86,7 +93,7 @@ static bool grid_shape(int kind, int W, int H, int n, double r_rewire, int threa
     g.list_cap = kind == RRTK_STANDARD ? 0 : (cap < need ? cap : need);
     g.smem = (size_t)4 * ((n + 1 + 31) & ~31) + (size_t)4 * 4 * g.list_cap + (((size_t)2 * (g.nbx * g.nby + 1) + 15) & ~(size_t)15);
     if (g.smem > (size_t)optin - 4096) return false;
-    int b = grid_occupancy(kind, g.smem);
+    int b = grid_occupancy(kind, g.K, g.smem);
     if (b <= 0) {
         b = (int)((size_t)sm_smem / (g.smem + 3072));
         if (b > 7) b = 7;
@@ -197,7 +204,7 @@ int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_
         P.sbits = 0; P.hit_words = 0; P.tail_bytes = 0; P.steps_max = 0;
         P.list_cap = g.list_cap;
         P.g_xb = g.xb; P.g_yb = g.yb; P.g_bshift = g.bshift; P.g_bshy = g.bshy; P.g_nbx = g.nbx; P.g_nby = g.nby; P.g_rad = g.rad; P.g_near_ok2 = g.near_ok2;
-        return grid_launch(kind, P, nplans, g.smem, st);
+        return grid_launch(kind, g.K, P, nplans, g.smem, st);
     }
     P.g_xb = P.g_yb = P.g_bshift = P.g_bshy = P.g_nbx = P.g_nby = P.g_rad = 0; P.g_near_ok2 = 0;
     P.sbits = s.sbits;
