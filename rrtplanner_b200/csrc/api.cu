@@ -49,6 +49,7 @@ int sample_streams_launch(const uint32_t *, const int32_t *, int, int, const rrt
 int plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
                 const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int plan_footprint(int, int, int, int, int, int, int, int *, int *);
+const char *plan_kernel_name(int, int, int, int, int, int, int);
 int paths_launch(const int32_t *, const int64_t *, int, int, int, int32_t *, int32_t *, cudaStream_t);
 int path_heads_launch(const int32_t *, const uint8_t *, int, int, int, uint8_t *, cudaStream_t);
 int paths_xy_launch(const int32_t *, const int16_t *, const double *, const int64_t *, int, int, int, int32_t *, int16_t *, int32_t *,
@@ -359,6 +360,13 @@ int rrtk_plan_batch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_p
     RRTK_TRY(dev_info(&d));
     return plan_launch(kind, d_bits, W, H, d_plans, nplans, n, r_rewire, r_goal, d_samples, d_balls, d_pts, d_cost, d_parent,
                        d_stats, d_ell_c, threads, d->optin, d->sm_smem, (cudaStream_t)stream);
+}
+
+const char *rrtk_plan_kernel(int kind, int W, int H, int n, int threads)
+{
+    DevInfo *d;
+    if (dev_info(&d) != RRTK_OK) return "";
+    return plan_kernel_name(kind, W, H, n, threads, d->optin, d->sm_smem);
 }
 
 int rrtk_plan_footprint(int kind, int W, int H, int n, int threads, int *smem_bytes, int *blocks_per_sm)

@@ -153,6 +153,15 @@ static bool scan_shape(int kind, int W, int H, int n, int threads, int optin, in
     return true;
 }
 
+// which of the three kernels plan_launch would run: "grid", "scan" or "wide"
+const char *plan_kernel_name(int kind, int W, int H, int n, int threads, int optin, int sm_smem)
+{
+    GridShape g;
+    if (grid_shape(kind, W, H, n, 0.0, threads, optin, sm_smem, &g)) return "grid";
+    ScanShape s;
+    return scan_shape(kind, W, H, n, threads, optin, sm_smem, &s) ? "scan" : "wide";
+}
+
 int plan_footprint(int kind, int W, int H, int n, int threads, int optin, int sm_smem, int *smem_bytes, int *blocks_per_sm)
 {
     GridShape g;
