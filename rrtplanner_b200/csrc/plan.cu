@@ -23,7 +23,7 @@ int scan_occupancy_standard(int, int, int, size_t);
 int scan_occupancy_star(int, int, int, size_t);
 int scan_occupancy_informed(int, int, int, size_t);
 int grid_launch(int, int, const PlanParams &, int, size_t, cudaStream_t);
-int grid_occupancy(int, int, size_t);
+int grid_occupancy(int, int, bool, size_t);
 int wide_plan_launch(int, const uint32_t *, int, int, const rrtk_plan_desc *, int, int, double, double, const int16_t *,
                      const double *, int16_t *, double *, int32_t *, int64_t *, double *, int, int, int, cudaStream_t);
 int wide_plan_footprint(int, int, int, int, int, int, int, int *, int *);
@@ -47,7 +47,7 @@ static int scan_min_blocks(int T) { return T <= 64 ? 12 : T <= 128 ? RRTK_MINB12
 
 // ---- the bucket form (plan_grid.cuh): RRTStandard / RRTStar whose tree entries fit one word ---------------------------------
 struct GridShape {
-    int xb, yb, bshift, bshy, nbx, nby, rad, list_cap, blocks_per_sm, K;
+    int xb, yb, bshift, bshy, nbx, nby, rad, list_cap, blocks_per_sm, K, kb, ent_words, off_list, off_bstart;
     uint32_t near_ok2;
     size_t smem;
 };
@@ -91,9 +91,18 @@ static bool grid_shape(int kind, int W, int H, int n, double r_rewire, int threa
     int cap = env_int("RRTK_PLAN_CAP", 256);
     const int need = (n + 1 + 31) & ~31;
     g.list_cap = kind == RRTK_STANDARD ? 0 : (cap < need ? cap : need);
-    g.smem = (size_t)4 * ((n + 1 + 31) & ~31) + (size_t)4 * 4 * g.list_cap + (((size_t)2 * (g.nbx * g.nby + 1) + 15) & ~(size_t)15);
+    g.ent_words = (n + 1 + 31) & ~31;
+    g.off_list = 4 * g.ent_words;
+    g.off_bstart = g.off_list + 4 * 4 * g.list_cap;
+    g.smem = (size_t)g.off_bstart + (((size_t)2 * (g.nbx * g.nby + 1) + 15) & ~(size_t)15);
+    // one-word (distance, id) keys: ids 0 .. n in kb bits, squared distances up to (W-1)^2 + (H-1)^2 in the rest
+    g.kb = bits_for(n);
+    {
+        const long long d2max = (long long)(W - 1) * (W - 1) + (long long)(H - 1) * (H - 1);
+        if (g.kb >= 32 || d2max >= (1ll << (32 - g.kb)) - 1 || env_int("RRTK_GRID_KEY32", 1) == 0) g.kb = 0;
+    }
     if (g.smem > (size_t)optin - 4096) return false;
-    int b = grid_occupancy(kind, g.K, g.smem);
+    int b = grid_occupancy(kind, g.K, g.kb > 0, g.smem);
     if (b <= 0) {
         b = (int)((size_t)sm_smem / (g.smem + 3072));
         if (b > 7) b = 7;
@@ -213,9 +222,11 @@ int plan_launch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_plan_
         P.sbits = 0; P.hit_words = 0; P.tail_bytes = 0; P.steps_max = 0;
         P.list_cap = g.list_cap;
         P.g_xb = g.xb; P.g_yb = g.yb; P.g_bshift = g.bshift; P.g_bshy = g.bshy; P.g_nbx = g.nbx; P.g_nby = g.nby; P.g_rad = g.rad; P.g_near_ok2 = g.near_ok2;
+        P.g_ent_words = g.ent_words; P.g_off_list = g.off_list; P.g_off_bstart = g.off_bstart; P.g_kb = g.kb;
         return grid_launch(kind, g.K, P, nplans, g.smem, st);
     }
     P.g_xb = P.g_yb = P.g_bshift = P.g_bshy = P.g_nbx = P.g_nby = P.g_rad = 0; P.g_near_ok2 = 0;
+    P.g_ent_words = P.g_off_list = P.g_off_bstart = P.g_kb = 0;
     P.sbits = s.sbits;
     P.list_cap = s.list_cap;
     P.hit_words = s.hit_words;

@@ -34,6 +34,8 @@ struct PlanParams {
     int g_nbx, g_nby;     // buckets per axis
     int g_rad;            // a sample reads the buckets that hold every cell within rad of it on both axes, rad >= r_rewire
     uint32_t g_near_ok2;  // rad^2: a nearest vertex at most this far away is the nearest of the whole tree
+    int g_ent_words, g_off_list, g_off_bstart;   // shared-memory layout: entries (words), byte offsets of the lists and of the bucket starts
+    int g_kb;             // id bits of a 32-bit (distance, id) key, 0 = distances and ids do not fit one word together
 };
 
 // what the owner warp of a sample hands to the commit phase

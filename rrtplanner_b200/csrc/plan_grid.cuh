@@ -37,7 +37,9 @@ constexpr int kFirst = 256;              // vertices also kept by index: the sca
 #define RRTK_GRID_MINB 7
 #endif
 
-template <int KIND, int K, int T>
+// KEY32: squared distances and vertex ids of the plan fit one 32-bit word together (cfg3: 19 + 13 bits), so a lane's nearest
+// vertex is one integer minimum per slot; otherwise distance and id are compared separately.
+template <int KIND, int K, int T, bool KEY32>
 __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams P)
 {
     constexpr int NW = T / 32;
@@ -68,9 +70,12 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
     const uint32_t near_ok2 = P.g_near_ok2;
 
     uint32_t *s_ent = smem;                                               // nslots entries in bucket order (padded to 32)
-    const int ent_words = (nslots + 31) & ~31;
-    uint32_t *s_list = s_ent + ent_words;                                 // [NW][cap] entries: one radius-set list per owner warp
-    uint16_t *s_bstart = reinterpret_cast<uint16_t *>(s_list + (KIND == RRTK_STANDARD ? 0 : NW * cap));   // NB + 1 first slots
+    const int ent_words = P.g_ent_words;
+    // offsets from the kernel parameters: constant-bank operands instead of address arithmetic the compiler redoes at every use
+    uint32_t *s_list = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(smem) + P.g_off_list);      // [NW][cap] entries: one radius-set list per owner warp
+    uint16_t *s_bstart = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(smem) + P.g_off_bstart);  // NB + 1 first slots
+    const int kb = P.g_kb;                                                // KEY32: id bits of a key
+    short2 *opts = P.pts + (size_t)plan * (n + 1);
 
     const rrtk_plan_desc *dsc = P.plans + plan;
     const uint32_t *gbits = P.bits + (size_t)dsc->world * P.words_per_grid;
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
     if (tid == 0) {
         const uint32_t e0 = make_entry(sx, sy, 0);
         s_ent[s_rootslot] = e0; s_first[0] = e0;
+        opts[0] = make_short2((short)sx, (short)sy);
         s_next = NW;
         s_checks = s_cells = 0ull; cost[0] = 0.0; parent[0] = -1;
     }
@@ -183,74 +189,36 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
             uint32_t *list = s_list + warp * cap;
             GPHASE_T(t_s0);
             // ---- near + within on the buckets around the sample ----
-            uint32_t bd = 0xffffffffu, bv = 0xffffffffu, be = 0u;            // this lane's nearest: distance, id, entry
+            uint32_t bd = 0xffffffffu, bv = 0xffffffffu, be = 0u;            // this lane's nearest: distance (KEY32: key), id, entry
             int total = 0;
-            // kVis x 32 slots per step, the kVis chains independent of each other: a warp of this kernel issues one instruction every
-            // ~10 cycles, so what a step costs is the length of its longest dependent chain, not its instruction count
-            constexpr int kVis = 4;
+            // 32 slots per step.  (Four steps unrolled into independent chains ran no faster: with 28 warps per SM the kernel is
+            // bound by issue slots, not by the chains, so what counts is not to touch a group of slots that the run does not have.)
+            constexpr int kVis = 1;
             auto visit = [&](const uint32_t *src, int base, int end, bool members) {
-                uint32_t e[kVis], d2[kVis];
-                if (end - base <= 32 * (kVis / 2)) {                        // short run (warp-uniform): half the groups
-                    uint32_t eh[kVis / 2], dh[kVis / 2];
-#pragma unroll
-                    for (int u = 0; u < kVis / 2; ++u) {
-                        const int idx = base + 32 * u + lane;
-                        eh[u] = idx < end ? src[idx] : kSlotEmpty;
-                    }
-#pragma unroll
-                    for (int u = 0; u < kVis / 2; ++u) {
-                        const int dx = (int)(eh[u] & xmask) - x, dy = (int)((eh[u] >> xb) & ymask) - y;
-                        dh[u] = eh[u] != kSlotEmpty ? (uint32_t)(dx * dx + dy * dy) : 0xffffffffu;
-                    }
-#pragma unroll
-                    for (int u = 0; u < kVis / 2; ++u) {
-                        const uint32_t id = eh[u] >> xyb;
-                        if (dh[u] < bd || (dh[u] == bd && id < bv)) { bd = dh[u]; bv = id; be = eh[u]; }
-                    }
-                    if (KIND != RRTK_STANDARD && members) {
-                        unsigned mh[kVis / 2];
-#pragma unroll
-                        for (int u = 0; u < kVis / 2; ++u) mh[u] = __ballot_sync(RRTK_FULL, dh[u] < r2x);
-#pragma unroll
-                        for (int u = 0; u < kVis / 2; ++u) {
-                            if (dh[u] < r2x) {
-                                const int at = total + __popc(mh[u] & ltmask);
-                                if (at < cap) list[at] = eh[u];
-                            }
-                            total += __popc(mh[u]);
-                        }
-                    }
-                    return;
-                }
-#pragma unroll
-                for (int u = 0; u < kVis; ++u) {
-                    const int idx = base + 32 * u + lane;
-                    e[u] = idx < end ? src[idx] : kSlotEmpty;
-                }
-#pragma unroll
-                for (int u = 0; u < kVis; ++u) {
-                    const int dx = (int)(e[u] & xmask) - x, dy = (int)((e[u] >> xb) & ymask) - y;
-                    d2[u] = e[u] != kSlotEmpty ? (uint32_t)(dx * dx + dy * dy) : 0xffffffffu;
-                }
-#pragma unroll
-                for (int u = 0; u < kVis; ++u) {
-                    const uint32_t id = e[u] >> xyb;
-                    if (d2[u] < bd || (d2[u] == bd && id < bv)) { bd = d2[u]; bv = id; be = e[u]; }
+                const int idx = base + lane;
+                const uint32_t e = idx < end ? src[idx] : kSlotEmpty;
+                const int dx = (int)(e & xmask) - x, dy = (int)((e >> xb) & ymask) - y;
+                const bool valid = e != kSlotEmpty;
+                const uint32_t d2r = (uint32_t)(dx * dx + dy * dy);
+                const uint32_t id = e >> xyb;
+                bool mem;
+                if (KEY32) {
+                    const uint32_t key = valid ? (d2r << kb) + id : 0xffffffffu;
+                    bd = min(bd, key);
+                    mem = valid && d2r < r2x;
+                } else {
+                    const uint32_t d2 = valid ? d2r : 0xffffffffu;
+                    if (d2 < bd || (d2 == bd && id < bv)) { bd = d2; bv = id; be = e; }
+                    mem = d2 < r2x;
                 }
                 if (KIND != RRTK_STANDARD && members) {
-                    unsigned mm[kVis];
-#pragma unroll
-                    for (int u = 0; u < kVis; ++u) mm[u] = __ballot_sync(RRTK_FULL, d2[u] < r2x);
-#pragma unroll
-                    for (int u = 0; u < kVis; ++u) {
-                        if (d2[u] < r2x) {
-                            const int at = total + __popc(mm[u] & ltmask);
-                            if (at < cap) list[at] = e[u];
-                        }
-                        total += __popc(mm[u]);
-                    }
+                    const unsigned mm = __ballot_sync(RRTK_FULL, mem);
+                    const int at = total + __popc(mm & ltmask);
+                    if (mem && at < cap) list[at] = e;
+                    total += __popc(mm);
                 }
             };
+            auto nearest_d2 = [&]() { const uint32_t m = __reduce_min_sync(RRTK_FULL, bd); return KEY32 ? (m >> kb) : m; };
             if (j <= kFirst) {
                 for (int base = 0; base < j; base += 32 * kVis) visit(s_first, base, j, true);
             } else {
@@ -262,7 +230,7 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                     const int s0 = s_bstart[bxx * NBY + by0], s1 = s_bstart[bxx * NBY + by1 + 1];
                     for (int base = s0; base < s1; base += 32 * kVis) visit(s_ent, base, s1, true);
                 }
-                if (__reduce_min_sync(RRTK_FULL, bd) > near_ok2) {
+                if (nearest_d2() > near_ok2) {
                     // nothing that close in these buckets: the nearest vertex may lie anywhere (the radius set is complete as it is)
                     ++my_far;
                     for (int base = 0; base < nslots; base += 32 * kVis) visit(s_ent, base, nslots, false);
@@ -270,11 +238,22 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
             }
             GPHASE_T(t_s1);
             GPHASE_ADD(clk_scan, t_s0, t_s1);
-            const uint32_t md = __reduce_min_sync(RRTK_FULL, bd);
-            const uint32_t mv = __reduce_min_sync(RRTK_FULL, bd == md ? bv : 0xffffffffu);
-            const uint32_t near_e = __shfl_sync(RRTK_FULL, be, __ffs(__ballot_sync(RRTK_FULL, bd == md && bv == mv)) - 1);
-            bd = md;
-            const int vnear = (int)mv;
+            int vnear;
+            uint32_t pnear;
+            if (KEY32) {
+                const uint32_t mk = __reduce_min_sync(RRTK_FULL, bd);
+                bd = mk >> kb;
+                vnear = (int)(mk & ((1u << kb) - 1u));
+                const short2 pn = opts[vnear];                                // written when the vertex was inserted
+                pnear = pack_xy(pn.x, pn.y);
+            } else {
+                const uint32_t md = __reduce_min_sync(RRTK_FULL, bd);
+                const uint32_t mv = __reduce_min_sync(RRTK_FULL, bd == md ? bv : 0xffffffffu);
+                const uint32_t near_e = __shfl_sync(RRTK_FULL, be, __ffs(__ballot_sync(RRTK_FULL, bd == md && bv == mv)) - 1);
+                bd = md;
+                vnear = (int)mv;
+                pnear = ent_xy(near_e);
+            }
             // `sampled` holds accepted samples only, not xstart (rrt.py:410,426): a sample on the root's cell is a
             // duplicate only if some vertex >= 1 sits there too
             bool dup = bd == 0 && vnear >= 1;
@@ -291,7 +270,6 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                 }
                 dup = __any_sync(RRTK_FULL, f);
             }
-            const uint32_t pnear = ent_xy(near_e);
             int flags = 1 | (dup ? 2 : 0);
             double c0 = 0.0, wc = CUDART_INF;
             int wv = 0x7fffffff, ring = 0;
@@ -425,6 +403,7 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                 const uint32_t e = make_entry(px(pnew), py(pnew), v);
                 s_ent[slot] = e;
                 if (v < kFirst) s_first[v] = e;
+                if (KEY32) opts[v] = make_short2((short)px(pnew), (short)py(pnew));
             };
             if (j + kact <= n) {
                 const SampleRec r = s_rec[min(lane, K - 1)];
@@ -621,15 +600,15 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
     const int vparent = s_goalv;
     const bool found = reachable && vparent != 0x7fffffff;
     const int top = found ? j + 1 : j;     // rows holding real vertices
-    short2 *opts = P.pts + (size_t)plan * (n + 1);
     for (int v = j + tid; v <= n; v += T) {                                    // rows without a vertex (the parked slots among them)
         opts[v] = (v == j && found) ? make_short2((short)gx, (short)gy) : make_short2(-32768, -32768);
         if (v >= top) { cost[v] = CUDART_INF; parent[v] = -1; }
     }
-    for (int s = tid; s < nslots; s += T) {
-        const uint32_t e = s_ent[s];
-        if (e != kSlotEmpty) opts[ent_id(e)] = make_short2((short)(e & xmask), (short)((e >> xb) & ymask));
-    }
+    if (!KEY32)
+        for (int s = tid; s < nslots; s += T) {
+            const uint32_t e = s_ent[s];
+            if (e != kSlotEmpty) opts[ent_id(e)] = make_short2((short)(e & xmask), (short)((e >> xb) & ymask));
+        }
     if (lane == 0) {      // every warp has committed some rounds: add the counters up
         atomicAdd(&s_cnt[1], (unsigned long long)nn_pairs);
         atomicAdd(&s_cnt[2], (unsigned long long)ring_members); atomicAdd(&s_cnt[3], (unsigned long long)accepted);
