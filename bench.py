@@ -47,8 +47,8 @@ W = H = 512
 N_ITER = 5000
 R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
-NCU_DRAM_BYTES_PER_PLAN = (71214336.0 + 32413696.0) / 1036          # re-captured whenever the plan kernel changes
-NCU_DRAM_SOURCE = "profiles/r2_v4_plan_ncu.txt: 71.21 MB read + 32.41 MB written for 1036 plans"
+NCU_DRAM_BYTES_PER_PLAN = (103698176.0 + 52496896.0) / 1036          # re-captured whenever the plan kernel changes
+NCU_DRAM_SOURCE = "profiles/r2_v5_plan_ncu.txt (plan_grid_kernel): 103.70 MB read + 52.50 MB written for 1036 plans"
 NCU_CFD_DRAM_BYTES = 45536256.0 + 416000.0
 NCU_CFD_DRAM_SOURCE = ("profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                        "launch (profiles/r2_v4_cfd_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 29.5 MB of the 32 MB of fields, once")
