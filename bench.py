@@ -47,11 +47,11 @@ W = H = 512
 N_ITER = 5000
 R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
-NCU_DRAM_BYTES_PER_PLAN = (103698176.0 + 52496896.0) / 1036          # re-captured whenever the plan kernel changes
-NCU_DRAM_SOURCE = "profiles/r2_v5_plan_ncu.txt (plan_grid_kernel): 103.70 MB read + 52.50 MB written for 1036 plans"
+NCU_DRAM_BYTES_PER_PLAN = (98406144.0 + 51495936.0) / 1036          # re-captured whenever the plan kernel changes
+NCU_DRAM_SOURCE = "profiles/r2_v5_plan_ncu.txt (plan_grid_kernel): 98.41 MB read + 51.50 MB written for 1036 plans"
 NCU_CFD_DRAM_BYTES = 45536256.0 + 416000.0
 NCU_CFD_DRAM_SOURCE = ("profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                       "launch (profiles/r2_v4_cfd_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 29.5 MB of the 32 MB of fields, once")
+                       "launch (profiles/r2_v5_cfd_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 29.5 MB of the 32 MB of fields, once")
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
 
 
@@ -257,7 +257,7 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
         "cells_per_s": ncells / (ms / 1e3), "ms_per_launch": ms, "gpu_launches": reps,
         "roofline": roof("rrtk::collision_global_kernel", ms, 17309184.0,
                          "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
-                         "this launch (profiles/r2_v4_cc_ncu.txt): 16 MB of segment records + the 512 KB grid, once"),
+                         "this launch (profiles/r2_v5_cc_ncu.txt): 16 MB of segment records + the 512 KB grid, once"),
     }
     # K1 with the grid staged in shared memory (grids up to ~110 KB of bits: the planner-sized worlds), 512x512 here
     S2 = 512
@@ -327,7 +327,7 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
         "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free2) and torch.equal(cells, cells2)),
         "roofline": roof("rrtk::collision_cf_kernel", ms_cf, 20984576.0,
                          "profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
-                         "launch (profiles/r2_v4_cf_ncu.txt): 16 MB of segment records + the 4 MB field, once (the 5 MB of results stay in L2)"),
+                         "launch (profiles/r2_v5_cf_ncu.txt): 16 MB of segment records + the 4 MB field, once (the 5 MB of results stay in L2)"),
     }
     # K1b on directional fields: one field per octant of the walk (8 bytes per cell), about half the reads per segment
     cap8 = 255

@@ -3,7 +3,7 @@ TAG=${1:-r2}; PLANS=${2:-1036}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-dubins --no-informed --no-class-api --no-strong > gpurun_out/${TAG}_launches_bench.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:plan_scan_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_plan \
+ncu --set full --clock-control none --import-source on -k "regex:plan_(grid|scan)_kernel" -s 3 -c 1 -f -o gpurun_out/${TAG}_plan \
     python bench.py --steps 1 --warmup 3 --plans $PLANS --plan-only > gpurun_out/${TAG}_plan_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:collision_cf -s 3 -c 1 -f -o gpurun_out/${TAG}_cf \
     python bench.py --collision-only --no-cpu > gpurun_out/${TAG}_cf_bench.log 2>&1
