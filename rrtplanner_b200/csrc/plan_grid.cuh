@@ -150,8 +150,9 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
     // block-uniform state, replicated in every thread (refreshed from s_sum after each round)
     int j = 1, it0 = 0, kwant = 1;
     int cw = 0;                          // the commit duty rotates over the warps (plan_scan.cuh)
-    long long nn_pairs = 0, ring_members = 0, accepted = 0;
-    unsigned my_checks = 0, my_cells = 0, my_far = 0;      // my_far: samples whose nearest vertex lay outside their buckets
+    // the statistics the commit phase adds up live in shared memory (s_cnt, one writer per round): the kernel is at its register
+    // limit, and three 64-bit counters carried through the whole loop cost more than three shared-memory updates per round
+    unsigned my_checks = 0, my_cells = 0;
     const unsigned ltmask = (1u << lane) - 1u;
     // -DRRTK_PHASE_CLOCKS (experiment builds, scripts/phase_clocks.py): cycles per phase in spare stats slots
 #ifdef RRTK_PHASE_CLOCKS
@@ -232,7 +233,6 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                 }
                 if (nearest_d2() > near_ok2) {
                     // nothing that close in these buckets: the nearest vertex may lie anywhere (the radius set is complete as it is)
-                    ++my_far;
                     for (int base = 0; base < nslots; base += 32 * kVis) visit(s_ent, base, nslots, false);
                 }
             }
@@ -456,9 +456,8 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                 }
                 consumed = stop;
                 jc = j + __popc(accm);
-                nn_pairs += __reduce_add_sync(RRTK_FULL, cons ? myj : 0);
-                ring_members += __reduce_add_sync(RRTK_FULL, acc ? r.ring + extra : 0);
-                accepted += __popc(accm);
+                const int np_ = __reduce_add_sync(RRTK_FULL, cons ? myj : 0), rm_ = __reduce_add_sync(RRTK_FULL, acc ? r.ring + extra : 0);
+                if (lane == 0) { s_cnt[1] += (unsigned long long)np_; s_cnt[2] += (unsigned long long)rm_; s_cnt[3] += (unsigned long long)__popc(accm); }
                 fast = true;
             }
             for (int k = 0; k < kact && !fast; ++k) {                         // rounds in which the tree may fill up: one sample at a time
@@ -497,15 +496,14 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                     }
                 }
                 ++consumed;
-                nn_pairs += jc;
+                if (lane == 0) s_cnt[1] += (unsigned long long)jc;
                 if (reject) continue;
-                ring_members += ringm;
+                if (lane == 0) { s_cnt[2] += (unsigned long long)ringm; s_cnt[3] += 1ull; }
                 const int vbest = (bv != 0x7fffffff) ? bv : r.vnear;
                 const double cbest = (bv != 0x7fffffff) ? bc : r.c0;
                 if (lane == 0) { insert(jc, r.pnew, s_sig[k]); cost[jc] = cbest; parent[jc] = vbest; }   // rrt.py:524-529
                 if (lane == nnew) { newp = r.pnew; newc = cbest; }
                 ++nnew;
-                ++accepted;
                 ++jc;
             }
             if (it0 + consumed >= n) finished = true;
@@ -592,7 +590,6 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
     if (lane == 0) {
         atomicAdd(&s_checks, (unsigned long long)my_checks);
         atomicAdd(&s_cells, (unsigned long long)my_cells);
-        atomicAdd(&s_cnt[0], (unsigned long long)my_far);
     }
     __syncthreads();
 
@@ -609,10 +606,6 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
             const uint32_t e = s_ent[s];
             if (e != kSlotEmpty) opts[ent_id(e)] = make_short2((short)(e & xmask), (short)((e >> xb) & ymask));
         }
-    if (lane == 0) {      // every warp has committed some rounds: add the counters up
-        atomicAdd(&s_cnt[1], (unsigned long long)nn_pairs);
-        atomicAdd(&s_cnt[2], (unsigned long long)ring_members); atomicAdd(&s_cnt[3], (unsigned long long)accepted);
-    }
     __syncthreads();
     if (tid == 0) {
         if (found) { cost[j] = __longlong_as_double((long long)cstar_bits); parent[j] = vparent; }
@@ -627,7 +620,7 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
         st[RRTK_STAT_NN_PAIRS] = (long long)s_cnt[1];
         st[RRTK_STAT_RING_MEMBERS] = (long long)s_cnt[2];
         st[RRTK_STAT_ACCEPTED] = (long long)s_cnt[3];
-        st[RRTK_STAT_RESERVED0] = (long long)s_cnt[0];     // diagnostic: samples that needed the all-slot scan for their nearest vertex
+        st[RRTK_STAT_RESERVED0] = 0;
         st[RRTK_STAT_RESERVED1] = 0;
 #ifdef RRTK_PHASE_CLOCKS                      // thread 0's view: scan = its own neighbourhood scans, owner = round start .. first barrier
         st[RRTK_STAT_RESERVED0] = clk_scan;
