@@ -47,8 +47,8 @@ W = H = 512
 N_ITER = 5000
 R_REWIRE = 50.0
 METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
-NCU_DRAM_BYTES_PER_PLAN = (98406144.0 + 51495936.0) / 1036          # re-captured whenever the plan kernel changes
-NCU_DRAM_SOURCE = "profiles/r2_v5_plan_ncu.txt (plan_grid_kernel): 98.41 MB read + 51.50 MB written for 1036 plans"
+NCU_DRAM_BYTES_PER_PLAN = (97265664.0 + 52136192.0) / 1036          # re-captured whenever the plan kernel changes
+NCU_DRAM_SOURCE = "profiles/r2_v5_plan_ncu.txt (plan_grid_kernel): 97.27 MB read + 52.14 MB written for 1036 plans"
 NCU_CFD_DRAM_BYTES = 45536256.0 + 416000.0
 NCU_CFD_DRAM_SOURCE = ("profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                        "launch (profiles/r2_v5_cfd_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 29.5 MB of the 32 MB of fields, once")

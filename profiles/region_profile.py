@@ -1,3 +1,5 @@
+"""Warp instructions and stall samples of plan_grid_kernel per phase (line ranges of csrc/plan_grid.cuh as committed with the
+profile): python profiles/region_profile.py sass.csv librrtk.so plan_grid.sm_100a.cubin <mangled-name part>  (see line_profile.py)."""
 import csv, re, subprocess, sys, tempfile, os
 sass_csv, so, cubin_name, func_pat = sys.argv[1:5]
 tmp = tempfile.mkdtemp()
@@ -20,7 +22,7 @@ for ln in dis.splitlines():
 rows = list(csv.reader(open(sass_csv))); hdr = rows[1]
 ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
 base = int(rows[2][0], 16)
-regions = [("setup+prologue", 0, 177), ("owner:pickup", 178, 190), ("owner:scan", 191, 239), ("owner:nearest/dup/walk", 240, 287), ("owner:costing+cands", 288, 378), ("owner:record", 379, 392), ("commit", 393, 530), ("round end", 531, 545), ("goal+out", 546, 700)]
+regions = [("setup+prologue", 0, 178), ("owner:pickup", 179, 191), ("owner:scan", 192, 239), ("owner:nearest/dup/walk", 240, 287), ("owner:costing+cands", 288, 378), ("owner:record", 379, 392), ("commit", 393, 528), ("round end", 529, 543), ("goal+out", 544, 700)]
 agg = {r[0]: [0, 0] for r in regions}; agg["other"] = [0, 0]; tot=[0,0]
 unk = {}
 for r in rows[2:]:

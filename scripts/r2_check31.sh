@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize.py -q -m gpu 2>&1 | tail -2
-bash scripts/variants.sh 0 main main 2>&1 | tail -2
+RRTK_GRID_BSY=4 RRTK_PLAN_CAP=192 bash scripts/variants.sh 0 g8 main 2>&1 | tail -2
+RRTK_GRID_BSY=5 RRTK_PLAN_CAP=160 bash scripts/variants.sh 0 g8 2>&1 | tail -1
