@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                 }
             };
             auto nearest_d2 = [&]() { const uint32_t m = __reduce_min_sync(RRTK_FULL, bd); return KEY32 ? (m >> kb) : m; };
+            __syncwarp();                                                  // the lanes are done reading the previous sample's list
             if (j <= kFirst) {
                 for (int base = 0; base < j; base += 32 * kVis) visit(s_first, base, j, true);
             } else {
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(T, RRTK_GRID_MINB) plan_grid_kernel(PlanParams
                     for (int base = 0; base < nslots; base += 32 * kVis) visit(s_ent, base, nslots, false);
                 }
             }
+            __syncwarp();                                                  // list entries written by other lanes are read below
             GPHASE_T(t_s1);
             GPHASE_ADD(clk_scan, t_s0, t_s1);
             int vnear;

@@ -7,6 +7,12 @@ run() { echo "== compute-sanitizer --tool $1 :: pytest $2 -k \"$3\"" >> $LOG
   timeout 900 compute-sanitizer --tool $1 --print-limit 10 python -m pytest $2 -x -q -k "$3" 2>&1 | grep -vE "Host Frame|^\s*$" | tail -6 >> $LOG; }
 run racecheck "tests/test_gpu_parity.py" "test_plan_golden and not wide and (blobs or adversarial or wall)"
 run racecheck "tests/test_gpu_parity.py" "test_plan_golden_wide and (blobs or wall)"
+# the bucket form of K7 (plan_grid.cuh), forced for the golden plans (n = 40 .. 1000: by-index scan and bucket scan) and at cfg3's shape
+RRTK_PLAN_IMPL=grid run racecheck "tests/test_gpu_parity.py" "test_plan_golden and not wide and not informed and (blobs or adversarial or wall or cfg1)"
+RRTK_PLAN_IMPL=grid run synccheck "tests/test_gpu_parity.py" "test_plan_golden and not wide and not informed and (blobs or cfg1)"
+RRTK_PLAN_IMPL=grid run memcheck "tests/test_gpu_parity.py" "test_plan_golden and not wide and not informed"
+run memcheck "tests/test_gpu_parity.py" "cfg3_batch_vs_oracle and star"
+run memcheck "tests/test_gpu_rewire.py tests/test_gpu_clearance.py" "informed_plans_bit_exact and 96x96 or directional or pipelined_worlds"
 run racecheck "tests/test_gpu_rewire.py" "96x96_n500 or 96x96_n600 or several_plans"
 run racecheck "tests/test_gpu_parity.py" "sample_stream or rejection_path"
 run synccheck "tests/test_gpu_rewire.py tests/test_gpu_parity.py" "96x96_n500 or 96x96_n600 or several_plans or (test_plan_golden and blobs)"
