@@ -395,6 +395,27 @@ def test_cfg3_batch_vs_oracle(kind):
         assert path[p, :ln[p]].tolist() == res.path(p)
 
 
+@pytest.mark.parametrize("kind,W,H,n,r", [("star", 300, 200, 2500, 30.0), ("star", 1000, 700, 3000, 80.0), ("standard", 2048, 64, 4000, 0.0),
+                                           ("star", 512, 512, 2100, 12.5), ("star", 130, 130, 5100, 300.0)])
+def test_bucket_kernel_shapes_vs_oracle(kind, W, H, n, r):
+    """The bucket form of K7 (plan_grid.cuh) on shapes other than cfg3 -- non-square and non-power-of-two grids, keys that do not
+    fit one word (1000 x 700), a radius below one bucket and one that covers the grid (every vertex is a member: the list
+    overflows into the all-slot path) -- must be the kernel the dispatch picks, and every tree equal to the C oracle's."""
+    nplans = 3
+    db = batch.DeviceBatch(kind, W, H, n, r)
+    assert db.L.rrtk_plan_kernel(db.kind, W, H, n, 0).decode() == "grid"
+    ogs = np.stack([worlds.perlin_occupancygrid(W, H, seed=50 + w) for w in range(nplans)]).astype(np.uint8)
+    db.set_worlds_host(ogs)
+    pairs = [worlds.start_goal(ogs[p], p) for p in range(nplans)]
+    db.set_plans(batch.make_desc(np.arange(nplans), [a for a, _ in pairs], [b for _, b in pairs]))
+    db.seed_samples(10 + np.arange(nplans))
+    res = db.run().download()
+    samples = db.samples.cpu().numpy()
+    for p in range(nplans):
+        want = oracle_tree(kind, ogs[p], n, pairs[p][0], pairs[p][1], samples[p], r)
+        assert_same_as_oracle(res, p, want)
+
+
 def test_cfg4_informed_vs_oracle():
     """BASELINE cfg4 shape: one 1024^2 world, several pairs, n=20000, r=50, r_goal=5."""
     W = H = 1024
