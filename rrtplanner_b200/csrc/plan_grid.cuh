@@ -3,28 +3,34 @@
 // Same loop, same results as plan_scan.cuh (rrt.py:418-437, 498-548, go2goal :284-332; near :131-155, within :157-181,
 // collisionfree :183-229, default costfn :70-78) -- tests/test_gpu_parity.py runs every golden tree through both.  What
 // changes is how `near` and `within` are answered.  Every vertex the tree will ever hold is one of the n samples, and those
-// are known when the plan starts.  So the block first sorts the SAMPLES (and the start) by spatial bucket (cells of
-// 2^bshift a side, x-major) and gives each a fixed slot of the on-chip tree in that order; a slot is EMPTY until its sample
-// is accepted, then holds  id << (xb + yb) | y << xb | x.  `near` / `within` for a sample then read only the slots of the
-// (2 R + 1)^2 buckets around it, R * 2^bshift >= r_rewire: five runs of consecutive slots for cfg3 (32-cell buckets, r = 50),
-// about a tenth of the tree, straight from shared memory by the warp that owns the sample:
-//   * every vertex closer than R * 2^bshift on both axes lies in those buckets, so the radius set is complete, and the
-//     nearest vertex found there is THE nearest vertex whenever it is closer than that (lowest index among equals: ids are
-//     in the entries).  If it is not (a sparse tree), the warp scans all slots for the nearest vertex; while the tree has at
-//     most kFirst vertices it scans a by-index copy of them instead of the buckets.
+// are known when the plan starts.  So the block first sorts the SAMPLES (and the start) by spatial bucket (2^bshift cells in
+// x, 2^bshy in y, x-major: 32 x 4 cells for cfg3) and gives each a fixed slot of the on-chip tree in that order; a slot is
+// EMPTY until its sample is accepted, then holds  id << (xb + yb) | y << xb | x.  `near` / `within` for a sample then read
+// only the slots of the buckets that hold every cell within rr >= r_rewire of it on both axes -- whole bucket columns in x (one
+// run of consecutive slots each, ~4 for cfg3), the exact range of the fine buckets in y: ~260 slots in 11 groups of 32 instead
+// of the whole tree -- straight from shared memory, by the warp that owns the sample:
+//   * every vertex closer than rr on both axes lies in those buckets, so the radius set is complete, and the nearest vertex
+//     found there is THE nearest vertex whenever it is closer than rr (lowest index among equals: ids are in the entries).
+//     If it is not (a sparse tree; 13 samples per plan on cfg3), the warp scans all slots for the nearest vertex; while the
+//     tree has at most kFirst vertices it scans a by-index copy of them instead of the buckets.
 //   * members go to the warp's list as they are found (one ballot per 32 slots); no membership words, no compaction, no
 //     block-wide scan phase and no barrier for it: a round is owner phase, barrier, commit phase, barrier.
+//   * KEY32: when squared distances and ids fit one word together (cfg3: 19 + 13 bits) a lane's nearest vertex is one
+//     integer minimum per slot, and the nearest vertex's point is read back from the `pts` output (written at insertion).
 // The owner phase from the costing on and the whole commit phase are those of plan_scan.cuh (see its header for why a round
-// of K samples replays to exactly the sequential result).  Against that kernel on cfg3: fewer instructions per plan
-// (no 12.5 M vertex-sample pairs), two barriers per round instead of three, 5 KB less shared memory per plan.
+// of K samples replays to exactly the sequential result).  Against that kernel on cfg3 (profiles/r2_v5_plan_ncu.txt): 6.4 M
+// instead of 8.3 M warp instructions per plan (no 12.5 M vertex-sample pairs), two barriers per round instead of three, K = 16
+// samples per round pay (with the scan they did not), 113 k instead of 89.6 k plans/s.  The kernel is bound by issue slots
+// (28 warps per SM, one instruction per warp every ~10 cycles whatever the dependences) and register-limited: what helped
+// was removing instructions and live values, not overlapping chains.
 //
 // Slot of sample i: found with shared-memory atomics in the prologue (the order inside a bucket is arbitrary and immaterial:
 // every tie is broken on the vertex id), kept until the sample's turn in row i + 1 of the plan's `parent` output, which no
 // vertex can occupy before iteration i has been committed (the tree has at most i + 1 vertices then).
 //
 // Limits (plan.cu falls back to plan_scan.cuh): bits(W - 1) + bits(H - 1) + bits(n + 1) <= 32 so that an entry fits a word
-// (cfg3: 9 + 9 + 13), at most 1024 buckets, RRTStandard / RRTStar only (an informed plan draws its samples from the tree's
-// own state, so they are not known in advance).
+// (cfg3: 9 + 9 + 13), at most 2048 buckets (coarser ones otherwise), 2048 <= n < 5120 by default, RRTStandard / RRTStar only
+// (an informed plan draws its samples from the tree's own state, so they are not known in advance).
 #pragma once
 #include "plan_common.cuh"
 
