@@ -227,7 +227,7 @@ int rrtk_plan_batch(int kind, const uint32_t *d_bits, int W, int H, const rrtk_p
                     const double *d_balls, int16_t *d_pts, double *d_cost, int32_t *d_parent,
                     int64_t *d_stats, double *d_ell_c, int threads, void *stream);
 
-/* Which plan kernel rrtk_plan_batch runs for this shape on the current device: "grid" (RRTStandard / RRTStar, 2048 <= n < 5120,
+/* Which plan kernel rrtk_plan_batch runs for this shape on the current device: "grid" (RRTStandard / RRTStar, n >= 256,
  * tree entries fit one word: near / within from spatial buckets of the pre-known samples), "scan" (brute-force packed-key scan)
  * or "wide" (32-bit distances, any grid); "" without a device.  The trees are the same whichever runs. */
 const char *rrtk_plan_kernel(int kind, int W, int H, int n, int threads);

@@ -1,8 +1,8 @@
 // K7 dispatch: which plan kernel runs a batch, with what block shape and shared-memory budget.
 //
-// 1. RRTStandard / RRTStar with 2048 <= n < 5120 whose tree entries fit one word (bits(W-1) + bits(H-1) + bits(n+1) <= 32,
-//    cfg3: 9 + 9 + 13): the bucket kernel (plan_grid.cuh) -- the tree in shared memory in bucket order of the samples,
-//    near / within from the buckets around a sample, 16 samples per round, 128 threads.
+// 1. RRTStandard / RRTStar with n >= 256 whose tree entries fit one word (bits(W-1) + bits(H-1) + bits(n+1) <= 32, cfg3:
+//    9 + 9 + 13) and whose tree fits shared memory: the bucket kernel (plan_grid.cuh) -- the tree in shared memory in
+//    bucket order of the samples, near / within from the buckets around a sample, 16 samples per round, 128 threads.
 // 2. Otherwise the packed-key scan kernel (plan_scan.cuh): brute-force scan over the whole tree.  Its keys hold
 //    (d2 - |q|^2) * 2^sbits + row in 32 bits, so it takes grids up to 2896 / 2048 / 1448 cells a side (1 / 2 / 3-4
 //    membership words per thread, i.e. n up to 32 / 64 / 128 vertices per thread).
@@ -64,9 +64,10 @@ static bool grid_shape(int kind, int W, int H, int n, double r_rewire, int threa
     if (kind != RRTK_STANDARD && kind != RRTK_STAR) return false;
     if (threads != 0 && threads != 128) return false;
     if (env_int("RRTK_PLAN_T", 0) != 0) return false;
-    if (n < 2048 || n >= 5120) {                                               // the range plan_scan.cuh runs with 128 threads
-        if (!(impl && impl[0] == 'g' && n <= 60000)) return false;              // forced (tests): any size that fits
-    }
+    // measured against the scan form on 512 x 512 worlds, r = 50 (scripts/size_sweep.py): n = 400 / 1000 / 2048 / 5000 / 5500 / 8000 ->
+    // 1.09 / 1.19 / 1.22 / 1.27 / 1.82 / 1.71 x; trees of fewer than 256 vertices never leave the by-index path, so they stay
+    // with the scan form unless the bucket form is forced (tests)
+    if (n < 256 && !(impl && impl[0] == 'g')) return false;
     GridShape g;
     g.K = env_int("RRTK_GRID_K", 16);                                          // measured on cfg3: 100.4 k plans/s against 99.2 k with 8
     if (g.K != 8 && g.K != 16) return false;
@@ -78,10 +79,10 @@ static bool grid_shape(int kind, int W, int H, int n, double r_rewire, int threa
     g.bshift = env_int("RRTK_GRID_BSX", 5); g.bshy = env_int("RRTK_GRID_BSY", 2);
     for (;;) {
         g.nbx = (W + (1 << g.bshift) - 1) >> g.bshift; g.nby = (H + (1 << g.bshy) - 1) >> g.bshy;
-        if (g.nbx * g.nby <= 2048) break;
+        if (g.nbx * g.nby <= 2048 && g.nbx * g.nby + 1 <= n) break;           // (the prologue's counters live in the entry array)
+        if (g.bshift >= 15) return false;
         if (g.bshy < g.bshift) ++g.bshy; else ++g.bshift;
     }
-    if (g.nbx * g.nby + 1 > n) return false;                                   // the prologue's counters live in the entry array
     const double r = kind == RRTK_STAR ? (r_rewire > 0.0 ? r_rewire : 0.0) : 0.0;
     double rad = ceil(r);
     if (rad < (double)(1 << g.bshift)) rad = (double)(1 << g.bshift);          // near: look at least one x bucket around

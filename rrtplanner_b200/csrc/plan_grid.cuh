@@ -29,7 +29,7 @@
 // vertex can occupy before iteration i has been committed (the tree has at most i + 1 vertices then).
 //
 // Limits (plan.cu falls back to plan_scan.cuh): bits(W - 1) + bits(H - 1) + bits(n + 1) <= 32 so that an entry fits a word
-// (cfg3: 9 + 9 + 13), at most 2048 buckets (coarser ones otherwise), 2048 <= n < 5120 by default, RRTStandard / RRTStar only
+// (cfg3: 9 + 9 + 13), at most 2048 buckets and fewer than n (coarser ones otherwise), n >= 256 by default, RRTStandard / RRTStar only
 // (an informed plan draws its samples from the tree's own state, so they are not known in advance).
 #pragma once
 #include "plan_common.cuh"
