@@ -225,13 +225,15 @@ class RRT(object):
         ``parents`` with ``dist`` (segment length) and ``cost`` (cost-to-come of the child)."""
         T = nx.DiGraph()
         T.add_node(vgoal, pt=points[vgoal])
-        for i in range(points.shape[0]):
-            T.add_node(i, pt=points[i])
-        for child, parent in parents.items():
-            if parent is None:
-                continue
-            step = points[child] - points[parent]
-            T.add_edge(parent, child, dist=r2norm(step), cost=vcosts[child])
+        T.add_nodes_from((i, {"pt": points[i]}) for i in range(points.shape[0]))
+        # the edges in the order of ``parents`` (insertion order), their lengths in one pass: sqrt of an exact integer sum, the
+        # same double math.sqrt gives edge by edge
+        children = [c for c, p in parents.items() if p is not None]
+        if children:
+            pars = [parents[c] for c in children]
+            steps = points[np.asarray(children, dtype=np.int64)] - points[np.asarray(pars, dtype=np.int64)]
+            dists = np.sqrt((steps[:, 0] * steps[:, 0] + steps[:, 1] * steps[:, 1]).astype(np.float64)).tolist()
+            T.add_edges_from((p, c, {"dist": d, "cost": vcosts[c]}) for p, c, d in zip(pars, children, dists))
         return T
 
     # ---- shared plan() machinery ----------------------------------------------------------------------
@@ -290,8 +292,7 @@ class RRT(object):
             points[n] = pts[j]
             vcosts[n] = cost[j]
         parents = {0: None}
-        for v in range(1, j):
-            parents[v] = np.int64(parent[v])
+        parents.update(zip(range(1, j), np.asarray(parent[1:j]).astype(np.int64)))
         if found:
             parents[vgoal] = np.int64(parent[j])
         gv = vgoal if found else np.int64(0)
