@@ -50,6 +50,9 @@ METRIC = "RRT* plans/sec (512x512 grid, n=5000)"
 NCU_DRAM_BYTES_PER_PLAN = (97265664.0 + 52136192.0) / 1036          # re-captured whenever the plan kernel changes
 NCU_DRAM_SOURCE = "profiles/r2_v5_plan_ncu.txt (plan_grid_kernel): 97.27 MB read + 52.14 MB written for 1036 plans"
 NCU_CFD_DRAM_BYTES = 45536256.0 + 416000.0
+NCU_CFD16_DRAM_BYTES = 67017472.0 + 3128320.0
+NCU_CFD16_DRAM_SOURCE = ("profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                         "launch (profiles/r2_v5_cfd16_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 51 MB of the 64 MB of fields, once")
 NCU_CFD_DRAM_SOURCE = ("profile constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
                        "launch (profiles/r2_v5_cfd_ncu.txt, cold L2 as ncu replays it): 16 MB of segment records + 29.5 MB of the 32 MB of fields, once")
 WORKLOAD = "cfg3: batched RRTStar, independent 512x512 value-noise worlds, n=5000, r_rewire=50"
@@ -351,20 +354,52 @@ def collision_microbench(local: int, steps: int, warmup: int, cpu: bool, sm_mhz:
     e1.record(stream)
     torch.cuda.synchronize(dev)
     ms_cfd = e0.elapsed_time(e1) / reps
-    out = {
-        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
-        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
-        "obstacle_fraction": float(db.og.float().mean().item()),
-        # the fastest of the three kernels carries the leg's headline numbers; each is listed with its own roofline object
-        "kernel": "rrtk::collision_cf_kernel (thread per segment on eight directional uint8 clearance fields, one per octant of the walk, cap %d; "
-                  "rrtk_clearance_field_dir + rrtk_collision_segments_cfd)" % cap8,
+    # the same with every octant split at slope 1/2: sixteen fields (16 bytes per cell), longer steps again
+    clear16 = torch.empty((16, CC_SIZE, CC_SIZE), dtype=torch.uint8, device=dev)
+    eb2, eb3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb2.record(stream)
+    _lib.check(L.rrtk_clearance_field_dir16(db.bits.data_ptr(), 1, CC_SIZE, CC_SIZE, cap8, clear16.data_ptr(), stream.cuda_stream), "clearance_field_dir16")
+    eb3.record(stream)
+    free4 = torch.empty_like(free)
+    cells4 = torch.empty_like(cells)
+
+    def launch_cfd16():
+        _lib.check(L.rrtk_collision_segments_cfd16(clear16.data_ptr(), CC_SIZE, CC_SIZE, segs.data_ptr(), None, CC_NSEG, free4.data_ptr(),
+                                                   cells4.data_ptr(), stream.cuda_stream), "collision_segments_cfd16")
+
+    for _ in range(max(3, warmup)):
+        launch_cfd16()
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for _ in range(reps):
+        launch_cfd16()
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms_cfd16 = e0.elapsed_time(e1) / reps
+    octants = {
+        "kernel": "rrtk::collision_cf_kernel on eight directional uint8 clearance fields, one per octant of the walk (rrtk_clearance_field_dir + "
+                  "rrtk_collision_segments_cfd), cap %d" % cap8,
         "segments_per_s": CC_NSEG / (ms_cfd / 1e3), "cells_per_s": ncells / (ms_cfd / 1e3), "ms_per_launch": ms_cfd, "gpu_launches": reps,
         "field_build_ms": eb0.elapsed_time(eb1), "field_bytes": 8 * CC_SIZE * CC_SIZE,
         "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free3) and torch.equal(cells, cells3)),
         "roofline": roof("rrtk::collision_cf_kernel", ms_cfd, NCU_CFD_DRAM_BYTES, NCU_CFD_DRAM_SOURCE),
+    }
+    out = {
+        "workload": "cfg2: %d random segments on one %dx%d bit-packed world (512 KB, L2-resident)" % (CC_NSEG, CC_SIZE, CC_SIZE),
+        "mean_cells_per_segment": ncells / CC_NSEG, "free_fraction": nfree / CC_NSEG,
+        "obstacle_fraction": float(db.og.float().mean().item()),
+        # the fastest of the kernels carries the leg's headline numbers; each is listed with its own roofline object
+        "kernel": "rrtk::collision_cf_kernel (thread per segment on sixteen directional uint8 clearance fields: the octants of the walk split at "
+                  "slope 1/2, cap %d; rrtk_clearance_field_dir16 + rrtk_collision_segments_cfd16)" % cap8,
+        "segments_per_s": CC_NSEG / (ms_cfd16 / 1e3), "cells_per_s": ncells / (ms_cfd16 / 1e3), "ms_per_launch": ms_cfd16, "gpu_launches": reps,
+        "field_build_ms": eb2.elapsed_time(eb3), "field_bytes": 16 * CC_SIZE * CC_SIZE,
+        "same_outputs_as_bit_grid_kernel": bool(torch.equal(free, free4) and torch.equal(cells, cells4)),
+        "roofline": roof("rrtk::collision_cf_kernel", ms_cfd16, NCU_CFD16_DRAM_BYTES, NCU_CFD16_DRAM_SOURCE),
         "note": "a clearance-field walk skips the cells the field proves free, so it reads far fewer bytes than the algorithmic 4 B x cells the "
-                "reference would test (about 5 scattered byte reads per segment here, 10 on the isotropic field); what bounds it is the rate of "
-                "scattered L1 reads (~1.08 cycles per lane-load per SM, scripts/micro/scatter.cu) and the slowest lane of each warp",
+                "reference would test (about 4 scattered byte reads per segment here, 5 on the eight octant fields, 10 on the isotropic field); "
+                "what bounds it is the rate of scattered L1 reads (~1.08 cycles per lane-load per SM, scripts/micro/scatter.cu) and the slowest "
+                "lane of each warp",
+        "octant_fields_kernel": octants,
         "isotropic_field_kernel": iso_field,
         "bit_grid_kernel": bit_grid,
         "shared_grid_kernel": shared_grid,

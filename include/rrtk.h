@@ -154,6 +154,14 @@ int rrtk_clearance_field_dir(const uint32_t *d_bits, int nworlds, int W, int H, 
 int rrtk_collision_segments_cfd(const uint8_t *d_clear8, int W, int H, const int32_t *d_segs, const int32_t *d_world,
                                 int64_t nseg, uint8_t *d_free, int32_t *d_cells, void *stream);
 
+/* The same with every octant split at slope 1/2 (sixteen fields per world, 16 bytes per cell): a walk whose minor / major
+ * ratio is at most 1/2 strays at most ceil(i / 2) cells sideways in i steps, a steeper one at least floor(i / 2), so each half
+ * has a narrower free cone and the walk takes longer steps again (cfg2: 3.9 reads per segment instead of 4.9).
+ *   field index = 2 * o + (2 * min(|dx|, |dy|) > max(|dx|, |dy|)),  o as above;   d_clear16[((w * 16 + f) * W + x) * H + y]. */
+int rrtk_clearance_field_dir16(const uint32_t *d_bits, int nworlds, int W, int H, int cap, uint8_t *d_clear16, void *stream);
+int rrtk_collision_segments_cfd16(const uint8_t *d_clear16, int W, int H, const int32_t *d_segs, const int32_t *d_world,
+                                  int64_t nseg, uint8_t *d_free, int32_t *d_cells, void *stream);
+
 /* ---- K2: RRT.near(points, x)[0] (rrt.py:131-155), batched, pinned tie rule (lowest index) ------- */
 /* d_pts: npts x (x, y) int32.  d_queries: nq x (x, y).  d_count (optional): query q only sees the
  * first d_count[q] points (the filled prefix of the tree); NULL = all npts.  d_idx[q] = nearest

@@ -71,6 +71,8 @@ SIGNATURES = {
     "rrtk_collision_segments_cf": (_i, [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "rrtk_clearance_field_dir": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "rrtk_collision_segments_cfd": (_i, [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "rrtk_clearance_field_dir16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "rrtk_collision_segments_cfd16": (_i, [_vp, _i, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "rrtk_nearest_batch": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rrtk_nearest_batch_f64": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "rrtk_within_batch": (_i, [_vp, _i, _vp, _vp, _i, _d, _i, _vp, _vp, _vp]),

@@ -33,6 +33,7 @@ int collision_launch(const uint32_t *, int, int, const int32_t *, const int32_t 
                      cudaStream_t);
 int clearance_launch(const uint32_t *, int, int, int, int, uint8_t *, uint32_t *, cudaStream_t);
 int clearance_dir_launch(const uint32_t *, int, int, int, int, uint8_t *, cudaStream_t);
+int clearance_dir16_launch(const uint32_t *, int, int, int, int, uint8_t *, cudaStream_t);
 int collision_cf_launch(const uint8_t *, int, int, const int32_t *, const int32_t *, int, int64_t, uint8_t *, int32_t *, int, cudaStream_t);
 int unpack_launch(const uint32_t *, int, int, int, uint8_t *, cudaStream_t);
 int inflate_launch(const uint32_t *, int, int, int, int, const int32_t *, int, uint32_t *, uint32_t *, cudaStream_t);
@@ -277,6 +278,25 @@ int rrtk_collision_segments_cfd(const uint8_t *d_clear8, int W, int H, const int
     DevInfo *d;
     RRTK_TRY(dev_info(&d));
     return collision_cf_launch(d_clear8, W, H, d_segs, d_world, 8, nseg, d_free, d_cells, d->sms, (cudaStream_t)stream);
+}
+
+int rrtk_clearance_field_dir16(const uint32_t *d_bits, int nworlds, int W, int H, int cap, uint8_t *d_clear16, void *stream)
+{
+    RRTK_REQUIRE(d_bits && d_clear16 && nworlds >= 0, "rrtk_clearance_field_dir16: null pointer or negative count");
+    RRTK_REQUIRE(cap >= 2 && cap <= 255, "rrtk_clearance_field_dir16: cap must be in [2, 255]");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    if (nworlds == 0) return RRTK_OK;
+    return clearance_dir16_launch(d_bits, nworlds, W, H, cap, d_clear16, (cudaStream_t)stream);
+}
+
+int rrtk_collision_segments_cfd16(const uint8_t *d_clear16, int W, int H, const int32_t *d_segs, const int32_t *d_world, int64_t nseg,
+                                  uint8_t *d_free, int32_t *d_cells, void *stream)
+{
+    RRTK_REQUIRE(nseg >= 0 && (nseg == 0 || (d_clear16 && d_segs && d_free)), "rrtk_collision_segments_cfd16: bad argument");
+    RRTK_TRY(check_grid_dims(W, H, 32768));
+    DevInfo *d;
+    RRTK_TRY(dev_info(&d));
+    return collision_cf_launch(d_clear16, W, H, d_segs, d_world, 16, nseg, d_free, d_cells, d->sms, (cudaStream_t)stream);
 }
 
 int rrtk_nearest_batch(const int32_t *d_pts, int npts, const int32_t *d_queries, const int32_t *d_count, int nq,

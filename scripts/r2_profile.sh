@@ -7,7 +7,9 @@ ncu --set full --clock-control none --import-source on -k "regex:plan_(grid|scan
     python bench.py --steps 1 --warmup 3 --plans $PLANS --plan-only > gpurun_out/${TAG}_plan_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:collision_cf -s 3 -c 1 -f -o gpurun_out/${TAG}_cf \
     python bench.py --collision-only --no-cpu > gpurun_out/${TAG}_cf_bench.log 2>&1
-# the same kernel on the eight directional fields: its launches come after the 13 on the isotropic field
+# the same kernel on the eight octant fields and on the sixteen half-octant fields: their launches come after the 13 / 26 on the fields before
+ncu --set full --clock-control none --import-source on -k regex:collision_cf -s 29 -c 1 -f -o gpurun_out/${TAG}_cfd16 \
+    python bench.py --collision-only --no-cpu > gpurun_out/${TAG}_cfd16_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:collision_cf -s 16 -c 1 -f -o gpurun_out/${TAG}_cfd \
     python bench.py --collision-only --no-cpu > gpurun_out/${TAG}_cfd_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:collision_global -s 3 -c 1 -f -o gpurun_out/${TAG}_cc \

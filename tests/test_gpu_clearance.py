@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-MODES = ["iso", "dir"]
+MODES = ["iso", "dir", "dir16"]
 
 
 def clearance_and_check(ogs, cap, segs, wid=None, mode="iso"):
@@ -28,10 +28,14 @@ def clearance_and_check(ogs, cap, segs, wid=None, mode="iso"):
         scratch = torch.empty((2 * nw * db.words,), dtype=torch.int32, device="cuda")
         _lib.check(db.L.rrtk_clearance_field(db.bits.data_ptr(), nw, W, H, cap, clear.data_ptr(), scratch.data_ptr(), st), "clearance_field")
         walk = db.L.rrtk_collision_segments_cf
-    else:
+    elif mode == "dir":
         clear = torch.full((nw, 8, W, H), 77, dtype=torch.uint8, device="cuda")
         _lib.check(db.L.rrtk_clearance_field_dir(db.bits.data_ptr(), nw, W, H, cap, clear.data_ptr(), st), "clearance_field_dir")
         walk = db.L.rrtk_collision_segments_cfd
+    else:
+        clear = torch.full((nw, 16, W, H), 77, dtype=torch.uint8, device="cuda")
+        _lib.check(db.L.rrtk_clearance_field_dir16(db.bits.data_ptr(), nw, W, H, cap, clear.data_ptr(), st), "clearance_field_dir16")
+        walk = db.L.rrtk_collision_segments_cfd16
     nseg = segs.shape[0]
     d_segs = torch.from_numpy(np.ascontiguousarray(segs, dtype=np.int32)).cuda()
     d_w = None if wid is None else torch.from_numpy(np.ascontiguousarray(wid, dtype=np.int32)).cuda()
@@ -82,6 +86,47 @@ def test_directional_fields_are_capped_cone_depths(shape, cap):
     clear, _, _ = clearance_and_check(og[None], cap, np.zeros((1, 4), dtype=np.int32), mode="dir")
     for octant in range(8):
         assert np.array_equal(clear[0, octant].astype(np.int64), cone_depth(og, cap, octant)), octant
+
+
+def half_cone_depths(og, cap, octant):
+    """The two fields of an octant split at slope 1/2, by definition (include/rrtk.h): low half A = 1 + min(B(+a), B(+a+b)),
+    B = 1 + A(+a); high half C = 1 + min(D(+a), D(+a+b)), D = 1 + C(+a+b); 0 on obstacles, capped, outside the grid free."""
+    xmajor, xpos, ypos = bool(octant & 4), bool(octant & 2), bool(octant & 1)
+    occ = (og != 0) if xmajor else (og != 0).T
+    smaj, smin = (xpos, ypos) if xmajor else (ypos, xpos)
+    occ = occ[::1 if smaj else -1, ::1 if smin else -1]
+    n0, n1 = occ.shape
+    A = np.full((n0 + 1, n1 + 1), cap, dtype=np.int64); B = A.copy(); C = A.copy(); D = A.copy()
+    for a in range(n0 - 1, -1, -1):
+        o = occ[a]
+        A[a, :n1] = np.where(o, 0, np.minimum(cap, 1 + np.minimum(B[a + 1, :n1], B[a + 1, 1:])))
+        B[a, :n1] = np.where(o, 0, np.minimum(cap, 1 + A[a + 1, :n1]))
+        C[a, :n1] = np.where(o, 0, np.minimum(cap, 1 + np.minimum(D[a + 1, :n1], D[a + 1, 1:])))
+        D[a, :n1] = np.where(o, 0, np.minimum(cap, 1 + C[a + 1, 1:]))
+    out = []
+    for F in (A, C):
+        F = F[:n0, :n1][::1 if smaj else -1, ::1 if smin else -1]
+        out.append(F if xmajor else F.T)
+    return out
+
+
+@pytest.mark.parametrize("shape,cap", [((64, 64), 9), ((43, 100), 16), ((33, 31), 40), ((1, 1), 5), ((1300, 70), 255), ((50, 2100), 200)])
+def test_half_octant_fields_are_capped_cone_depths(shape, cap):
+    rng = np.random.default_rng(shape[0] + cap + 1)
+    og = (rng.random(shape) < 0.01).astype(np.uint8)
+    clear, _, _ = clearance_and_check(og[None], cap, np.zeros((1, 4), dtype=np.int32), mode="dir16")
+    for octant in range(8):
+        low, high = half_cone_depths(og, cap, octant)
+        assert np.array_equal(clear[0, 2 * octant].astype(np.int64), low), octant
+        assert np.array_equal(clear[0, 2 * octant + 1].astype(np.int64), high), octant
+
+
+def test_half_octant_fields_dominate_the_octant_fields():
+    og = worlds.perlin_occupancygrid(200, 168, seed=3).astype(np.uint8)
+    d8, _, _ = clearance_and_check(og[None], 64, np.zeros((1, 4), dtype=np.int32), mode="dir")
+    d16, _, _ = clearance_and_check(og[None], 64, np.zeros((1, 4), dtype=np.int32), mode="dir16")
+    for octant in range(8):
+        assert (d16[0, 2 * octant] >= d8[0, octant]).all() and (d16[0, 2 * octant + 1] >= d8[0, octant]).all()
 
 
 def test_directional_fields_dominate_the_isotropic_field():

@@ -37,6 +37,13 @@ def test_cfg2_one_million_segments_against_the_oracle():
     free2.zero_(); cells2.zero_()
     _lib.check(db.L.rrtk_collision_segments_cfd(clear8.data_ptr(), S, S, d_segs.data_ptr(), None, nseg, free2.data_ptr(), cells2.data_ptr(), st))
     assert torch.equal(free, free2) and torch.equal(cells, cells2)
+    # and on the sixteen half-octant fields (64 MB)
+    clear16 = torch.empty((16, S, S), dtype=torch.uint8, device="cuda")
+    _lib.check(db.L.rrtk_clearance_field_dir16(db.bits.data_ptr(), 1, S, S, 255, clear16.data_ptr(), st))
+    free2.zero_(); cells2.zero_()
+    _lib.check(db.L.rrtk_collision_segments_cfd16(clear16.data_ptr(), S, S, d_segs.data_ptr(), None, nseg, free2.data_ptr(), cells2.data_ptr(), st))
+    assert torch.equal(free, free2) and torch.equal(cells, cells2)
+    del clear16
     # reversing a free segment keeps it free only if the reversed walk is free too: verdicts of both directions vs the oracle
     rev = np.ascontiguousarray(segs[: 1 << 17][:, [2, 3, 0, 1]])
     d_rev = torch.from_numpy(rev).cuda()
