@@ -13,6 +13,7 @@ RRTK_PLAN_IMPL=grid run synccheck "tests/test_gpu_parity.py" "test_plan_golden a
 RRTK_PLAN_IMPL=grid run memcheck "tests/test_gpu_parity.py" "test_plan_golden and not wide and not informed"
 run memcheck "tests/test_gpu_parity.py" "cfg3_batch_vs_oracle and star"
 run memcheck "tests/test_gpu_rewire.py tests/test_gpu_clearance.py" "informed_plans_bit_exact and 96x96 or directional or pipelined_worlds"
+run racecheck "tests/test_gpu_clearance.py" "fields_are_capped_cone_depths"
 run racecheck "tests/test_gpu_rewire.py" "96x96_n500 or 96x96_n600 or several_plans"
 run racecheck "tests/test_gpu_parity.py" "sample_stream or rejection_path"
 run synccheck "tests/test_gpu_rewire.py tests/test_gpu_parity.py" "96x96_n500 or 96x96_n600 or several_plans or (test_plan_golden and blobs)"
